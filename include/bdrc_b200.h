@@ -1,0 +1,191 @@
+/*
+ * bdrc_b200.h -- C ABI of libbdrc_b200.so: the B200 (sm_100a) page->text hot path of the
+ * BDRC OCR pipeline (buda-base/ocr-inference).
+ *
+ * The reference has no FFI of its own for this path: the native boundary is
+ * onnxruntime's InferenceSession.run_with_ort_values plus the numpy/cv2 calls around it
+ * (BDRC/inference.py:128-130,152-160,294,359-370).  Every entry point below replaces one
+ * such call site; the citation on each is the reference interface it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name
+ *     ends in _host; `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success or a BDRC_ERR_* code; the message is available
+ *     from bdrc_last_error(ctx).  Nothing throws, nothing is allocated behind the caller's
+ *     back: scratch memory is sized by the *_workspace_bytes() queries and passed in.
+ *   - one bdrc_ctx per GPU; a ctx is not thread-safe (the reference objects are not
+ *     either).
+ *   - there is NO CPU fallback: without a CUDA device bdrc_create fails.
+ */
+#ifndef BDRC_B200_H
+#define BDRC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDRC_OK 0
+#define BDRC_ERR_ARG 1
+#define BDRC_ERR_CUDA 2
+#define BDRC_ERR_UNSUPPORTED 3
+#define BDRC_ERR_WEIGHTS 4
+
+#define BDRC_MODEL_SEG_DLV3P_R34 1 /* DeepLabV3+/ResNet-34, PyTorch-LineInference.ipynb:L112-L469 */
+#define BDRC_MODEL_OCR_EASTER2 2   /* Easter2 1-D conv recogniser, SURVEY 8(a)-8 */
+
+#define BDRC_POST_SIGMOID 0 /* LineDetection.predict   BDRC/inference.py:170-183 */
+#define BDRC_POST_SOFTMAX 1 /* LayoutDetection.predict BDRC/inference.py:263-276 */
+
+#define BDRC_LAYOUT_TV 0 /* logits [L][T][V] */
+#define BDRC_LAYOUT_VT 1 /* logits [L][V][T] (what the reference's ONNX emits, inference.py:373-376) */
+
+typedef struct bdrc_ctx bdrc_ctx;
+typedef struct bdrc_model bdrc_model;
+
+/* ---- context -------------------------------------------------------------------------- */
+int bdrc_create(int device, bdrc_ctx** out);
+void bdrc_destroy(bdrc_ctx* ctx);
+const char* bdrc_last_error(bdrc_ctx* ctx);
+const char* bdrc_version(void);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t bdrc_launch_count(bdrc_ctx* ctx);
+/* conv engine: 0 = tcgen05/TMEM implicit GEMM (product path), 1 = SIMT (debug cross-check) */
+int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine);
+/* per-launch CUDA-event profile of the network kernels (bench.py roofline numbers) */
+int bdrc_profile_enable(bdrc_ctx* ctx, int on);
+int bdrc_profile_reset(bdrc_ctx* ctx);
+int bdrc_profile_count(bdrc_ctx* ctx);
+/* synchronises the recorded events; ms and flops are per launch, name is a static string */
+int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double* flops);
+
+/* ---- models: replaces ort.InferenceSession(path)  BDRC/inference.py:128-130, 294 ------- */
+/* blob_host: a "BDRCW1" weight container (see ocr_inference_b200/weights.py), fp32 OIHW
+ * tensors with BN already folded (the ONNX files the reference loads are folded too).
+ * n_out = number of segmentation classes, or the OCR vocabulary size V (blank included). */
+int bdrc_load_weights(bdrc_ctx* ctx, int model_kind, const void* blob_host, size_t blob_bytes,
+                      int n_out, bdrc_model** out);
+void bdrc_free_model(bdrc_model* m);
+
+/* ---- a-1: Detection._preprocess_image  BDRC/inference.py:132-139 ----------------------- */
+/* (utils.preprocess_image :741-778, tile_image :713-721, binarize :796-815, normalize :781-793)
+ * page: HWC u8 [H][W][3], already clamp-resized (bdrc_resize_bilinear_u8) if needed.
+ * Pads bottom/right with 255 to a multiple of `patch`, tiles row-major, per tile
+ * gray -> 51x51 Gaussian adaptive threshold (C=13, replicate border at TILE edges) and
+ * writes u8 {0,1} tiles [nty*ntx][patch][patch] (the three reference channels are
+ * identical, so one is stored).  nty = ceil(H/patch), ntx = ceil(W/patch). */
+int bdrc_seg_preprocess(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
+                        uint8_t* tiles, void* stream);
+/* torch-path tiling  utils.multi_image_collate_fn :1142-1172 (no binarise): pads with 255 and
+ * writes u8 RGB tiles [nty*ntx][patch][patch][3]; the /255 happens in the network stem. */
+int bdrc_seg_tile_rgb(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
+                      uint8_t* tiles, void* stream);
+
+/* ---- a-2: Detection._predict  BDRC/inference.py:152-160 -------------------------------- */
+/* tiles: u8 [N][512][512][cin], cin = 1 ({0,1} binarised, scale 1) or 3 (RGB, scale 1/255).
+ * logits: fp32 NCHW [N][C][512][512], like the ONNX "output". */
+size_t bdrc_seg_workspace_bytes(bdrc_model* m, int n_tiles);
+int bdrc_seg_forward(bdrc_ctx* ctx, bdrc_model* m, const uint8_t* tiles, int n_tiles, int cin,
+                     float* logits, void* workspace, size_t workspace_bytes, void* stream);
+/* same network, but stops at the 128x128 head output (fp32 [N][C][128][128]); the x4
+ * align_corners upsample is then fused into bdrc_seg_postprocess_lowres. */
+int bdrc_seg_forward_lowres(bdrc_ctx* ctx, bdrc_model* m, const uint8_t* tiles, int n_tiles,
+                            int cin, float* logits_lowres, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---- a-3: LineDetection.predict / LayoutDetection.predict post  inference.py:175-181 ---- */
+/* logits fp32 NCHW [nty*ntx][C][patch][patch] -> mask u8 [H0][W0][C] {0,255} (C=1: [H0][W0]).
+ * sigmoid(x) > thr (mode SIGMOID) or softmax_c(x) > thr (mode SOFTMAX), stitch row-major,
+ * crop the padding (Hc x Wc = clamped page size), and if (Hc,Wc) != (H0,W0) apply the
+ * reference's cv2.resize of the {0,1} map followed by astype(u8) truncation
+ * (inference.py:141-150,180): a pixel is 255 only if its bilinear value is exactly 1. */
+int bdrc_seg_postprocess(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C, int patch,
+                         int Hc, int Wc, int H0, int W0, int mode, float thr, uint8_t* mask,
+                         void* stream);
+/* fused x4 align_corners bilinear upsample (PyTorch-LineInference.ipynb:L465-L469) + the above */
+int bdrc_seg_postprocess_lowres(bdrc_ctx* ctx, const float* logits_lowres, int nty, int ntx,
+                                int C, int patch, int Hc, int Wc, int mode, float thr,
+                                uint8_t* mask, void* stream);
+/* torch-path post  inference.py:947-956: softmax -> stitch -> crop -> float bilinear
+ * (align_corners=False) to H0 x W0 -> > thr -> u8*255, planar [C][H0][W0]. */
+int bdrc_seg_postprocess_torch(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C,
+                               int patch, int Hc, int Wc, int H0, int W0, float thr,
+                               uint8_t* mask, void* stream);
+
+/* ---- resize / remap: cv2.resize, cv2.warpAffine, map_coordinates ----------------------- */
+/* cv2.resize(INTER_LINEAR) on u8, 11-bit fixed point (utils.py:457-494, inference.py:148) */
+int bdrc_resize_bilinear_u8(bdrc_ctx* ctx, const uint8_t* src, int Hs, int Ws, int C,
+                            uint8_t* dst, int Hd, int Wd, void* stream);
+/* F.interpolate(bilinear, align_corners=False) on u8->fp32 rounding as utils.resize_clamp
+ * :967-999 does (float result, then consumed as float/255 by the stem): writes fp32 */
+int bdrc_resize_bilinear_f32(bdrc_ctx* ctx, const uint8_t* src, int Hs, int Ws, int C,
+                             float* dst, int Hd, int Wd, void* stream);
+/* cv2.warpAffine(image, M, (W,H), INTER_LINEAR, borderValue=0)  line_detection.py:62-76.
+ * M is the 2x3 forward matrix from cv2.getRotationMatrix2D (row-major, 6 doubles, host). */
+int bdrc_warp_affine_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
+                        const double* M_host, uint8_t* dst, void* stream);
+/* bilinear remap with an explicit coordinate field (scipy.ndimage.map_coordinates order=1,
+ * mode='constant', cval=0; image_dewarping.py:66-72): coords fp32 [2][H][W] = (row, col). */
+int bdrc_remap_bilinear_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
+                           const float* coords, uint8_t* dst, void* stream);
+/* fused thin-plate-spline evaluate + bilinear sample (image_dewarping.py:55-72): ctrl_host
+ * [n][2] control points (row,col), params_host [(n+3)][2] solved spline parameters. */
+int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
+                      const double* ctrl_host, const double* params_host, int n_ctrl,
+                      uint8_t* dst, void* stream);
+
+/* ---- a-5: extract_line_images  BDRC/line_detection.py:330-359 --------------------------- */
+/* One call per attempt-set: for each line l the caller supplies the filled-contour mask as
+ * run-length spans (host cv2.drawContours is replaced by a device polygon fill from the
+ * contour points): poly_xy int32 [sum n_pts][2], poly_off int32 [L+1].  For line l the SE is
+ * kw[l] x kh[l] (cv2.getStructuringElement(MORPH_RECT,(k, int(k*kf))), anchor at centre).
+ * Output: crops packed back to back in `crops` (u8 HWC, 3 channels), crop_hw[l] = (h,w),
+ * crop_off[l] = byte offset.  Rows/cols where ANY channel is all-zero over the masked page are
+ * deleted (mask_n_crop :79-104). `crops_capacity` bytes available; returns BDRC_ERR_ARG if
+ * exceeded (crop_hw is still valid so the caller can retry). */
+size_t bdrc_extract_lines_workspace_bytes(int H, int W, int L);
+int bdrc_extract_lines(bdrc_ctx* ctx, const uint8_t* page, int H, int W, const int32_t* poly_xy,
+                       const int32_t* poly_off, int L, const int32_t* kw, const int32_t* kh,
+                       uint8_t* crops, size_t crops_capacity, int32_t* crop_hw,
+                       int64_t* crop_off, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ---- a-7: OCRInference._prepare_ocr_line  BDRC/inference.py:313-357 --------------------- */
+/* crops: L ragged HWC u8 (3 ch) images at byte offsets crop_off, sizes crop_hw (h,w).
+ * Per line: optional h x h white pre-pad left/right, aspect-preserving cv2 resize to fit
+ * Wt x Ht, centre pad with black, adaptive-threshold binarise, -> {-1,+1}.
+ * Output `lines`: bf16 [L][Wt][Cpad] time-major (image rows are channels, zero-padded from
+ * Ht to Cpad) -- the layout the recogniser's first conv consumes.  `lines_f32` (optional,
+ * may be NULL) receives the reference layout fp32 [L][Ht][Wt] for parity checks. */
+size_t bdrc_ocr_prepare_workspace_bytes(int L, int Ht, int Wt);
+int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* crop_hw,
+                           const int64_t* crop_off, int L, int Ht, int Wt, int pre_pad,
+                           int Cpad, void* lines_bf16, float* lines_f32, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ---- a-8: OCRInference._predict  BDRC/inference.py:359-370 ------------------------------ */
+/* lines: bf16 [L][Wt][Cpad] from bdrc_ocr_prepare_lines; logits fp32 [L][T][V] (T = Wt/4). */
+size_t bdrc_ocr_workspace_bytes(bdrc_model* m, int L, int Wt);
+int bdrc_ocr_forward(bdrc_ctx* ctx, bdrc_model* m, const void* lines_bf16, int L, int Wt,
+                     float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a-9: softmax + CTC greedy decode  BDRC/inference.py:372-384, 108-112 --------------- */
+/* per timestep argmax (ties -> lowest index, as np.argmax), collapse repeats, drop `blank`.
+ * ids int32 [L][T] (first lens[l] entries valid), lens int32 [L]. */
+int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout,
+                    int blank, int32_t* ids, int32_t* lens, void* stream);
+
+/* ---- test hook: one convolution through the implicit-GEMM engine ------------------------ */
+/* x bf16 NHWC [N][H][W][Cin]; w fp32 OIHW (host); bias fp32 (host, may be NULL); residual
+ * bf16 NHWC or NULL; y bf16 (or fp32 if out_fp32) NHWC [N][Ho][Wo][Cout]. */
+int bdrc_conv2d_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int Cin,
+                     const float* w_host, const float* bias_host, int Cout, int R, int S,
+                     int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                     const void* residual, int relu, int out_fp32, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDRC_B200_H */

@@ -1,0 +1,110 @@
+// Context management and the small C-ABI entry points that are not tied to one stage.
+#include "common.cuh"
+
+extern "C" {
+
+const char* bdrc_version(void) { return "bdrc_b200 0.1 (sm_100a)"; }
+
+int bdrc_create(int device, bdrc_ctx** out) {
+  if (!out) return BDRC_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    // No CPU fallback by design: the product path needs a B200.
+    return BDRC_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return BDRC_ERR_CUDA;
+  bdrc_ctx* ctx = new bdrc_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return BDRC_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    // the kernels are sm_100a-only (tcgen05/TMEM); refuse to run elsewhere
+    delete ctx;
+    return BDRC_ERR_UNSUPPORTED;
+  }
+  if (cudaMalloc(&ctx->d_errflag, sizeof(int)) != cudaSuccess) {
+    delete ctx;
+    return BDRC_ERR_CUDA;
+  }
+  cudaMemset(ctx->d_errflag, 0, sizeof(int));
+  *out = ctx;
+  return BDRC_OK;
+}
+
+void bdrc_destroy(bdrc_ctx* ctx) {
+  if (!ctx) return;
+  for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  if (ctx->d_errflag) cudaFree(ctx->d_errflag);
+  delete ctx;
+}
+
+const char* bdrc_last_error(bdrc_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+uint64_t bdrc_launch_count(bdrc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine) {
+  if (!ctx || engine < 0 || engine > 1) return BDRC_ERR_ARG;
+  ctx->conv_engine = engine;
+  return BDRC_OK;
+}
+
+int bdrc_profile_enable(bdrc_ctx* ctx, int on) {
+  if (!ctx) return BDRC_ERR_ARG;
+  ctx->profile = on != 0;
+  return BDRC_OK;
+}
+
+int bdrc_profile_reset(bdrc_ctx* ctx) {
+  if (!ctx) return BDRC_ERR_ARG;
+  ctx->prof_used = 0;
+  ctx->prof_name.clear();
+  ctx->prof_flops.clear();
+  return BDRC_OK;
+}
+
+int bdrc_profile_count(bdrc_ctx* ctx) { return ctx ? (int)(ctx->prof_used / 2) : 0; }
+
+int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double* flops) {
+  if (!ctx || i < 0 || (size_t)i * 2 + 1 >= ctx->prof_used + 1 || (size_t)i >= ctx->prof_name.size())
+    return BDRC_ERR_ARG;
+  cudaEvent_t e0 = ctx->prof_ev[2 * i], e1 = ctx->prof_ev[2 * i + 1];
+  BDRC_CUDA(ctx, cudaEventSynchronize(e1));
+  float t = 0.f;
+  BDRC_CUDA(ctx, cudaEventElapsedTime(&t, e0, e1));
+  if (name) *name = ctx->prof_name[i].c_str();
+  if (ms) *ms = t;
+  if (flops) *flops = ctx->prof_flops[i];
+  return BDRC_OK;
+}
+
+int bdrc_conv2d_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int Cin,
+                     const float* w_host, const float* bias_host, int Cout, int R, int S,
+                     int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                     const void* residual, int relu, int out_fp32, void* y, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  ConvWeights cw;
+  BDRC_TRY(conv_pack_weights(ctx, w_host, bias_host, Cout, Cin, R, S, &cw));
+  ConvArgs a;
+  a.in = reinterpret_cast<const bf16*>(x);
+  a.N = N; a.Hin = H; a.Win = W; a.in_ld = Cin; a.in_coff = 0;
+  a.stride_h = stride_h; a.stride_w = stride_w; a.pad_h = pad_h; a.pad_w = pad_w;
+  a.dil_h = dil_h; a.dil_w = dil_w;
+  a.Hout = (H + 2 * pad_h - dil_h * (R - 1) - 1) / stride_h + 1;
+  a.Wout = (W + 2 * pad_w - dil_w * (S - 1) - 1) / stride_w + 1;
+  a.residual = reinterpret_cast<const bf16*>(residual);
+  a.res_ld = Cout;
+  a.out = y; a.out_ld = Cout; a.out_coff = 0; a.out_fp32 = out_fp32; a.relu = relu;
+  int rc = conv_launch(ctx, "conv2d_test", cw, a, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  conv_free_weights(&cw);
+  if (rc) return rc;
+  if (e != cudaSuccess) return bdrc_fail(ctx, BDRC_ERR_CUDA, "conv2d_test: %s", cudaGetErrorString(e));
+  return BDRC_OK;
+}
+
+}  // extern "C"
