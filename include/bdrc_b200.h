@@ -78,20 +78,24 @@ void bdrc_free_model(bdrc_model* m);
  * identical, so one is stored).  nty = ceil(H/patch), ntx = ceil(W/patch). */
 int bdrc_seg_preprocess(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
                         uint8_t* tiles, void* stream);
-/* torch-path tiling  utils.multi_image_collate_fn :1142-1172 (no binarise): pads with 255 and
- * writes u8 RGB tiles [nty*ntx][patch][patch][3]; the /255 happens in the network stem. */
-int bdrc_seg_tile_rgb(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
-                      uint8_t* tiles, void* stream);
+/* torch-path collate  utils.multi_image_collate_fn :1142-1172 (no binarise): resize_clamp
+ * (F.interpolate bilinear, align_corners=False, to Hc x Wc; identity when equal) -> pad with 255
+ * to a multiple of `patch` -> row-major tiles fp32 [nty*ntx][patch][patch][3] with values in
+ * [0,255]; the /255 happens in the network stem. */
+int bdrc_seg_tile_rgb(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int Hc, int Wc, int patch,
+                      float* tiles, void* stream);
 
 /* ---- a-2: Detection._predict  BDRC/inference.py:152-160 -------------------------------- */
-/* tiles: u8 [N][512][512][cin], cin = 1 ({0,1} binarised, scale 1) or 3 (RGB, scale 1/255).
+/* tiles: cin = 1 -> u8 [N][512][512] with values {0,1} (bdrc_seg_preprocess);
+ *        cin = 3 -> fp32 [N][512][512][3] with values in [0,255] (bdrc_seg_tile_rgb), scaled by
+ *        1/255 in the stem.
  * logits: fp32 NCHW [N][C][512][512], like the ONNX "output". */
 size_t bdrc_seg_workspace_bytes(bdrc_model* m, int n_tiles);
-int bdrc_seg_forward(bdrc_ctx* ctx, bdrc_model* m, const uint8_t* tiles, int n_tiles, int cin,
+int bdrc_seg_forward(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n_tiles, int cin,
                      float* logits, void* workspace, size_t workspace_bytes, void* stream);
-/* same network, but stops at the 128x128 head output (fp32 [N][C][128][128]); the x4
+/* same network, but stops at the 128x128 head output (fp32 NHWC [N][128][128][C]); the x4
  * align_corners upsample is then fused into bdrc_seg_postprocess_lowres. */
-int bdrc_seg_forward_lowres(bdrc_ctx* ctx, bdrc_model* m, const uint8_t* tiles, int n_tiles,
+int bdrc_seg_forward_lowres(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n_tiles,
                             int cin, float* logits_lowres, void* workspace,
                             size_t workspace_bytes, void* stream);
 

@@ -32,7 +32,8 @@ _SIGS = {
     "bdrc_load_weights": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, C.POINTER(c_void_p)]),
     "bdrc_free_model": (None, [c_void_p]),
     "bdrc_seg_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "bdrc_seg_tile_rgb": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "bdrc_seg_tile_rgb": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p]),
     "bdrc_seg_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "bdrc_seg_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

@@ -41,7 +41,7 @@ conv_simt_kernel(const bf16* __restrict__ in, int N, int Hin, int Win, int in_ld
                  const bf16* __restrict__ w, int Cin, int Cin_pad, int R, int S, int Cout,
                  int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int Hout,
                  int Wout, const float* __restrict__ bias, int bias_img_stride,
-                 const bf16* __restrict__ residual, int res_ld, void* __restrict__ out, int out_ld,
+                 const bf16* residual, int res_ld, void* out, int out_ld,
                  int out_coff, int out_fp32, int relu) {
   const long long M = (long long)N * Hout * Wout;
   const long long pix = (long long)blockIdx.x * 64 + threadIdx.x;

@@ -306,8 +306,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           if (p.residual) {
             const bf16* rp = p.residual + pix * p.res_ld + n0 + c0;
             if (full16 && (p.res_ld & 7) == 0) {
-              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+              // plain loads: the residual may alias the output (in-place shortcut add)
+              const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
               const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {

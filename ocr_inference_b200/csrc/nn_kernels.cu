@@ -1,0 +1,388 @@
+// Memory-bound network kernels between the implicit-GEMM convolutions (see nn_kernels.cuh).
+// All activations are bf16 NHWC; arithmetic is fp32.
+#include "nn_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    f[2 * q] = __low2float(h[q]);
+    f[2 * q + 1] = __high2float(h[q]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem 7x7 s2 p3, Cout = 64.  CTA = 4 output rows x 64 output cols; thread = 4 px x 16 couts.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_TH = 4, ST_TW = 64;
+constexpr int ST_IR = ST_TH * 2 + 5;    // 13 input rows
+constexpr int ST_IC = ST_TW * 2 + 5;    // 133 input cols
+constexpr int ST_ICS = 136;             // padded stride
+
+template <int CIN, typename TIn>
+__global__ void __launch_bounds__(256)
+stem_kernel(const TIn* __restrict__ in, float in_div, int H, int W, const float* __restrict__ wp,
+            const float* __restrict__ bias, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) float st_smem[];
+  float* s_in = st_smem;                              // [ST_IR][CIN][ST_ICS]
+  float* s_w = st_smem + ST_IR * CIN * ST_ICS;        // [49*CIN][64]
+  const int Ho = H / 2, Wo = W / 2;
+  const int n = blockIdx.z, oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+  for (int i = threadIdx.x; i < 49 * CIN * 64 / 4; i += 256)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wp) + i);
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < ST_IR * ST_IC; i += 256) {
+    const int r = i / ST_IC, c = i - r * ST_IC;
+    const int iy = iy0 + r, ix = ix0 + c;
+    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+    for (int ch = 0; ch < CIN; ++ch) {
+      float v = 0.f;
+      if (ok) v = (float)in[(((size_t)n * H + iy) * W + ix) * CIN + ch] / in_div;
+      s_in[(r * CIN + ch) * ST_ICS + c] = v;
+    }
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 3, pg = threadIdx.x >> 2;
+  const int row = pg >> 4, col4 = (pg & 15) * 4;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < CIN; ++ch) {
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r) {
+      const float* ip = s_in + ((row * 2 + r) * CIN + ch) * ST_ICS + col4 * 2;
+      float x[13];
+#pragma unroll
+      for (int k = 0; k < 13; ++k) x[k] = ip[k];
+      const float* wr = s_w + ((ch * 7 + r) * 7) * 64 + cg * 16;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        float wv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(wr + s * 64 + q * 4);
+          wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(x[2 * i + s], wv[j], acc[i][j]);
+      }
+    }
+  }
+  const int oy = oy0 + row;
+  if (oy >= Ho) return;
+  float b[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) b[j] = __ldg(bias + cg * 16 + j);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = ox0 + col4 + i;
+    if (ox >= Wo) continue;
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(acc[i][j] + b[j], 0.f);
+    uint4* o = reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * 64 + cg * 16);
+    o[0] = pack8(f);
+    o[1] = pack8(f + 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(const bf16* __restrict__ in, int N, int H, int W, int C,
+                               bf16* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  size_t p = idx / C8;
+  const int ox = (int)(p % Wo); p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = oy * 2 + dy;
+    if (iy < 0 || iy >= H) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = ox * 2 + dx;
+      if (ix < 0 || ix >= W) continue;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * H + iy) * W + ix) * C + c8 * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * C + c8 * 8) = pack8(m);
+}
+
+__global__ void depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int H,
+                                 int W, int C, int dil, const float* __restrict__ w9c,
+                                 bf16* __restrict__ out, int out_ld, int out_coff) {
+  const int C8 = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * H * W * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  size_t p = idx / C8;
+  const int x = (int)(p % W); p /= W;
+  const int y = (int)(p % H);
+  const int n = (int)(p / H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = y + (r - 1) * dil;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = x + (s - 1) * dil;
+      if (ix < 0 || ix >= W) continue;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * H + iy) * W + ix) * in_ld + in_coff + c8 * 8)), f);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9c + (r * 3 + s) * C + c8 * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9c + (r * 3 + s) * C + c8 * 8 + 4));
+      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * out_ld + out_coff + c8 * 8) = pack8(acc);
+}
+
+// align_corners=True bilinear, fp32 math in torch's operand order (UpSampleBilinear2d)
+__global__ void upsample_ac_kernel(const bf16* __restrict__ in, int N, int H, int W, int C, int f,
+                                   bf16* __restrict__ out, int out_ld, int out_coff) {
+  const int Ho = H * f, Wo = W * f, C8 = C / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  size_t p = idx / C8;
+  const int x = (int)(p % Wo); p /= Wo;
+  const int y = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  const float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
+  const float fy = sy * (float)y, fx = sx * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const bf16* b = in + (size_t)n * H * W * C + c8 * 8;
+  float v00[8], v01[8], v10[8], v11[8], r[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x0) * C)), v00);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x1) * C)), v01);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x0) * C)), v10);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x1) * C)), v11);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    r[j] = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
+  *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + y) * Wo + x) * out_ld + out_coff + c8 * 8) = pack8(r);
+}
+
+__global__ void upsample_logits_kernel(const float* __restrict__ in, int N, int h, int w, int C,
+                                       float* __restrict__ out) {
+  const int Ho = h * 4, Wo = w * 4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * C * Ho * Wo;
+  if (idx >= total) return;
+  size_t p = idx;
+  const int x = (int)(p % Wo); p /= Wo;
+  const int y = (int)(p % Ho); p /= Ho;
+  const int c = (int)(p % C);
+  const int n = (int)(p / C);
+  const float sy = (float)(h - 1) / (float)(Ho - 1), sx = (float)(w - 1) / (float)(Wo - 1);
+  const float fy = sy * (float)y, fx = sx * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* b = in + (size_t)n * h * w * C + c;
+  out[idx] = ly0 * (lx0 * b[((size_t)y0 * w + x0) * C] + lx1 * b[((size_t)y0 * w + x1) * C]) +
+             ly1 * (lx0 * b[((size_t)y1 * w + x0) * C] + lx1 * b[((size_t)y1 * w + x1) * C]);
+}
+
+// one CTA per image: mean over HW -> 1x1 conv + ReLU -> tail of the projection conv
+__global__ void __launch_bounds__(256)
+aspp_pool_bias_kernel(const bf16* __restrict__ x, int HW, int Cin, const float* __restrict__ Wp,
+                      const float* __restrict__ bp, int Cmid, const float* __restrict__ Wtail,
+                      const float* __restrict__ bproj, int Cout, int Cout_pad,
+                      float* __restrict__ bias_eff) {
+  extern __shared__ float pb_smem[];
+  float* g = pb_smem;          // [Cin]
+  float* h = pb_smem + Cin;    // [Cmid]
+  const int n = blockIdx.x;
+  const bf16* xb = x + (size_t)n * HW * Cin;
+  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(xb[(size_t)p * Cin + c]);
+    g[c] = s / (float)HW;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < Cmid; o += nw) {
+    float s = 0.f;
+    for (int c = lane; c < Cin; c += 32) s = fmaf(Wp[(size_t)o * Cin + c], g[c], s);
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (lane == 0) h[o] = fmaxf(s + bp[o], 0.f);
+  }
+  __syncthreads();
+  for (int o = warp; o < Cout_pad; o += nw) {
+    float s = 0.f;
+    if (o < Cout) {
+      for (int c = lane; c < Cmid; c += 32) s = fmaf(Wtail[(size_t)o * Cmid + c], h[c], s);
+      for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+      s += bproj[o];
+    }
+    if (lane == 0) bias_eff[(size_t)n * Cout_pad + o] = s;
+  }
+}
+
+// one CTA per line: column mean over T, FC -> ReLU -> FC -> sigmoid
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const bf16* __restrict__ d, int T, int C, const float* __restrict__ W1,
+               const float* __restrict__ b1, int Cmid, const float* __restrict__ W2,
+               const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float se_smem[];
+  float* m = se_smem;        // [C]
+  float* z = se_smem + C;    // [Cmid]
+  const int l = blockIdx.x;
+  const bf16* db = d + (size_t)l * T * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += __bfloat162float(db[(size_t)t * C + c]);
+    m[c] = s / (float)T;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < Cmid; o += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(W1[(size_t)o * C + c], m[c], s);
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (lane == 0) z[o] = fmaxf(s + b1[o], 0.f);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    float s = b2[o];
+    for (int c = 0; c < Cmid; ++c) s = fmaf(W2[(size_t)o * Cmid + c], z[c], s);
+    gate[(size_t)l * C + o] = 1.f / (1.f + expf(-s));
+  }
+}
+
+__global__ void se_apply_kernel(const bf16* __restrict__ res, const bf16* __restrict__ d,
+                                const float* __restrict__ gate, int T, int C, size_t total8,
+                                bf16* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total8) return;
+  const int C8 = C / 8;
+  const int c8 = (int)(idx % C8);
+  const size_t row = idx / C8;          // l*T + t
+  const int l = (int)(row / T);
+  float r[8], dv[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(res) + idx), r);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(d) + idx), dv);
+  const float* gp = gate + (size_t)l * C + c8 * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(dv[j], gp[j], r[j]), 0.f);
+  reinterpret_cast<uint4*>(out)[idx] = pack8(o);
+}
+
+}  // namespace
+
+int stem_conv_launch(bdrc_ctx* ctx, const void* in, int cin, float in_div, int N, int H, int W,
+                     const float* w_packed, const float* bias, bf16* out, cudaStream_t s) {
+  BDRC_REQUIRE(ctx, (cin == 1 || cin == 3) && H % 2 == 0 && W % 2 == 0, "stem: cin must be 1 or 3");
+  dim3 grid(ceil_div(W / 2, ST_TW), ceil_div(H / 2, ST_TH), N);
+  const size_t smem = (size_t)(ST_IR * cin * ST_ICS + 49 * cin * 64) * sizeof(float);
+  if (cin == 1) {
+    auto k = stem_kernel<1, uint8_t>;
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, s>>>(reinterpret_cast<const uint8_t*>(in), in_div, H, W, w_packed, bias, out);
+  } else {
+    auto k = stem_kernel<3, float>;
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(in), in_div, H, W, w_packed, bias, out);
+  }
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int maxpool3x3s2_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, bf16* out,
+                        cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: C %% 8 != 0");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, H, W, C, out);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, int N, int H, int W,
+                        int C, int dil, const float* w9c, bf16* out, int out_ld, int out_coff,
+                        cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
+               "depthwise: channel counts must be multiples of 8");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  depthwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil,
+                                                                 w9c, out, out_ld, out_coff);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int upsample_bilinear_ac_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, int f,
+                                bf16* out, int out_ld, int out_coff, cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0, "upsample: C %% 8 != 0");
+  const size_t total = (size_t)N * H * f * W * f * (C / 8);
+  upsample_ac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, H, W, C, f, out, out_ld,
+                                                                   out_coff);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int upsample_logits_launch(bdrc_ctx* ctx, const float* in, int N, int h, int w, int C, float* out,
+                           cudaStream_t s) {
+  const size_t total = (size_t)N * C * h * 4 * w * 4;
+  upsample_logits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, h, w, C, out);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, const float* Wp,
+                          const float* bp, int Cmid, const float* Wtail, const float* bproj,
+                          int Cout, int Cout_pad, float* bias_eff, cudaStream_t s) {
+  aspp_pool_bias_kernel<<<N, 256, (size_t)(Cin + Cmid) * sizeof(float), s>>>(
+      x, HW, Cin, Wp, bp, Cmid, Wtail, bproj, Cout, Cout_pad, bias_eff);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
+                   const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
+                   cudaStream_t s) {
+  se_gate_kernel<<<L, 256, (size_t)(C + Cmid) * sizeof(float), s>>>(d, T, C, W1, b1, Cmid, W2, b2, gate);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* gate, int L, int T,
+                    int C, bf16* out, cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0, "se_apply: C %% 8 != 0");
+  const size_t total8 = (size_t)L * T * (C / 8);
+  se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(res, d, gate, T, C, total8, out);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}

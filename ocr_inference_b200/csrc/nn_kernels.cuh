@@ -1,0 +1,42 @@
+// Memory-bound network kernels that sit between the implicit-GEMM convolutions
+// (declarations; definitions in nn_kernels.cu).
+#pragma once
+#include "common.cuh"
+
+// Stem: conv 7x7 stride 2 pad 3 (+bias, ReLU), PyTorch-LineInference.ipynb:L233-L236.
+// in: u8 [N][H][W] (cin = 1, value * in_scale) or fp32 [N][H][W][3] (cin = 3, value * in_scale)
+// w: fp32 [49*cin][64] (tap-major), out: bf16 NHWC [N][H/2][W/2][64]
+int stem_conv_launch(bdrc_ctx* ctx, const void* in, int cin, float in_scale, int N, int H, int W,
+                     const float* w_packed, const float* bias, bf16* out, cudaStream_t s);
+
+// MaxPool 3x3 stride 2 pad 1 (ipynb:L237-L238), bf16 NHWC, C % 8 == 0
+int maxpool3x3s2_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, bf16* out,
+                        cudaStream_t s);
+
+// Depthwise 3x3, dilation d, pad d, no bias (ipynb:L411-L420, L445, L455).  w: fp32 [9][C]
+int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, int N, int H, int W,
+                        int C, int dil, const float* w9c, bf16* out, int out_ld, int out_coff,
+                        cudaStream_t s);
+
+// Bilinear upsample x`f`, align_corners=True (ipynb:L448-L452), bf16 NHWC -> bf16 NHWC slice
+int upsample_bilinear_ac_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, int f,
+                                bf16* out, int out_ld, int out_coff, cudaStream_t s);
+
+// Head upsample x4 align_corners=True: fp32 NHWC low-res [N][h][w][C] -> fp32 NCHW [N][C][4h][4w]
+int upsample_logits_launch(bdrc_ctx* ctx, const float* in, int N, int h, int w, int C, float* out,
+                           cudaStream_t s);
+
+// ASPP image-pooling branch folded into a per-tile bias of the projection conv
+// (ipynb:L421-L440; SURVEY a-2 note):
+//   g = mean_hw(x) [Cin]; h = relu(Wp g + bp) [Cmid]; bias_eff = b_proj + Wtail h  [Cout_pad]
+int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, const float* Wp,
+                          const float* bp, int Cmid, const float* Wtail, const float* bproj,
+                          int Cout, int Cout_pad, float* bias_eff, cudaStream_t s);
+
+// Easter2 squeeze-excite over time: gate = sigmoid(W2 relu(W1 mean_T(d) + b1) + b2)
+int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
+                   const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
+                   cudaStream_t s);
+// data = relu(res + d * gate)
+int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* gate, int L, int T,
+                    int C, bf16* out, cudaStream_t s);

@@ -1,0 +1,535 @@
+// HBM-bound pre/post-processing stages of the page->text path (everything around the two
+// networks): tiling + adaptive-threshold binarisation, mask thresholding / stitching / resize,
+// cv2-exact bilinear resize, OCR line preparation and greedy CTC decode.
+#include "adaptive.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// cv2.resize(INTER_LINEAR) coordinate tables, computed on the fly exactly as OpenCV does:
+//   scale = 1.0 / ((double)dsize / ssize);  fx = (float)((d + 0.5) * scale - 0.5);
+//   sx = floor(fx); fx -= sx; horizontal: fold out-of-range taps; vertical: clip index only.
+// (oracle/hostops.py:_linear_coefs)
+// ------------------------------------------------------------------------------------------
+struct LinCoef {
+  int i0, i1;
+  float w0, w1;
+};
+
+__device__ __forceinline__ LinCoef lin_coef(int d, int ssize, int dsize, bool vertical) {
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  int sx = (int)floorf(fx);
+  fx = fx - (float)sx;
+  if (!vertical) {
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= ssize - 1) { fx = 0.f; sx = ssize - 1; }
+  }
+  LinCoef c;
+  c.i0 = min(max(sx, 0), ssize - 1);
+  c.i1 = min(max(sx + 1, 0), ssize - 1);
+  c.w0 = 1.0f - fx;
+  c.w1 = fx;
+  return c;
+}
+
+__device__ __forceinline__ int fix11(float w) { return __float2int_rn(w * 2048.0f); }
+
+// one output sample of the 11-bit fixed-point bilinear (VResizeLinear 8u SIMD formula)
+__device__ __forceinline__ int resize_fix_sample(int s00, int s01, int s10, int s11, int a0, int a1,
+                                                 int b0, int b1) {
+  const int r0 = s00 * a0 + s01 * a1;
+  const int r1 = s10 * a0 + s11 * a1;
+  int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+  return min(max(v, 0), 255);
+}
+
+__global__ void resize_u8_kernel(const uint8_t* __restrict__ src, int Hs, int Ws, int C,
+                                 uint8_t* __restrict__ dst, int Hd, int Wd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= Wd) return;
+  uint8_t* o = dst + ((size_t)y * Wd + x) * C;
+  if (Hs == Hd && Ws == Wd) {
+    for (int c = 0; c < C; ++c) o[c] = src[((size_t)y * Ws + x) * C + c];
+    return;
+  }
+  if (Ws == 2 * Wd && Hs == 2 * Hd) {   // cv2's INTER_AREA fast path for exact 1/2 scaling
+    const uint8_t* p = src + ((size_t)(2 * y) * Ws + 2 * x) * C;
+    for (int c = 0; c < C; ++c)
+      o[c] = (uint8_t)((p[c] + p[C + c] + p[(size_t)Ws * C + c] + p[(size_t)Ws * C + C + c] + 2) >> 2);
+    return;
+  }
+  const LinCoef cx = lin_coef(x, Ws, Wd, false), cy = lin_coef(y, Hs, Hd, true);
+  const int a0 = fix11(cx.w0), a1 = fix11(cx.w1), b0 = fix11(cy.w0), b1 = fix11(cy.w1);
+  const uint8_t* r0 = src + (size_t)cy.i0 * Ws * C;
+  const uint8_t* r1 = src + (size_t)cy.i1 * Ws * C;
+  for (int c = 0; c < C; ++c)
+    o[c] = (uint8_t)resize_fix_sample(r0[cx.i0 * C + c], r0[cx.i1 * C + c], r1[cx.i0 * C + c],
+                                      r1[cx.i1 * C + c], a0, a1, b0, b1);
+}
+
+// torch F.interpolate(bilinear, align_corners=False) u8 -> fp32 (utils.resize_clamp :990-996)
+__global__ void resize_f32_kernel(const uint8_t* __restrict__ src, int Hs, int Ws, int C,
+                                  float* __restrict__ dst, int Hd, int Wd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= Wd) return;
+  const float sy = (float)Hs / (float)Hd, sx = (float)Ws / (float)Wd;
+  float fy = sy * ((float)y + 0.5f) - 0.5f;
+  float fx = sx * ((float)x + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  for (int c = 0; c < C; ++c) {
+    const float v00 = src[((size_t)y0 * Ws + x0) * C + c], v01 = src[((size_t)y0 * Ws + x1) * C + c];
+    const float v10 = src[((size_t)y1 * Ws + x0) * C + c], v11 = src[((size_t)y1 * Ws + x1) * C + c];
+    dst[((size_t)y * Wd + x) * C + c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// torch-path collate (utils.resize_clamp / pad_to_multiple / tile_timage :967-1023): float
+// bilinear (align_corners=False) resize, pad 255, RGB fp32 tiles with values in [0,255]
+// ------------------------------------------------------------------------------------------
+__global__ void tile_rgb_kernel(const uint8_t* __restrict__ page, int H, int W, int Hc, int Wc,
+                                int patch, int ntx, float* __restrict__ tiles) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;   // pixel column inside the tile
+  const int y = blockIdx.y;                                // tile row
+  const int t = blockIdx.z;                                // tile
+  if (x >= patch) return;
+  const int ty = t / ntx, tx = t - ty * ntx;
+  const int py = ty * patch + y, px = tx * patch + x;
+  float* o = tiles + (((size_t)t * patch + y) * patch + x) * 3;
+  if (py >= Hc || px >= Wc) { o[0] = o[1] = o[2] = 255.f; return; }
+  if (Hc == H && Wc == W) {
+    const uint8_t* p = page + ((size_t)py * W + px) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    return;
+  }
+  const float sy = (float)H / (float)Hc, sx = (float)W / (float)Wc;
+  float fy = sy * ((float)py + 0.5f) - 0.5f, fx = sx * ((float)px + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  for (int c = 0; c < 3; ++c) {
+    const float v00 = page[((size_t)y0 * W + x0) * 3 + c], v01 = page[((size_t)y0 * W + x1) * 3 + c];
+    const float v10 = page[((size_t)y1 * W + x0) * 3 + c], v11 = page[((size_t)y1 * W + x1) * 3 + c];
+    o[c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a-3 mask thresholding
+// ------------------------------------------------------------------------------------------
+struct PostParams {
+  const float* logits;   // [nt][C][P][P]  (or low-res [nt][C][P/4][P/4])
+  int ntx, C, P, lowres;
+  int Hc, Wc, H0, W0;
+  int mode;
+  float thr, thr_logit;
+  uint8_t* mask;         // [H0][W0][C]
+};
+
+// logit at padded-page pixel (py, px) for class c
+__device__ __forceinline__ float logit_at(const PostParams& p, int py, int px, int c) {
+  const int ty = py / p.P, tx = px / p.P;
+  const int y = py - ty * p.P, x = px - tx * p.P;
+  const int t = ty * p.ntx + tx;
+  if (!p.lowres) return p.logits[(((size_t)t * p.C + c) * p.P + y) * p.P + x];
+  // x4 bilinear, align_corners=True, fp32 like torch upsample_bilinear2d
+  const int L = p.P / 4;
+  const float sc = (float)(L - 1) / (float)(p.P - 1);
+  const float fy = sc * (float)y, fx = sc * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < L - 1 ? 1 : 0), x1 = x0 + (x0 < L - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float* b = p.logits + (size_t)t * L * L * p.C + c;   // low-res logits are NHWC
+  return ly0 * (lx0 * b[(y0 * L + x0) * p.C] + lx1 * b[(y0 * L + x1) * p.C]) +
+         ly1 * (lx0 * b[(y1 * L + x0) * p.C] + lx1 * b[(y1 * L + x1) * p.C]);
+}
+
+// {0,1} decisions for all classes of one padded-page pixel (bit c of the result)
+__device__ __forceinline__ uint32_t decide(const PostParams& p, int py, int px) {
+  if (p.mode == BDRC_POST_SIGMOID) {
+    uint32_t m = 0;
+    for (int c = 0; c < p.C; ++c) m |= (logit_at(p, py, px, c) >= p.thr_logit ? 1u : 0u) << c;
+    return m;
+  }
+  // softmax over classes in fp32, as scipy.special.softmax on the fp32 array (inference.py:269)
+  float v[32];
+  float mx = -INFINITY;
+  for (int c = 0; c < p.C; ++c) { v[c] = logit_at(p, py, px, c); mx = fmaxf(mx, v[c]); }
+  float s = 0.f;
+  for (int c = 0; c < p.C; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
+  uint32_t m = 0;
+  for (int c = 0; c < p.C; ++c) m |= ((v[c] / s) > p.thr ? 1u : 0u) << c;
+  return m;
+}
+
+__global__ void seg_post_kernel(const PostParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= p.W0) return;
+  uint32_t m;
+  if (p.Hc == p.H0 && p.Wc == p.W0) {
+    m = decide(p, y, x);
+  } else {
+    // cv2.resize of the float64 {0,1} map then astype(u8): 1 only where the double-precision
+    // bilinear value reaches 1.0 (inference.py:148,180; oracle resize_linear_f64)
+    const LinCoef cx = lin_coef(x, p.Wc, p.W0, false), cy = lin_coef(y, p.Hc, p.H0, true);
+    const uint32_t m00 = decide(p, cy.i0, cx.i0), m01 = decide(p, cy.i0, cx.i1);
+    const uint32_t m10 = decide(p, cy.i1, cx.i0), m11 = decide(p, cy.i1, cx.i1);
+    m = 0;
+    for (int c = 0; c < p.C; ++c) {
+      const double r0 = (double)((m00 >> c) & 1) * (double)cx.w0 + (double)((m01 >> c) & 1) * (double)cx.w1;
+      const double r1 = (double)((m10 >> c) & 1) * (double)cx.w0 + (double)((m11 >> c) & 1) * (double)cx.w1;
+      const double v = r0 * (double)cy.w0 + r1 * (double)cy.w1;
+      m |= (v >= 1.0 ? 1u : 0u) << c;
+    }
+  }
+  uint8_t* o = p.mask + ((size_t)y * p.W0 + x) * p.C;
+  for (int c = 0; c < p.C; ++c) o[c] = ((m >> c) & 1) ? 255 : 0;
+}
+
+// fast path: sigmoid, one class, full-res logits, no resize: 4 pixels per thread
+__global__ void seg_post_line_fast_kernel(const float* __restrict__ logits, int ntx, int P, int H0,
+                                          int W0, float thr_logit, uint8_t* __restrict__ mask) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x4 >= W0) return;
+  const int ty = y / P, tx = x4 / P;
+  const float* src = logits + (((size_t)(ty * ntx + tx)) * P + (y - ty * P)) * P + (x4 - tx * P);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+  uint8_t r[4] = {(uint8_t)(v.x >= thr_logit ? 255 : 0), (uint8_t)(v.y >= thr_logit ? 255 : 0),
+                  (uint8_t)(v.z >= thr_logit ? 255 : 0), (uint8_t)(v.w >= thr_logit ? 255 : 0)};
+  uint8_t* o = mask + (size_t)y * W0 + x4;
+  if (x4 + 3 < W0 && (W0 & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(r);
+  } else {
+    for (int j = 0; j < 4 && x4 + j < W0; ++j) o[j] = r[j];
+  }
+}
+
+// torch-path post (inference.py:947-956): softmax -> (stitch, crop) -> float bilinear
+// align_corners=False to H0 x W0 -> > thr -> planar u8 [C][H0][W0]
+__global__ void seg_post_torch_kernel(const PostParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= p.W0) return;
+  float prob[4][32];
+  int ys[2], xs[2];
+  float ly1 = 0.f, lx1 = 0.f;
+  if (p.Hc == p.H0 && p.Wc == p.W0) {
+    ys[0] = ys[1] = y; xs[0] = xs[1] = x;
+  } else {
+    const float sy = (float)p.Hc / (float)p.H0, sx = (float)p.Wc / (float)p.W0;
+    float fy = sy * ((float)y + 0.5f) - 0.5f, fx = sx * ((float)x + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+    ys[0] = (int)fy; xs[0] = (int)fx;
+    ys[1] = ys[0] + (ys[0] < p.Hc - 1 ? 1 : 0); xs[1] = xs[0] + (xs[0] < p.Wc - 1 ? 1 : 0);
+    ly1 = fy - (float)ys[0]; lx1 = fx - (float)xs[0];
+  }
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      float* v = prob[a * 2 + b];
+      float mx = -INFINITY;
+      for (int c = 0; c < p.C; ++c) { v[c] = logit_at(p, ys[a], xs[b], c); mx = fmaxf(mx, v[c]); }
+      float s = 0.f;
+      for (int c = 0; c < p.C; ++c) { v[c] = expf(v[c] - mx); s += v[c]; }
+      for (int c = 0; c < p.C; ++c) v[c] = v[c] / s;
+    }
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  for (int c = 0; c < p.C; ++c) {
+    const float v = ly0 * (lx0 * prob[0][c] + lx1 * prob[1][c]) + ly1 * (lx0 * prob[2][c] + lx1 * prob[3][c]);
+    p.mask[((size_t)c * p.H0 + y) * p.W0 + x] = v > p.thr ? 255 : 0;
+  }
+}
+
+// smallest fp32 logit whose fp32 sigmoid exceeds fp32(thr): the reference predicate
+// sigmoid(x) > thr (utils.py:563-573, inference.py:177) moved to the logit domain.
+float sigmoid_logit_threshold(float thr) {
+  auto pred = [thr](float x) { return 1.0f / (1.0f + expf(-x)) > thr; };
+  float lo = -30.f, hi = 30.f;
+  if (pred(lo)) return -INFINITY;
+  if (!pred(hi)) return INFINITY;
+  for (;;) {
+    const float mid = (float)(((double)lo + (double)hi) / 2.0);
+    if (mid == lo || mid == hi) break;
+    if (pred(mid)) hi = mid; else lo = mid;
+  }
+  return hi;
+}
+
+// ------------------------------------------------------------------------------------------
+// a-7 OCR line preparation, stage 1: (pre-pad) + aspect-preserving cv2 resize + black padding
+// + gray, written as a u8 gray canvas [L][Ht][Wt]
+// ------------------------------------------------------------------------------------------
+__global__ void ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__ hw,
+                                  const int64_t* __restrict__ off, int Ht, int Wt, int pre_pad,
+                                  uint8_t* __restrict__ canvas, int* __restrict__ status) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int l = blockIdx.z;
+  if (x >= Wt) return;
+  const int h = hw[2 * l], w0 = hw[2 * l + 1];
+  const int w = pre_pad ? w0 + 2 * h : w0;     // _pre_pad hstacks an h x h white patch each side
+  uint8_t g = 0;
+  if (h > 0 && w0 > 0) {
+    // geometry of _pad_ocr_line / pad_to_width / pad_to_height in Python float (double) math
+    const double wr = (double)Wt / (double)w, hr = (double)Ht / (double)h;
+    int rh, rw, top, left;
+    if (wr <= hr) { rw = Wt; rh = (int)((double)h * wr); top = (Ht - rh) / 2; left = 0; }
+    else { rh = Ht; rw = (int)((double)w * hr); top = 0; left = (Wt - rw) / 2; }
+    if (rh <= 0 || rw <= 0) {
+      if (x == 0 && y == 0) status[l] = 1;   // cv2.resize would raise on an empty target
+    } else if (y >= top && y < top + rh && x >= left && x < left + rw) {
+      const int dy = y - top, dx = x - left;
+      const uint8_t* base = crops + off[l];
+      int px[3];
+      auto fetch = [&](int sy, int sx, int* out3) {
+        if (pre_pad && (sx < h || sx >= h + w0)) { out3[0] = out3[1] = out3[2] = 255; return; }
+        const uint8_t* p = base + ((size_t)sy * w0 + (pre_pad ? sx - h : sx)) * 3;
+        out3[0] = p[0]; out3[1] = p[1]; out3[2] = p[2];
+      };
+      if (rh == h && rw == w) {
+        fetch(dy, dx, px);
+      } else if (w == 2 * rw && h == 2 * rh) {
+        int a[3], b[3], c[3], d[3];
+        fetch(2 * dy, 2 * dx, a); fetch(2 * dy, 2 * dx + 1, b);
+        fetch(2 * dy + 1, 2 * dx, c); fetch(2 * dy + 1, 2 * dx + 1, d);
+        for (int k = 0; k < 3; ++k) px[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
+      } else {
+        const LinCoef cx = lin_coef(dx, w, rw, false), cy = lin_coef(dy, h, rh, true);
+        const int a0 = fix11(cx.w0), a1 = fix11(cx.w1), b0 = fix11(cy.w0), b1 = fix11(cy.w1);
+        int s00[3], s01[3], s10[3], s11[3];
+        fetch(cy.i0, cx.i0, s00); fetch(cy.i0, cx.i1, s01);
+        fetch(cy.i1, cx.i0, s10); fetch(cy.i1, cx.i1, s11);
+        for (int k = 0; k < 3; ++k) px[k] = resize_fix_sample(s00[k], s01[k], s10[k], s11[k], a0, a1, b0, b1);
+      }
+      g = (uint8_t)((px[0] * 9798 + px[1] * 19235 + px[2] * 3735 + 16384) >> 15);
+    }
+  }
+  canvas[((size_t)l * Ht + y) * Wt + x] = g;
+}
+
+// ------------------------------------------------------------------------------------------
+// a-9 greedy CTC: argmax (first max wins, NaN counts as max like np.argmax) + collapse + drop blank
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  // true if (v, i) should replace (bv, bi): larger value, NaN beats numbers, ties -> lower index
+  const bool vn = isnan(v), bn = isnan(bv);
+  if (vn != bn) return vn;
+  if (vn && bn) return i < bi;
+  return v > bv || (v == bv && i < bi);
+}
+
+__global__ void __launch_bounds__(512)
+ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, int blank,
+                  int32_t* __restrict__ ids, int32_t* __restrict__ lens) {
+  extern __shared__ int sm[];
+  int* am = sm;            // [T] argmax per step
+  int* scan = sm + T;      // [T] keep flags / prefix sums
+  const int l = blockIdx.x;
+  const float* base = logits + (size_t)l * V * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  if (layout == BDRC_LAYOUT_TV) {
+    for (int t = warp; t < T; t += nwarp) {
+      const float* row = base + (size_t)t * V;
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int v = lane; v < V; v += 32) {
+        const float x = row[v];
+        if (bi == 0x7fffffff || better(x, v, bv, bi)) { bv = x; bi = v; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) am[t] = bi;
+    }
+  } else {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      float bv = base[t]; int bi = 0;
+      for (int v = 1; v < V; ++v) {
+        const float x = base[(size_t)v * T + t];
+        if (better(x, v, bv, bi)) { bv = x; bi = v; }
+      }
+      am[t] = bi;
+    }
+  }
+  __syncthreads();
+  // keep[t] = id != blank && (t == 0 || id != prev); exclusive scan by one warp-per-chunk pass
+  for (int t = threadIdx.x; t < T; t += blockDim.x)
+    scan[t] = (am[t] != blank && (t == 0 || am[t] != am[t - 1])) ? 1 : 0;
+  __syncthreads();
+  if (warp == 0) {
+    int carry = 0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+      const int t = t0 + lane;
+      const int k = t < T ? scan[t] : 0;
+      int incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      if (t < T && k) ids[(size_t)l * T + carry + incl - 1] = am[t];
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) lens[l] = carry;
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int bdrc_seg_preprocess(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
+                        uint8_t* tiles, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, page && tiles && H > 0 && W > 0 && patch > 0 && patch % 64 == 0,
+               "seg_preprocess: bad arguments (H=%d W=%d patch=%d)", H, W, patch);
+  const int nty = ceil_div(H, patch), ntx = ceil_div(W, patch);
+  adaptive::SrcPageTiles src{page, H, W, ntx, patch};
+  adaptive::SinkTiles01 sink{tiles, patch, patch};
+  return adaptive::launch(ctx, src, sink, nty * ntx, patch, patch, (cudaStream_t)stream);
+}
+
+int bdrc_seg_tile_rgb(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int Hc, int Wc, int patch,
+                      float* tiles, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, page && tiles && H > 0 && W > 0 && Hc > 0 && Wc > 0 && patch > 0,
+               "seg_tile_rgb: bad arguments");
+  const int nty = ceil_div(Hc, patch), ntx = ceil_div(Wc, patch);
+  dim3 grid(ceil_div(patch, 128), patch, nty * ntx);
+  tile_rgb_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(page, H, W, Hc, Wc, patch, ntx, tiles);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+static int seg_post_common(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C, int patch,
+                           int lowres, int Hc, int Wc, int H0, int W0, int mode, float thr,
+                           uint8_t* mask, int torch_path, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, logits && mask && C >= 1 && C <= 32 && nty > 0 && ntx > 0,
+               "seg_postprocess: bad arguments (C=%d)", C);
+  BDRC_REQUIRE(ctx, Hc <= nty * patch && Wc <= ntx * patch && Hc > (nty - 1) * patch &&
+                        Wc > (ntx - 1) * patch && H0 > 0 && W0 > 0,
+               "seg_postprocess: cropped size %dx%d inconsistent with %dx%d tiles", Hc, Wc, nty, ntx);
+  PostParams p;
+  p.logits = logits; p.ntx = ntx; p.C = C; p.P = patch; p.lowres = lowres;
+  p.Hc = Hc; p.Wc = Wc; p.H0 = H0; p.W0 = W0; p.mode = mode; p.thr = thr;
+  p.thr_logit = sigmoid_logit_threshold(thr);
+  p.mask = mask;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (torch_path) {
+    dim3 grid(ceil_div(W0, 128), H0);
+    seg_post_torch_kernel<<<grid, 128, 0, s>>>(p);
+  } else if (mode == BDRC_POST_SIGMOID && C == 1 && !lowres && Hc == H0 && Wc == W0 &&
+             patch % 4 == 0) {
+    dim3 grid(ceil_div(ceil_div(W0, 4), 128), H0);
+    seg_post_line_fast_kernel<<<grid, 128, 0, s>>>(logits, ntx, patch, H0, W0, p.thr_logit, mask);
+  } else {
+    dim3 grid(ceil_div(W0, 128), H0);
+    seg_post_kernel<<<grid, 128, 0, s>>>(p);
+  }
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int bdrc_seg_postprocess(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C, int patch,
+                         int Hc, int Wc, int H0, int W0, int mode, float thr, uint8_t* mask,
+                         void* stream) {
+  return seg_post_common(ctx, logits, nty, ntx, C, patch, 0, Hc, Wc, H0, W0, mode, thr, mask, 0, stream);
+}
+
+int bdrc_seg_postprocess_lowres(bdrc_ctx* ctx, const float* logits_lowres, int nty, int ntx, int C,
+                                int patch, int Hc, int Wc, int mode, float thr, uint8_t* mask,
+                                void* stream) {
+  return seg_post_common(ctx, logits_lowres, nty, ntx, C, patch, 1, Hc, Wc, Hc, Wc, mode, thr, mask, 0,
+                         stream);
+}
+
+int bdrc_seg_postprocess_torch(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C, int patch,
+                               int Hc, int Wc, int H0, int W0, float thr, uint8_t* mask,
+                               void* stream) {
+  return seg_post_common(ctx, logits, nty, ntx, C, patch, 0, Hc, Wc, H0, W0, BDRC_POST_SOFTMAX, thr,
+                         mask, 1, stream);
+}
+
+int bdrc_resize_bilinear_u8(bdrc_ctx* ctx, const uint8_t* src, int Hs, int Ws, int C, uint8_t* dst,
+                            int Hd, int Wd, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, src && dst && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0 && C > 0 && C <= 8,
+               "resize_bilinear_u8: bad arguments");
+  dim3 grid(ceil_div(Wd, 128), Hd);
+  resize_u8_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, Hs, Ws, C, dst, Hd, Wd);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int bdrc_resize_bilinear_f32(bdrc_ctx* ctx, const uint8_t* src, int Hs, int Ws, int C, float* dst,
+                             int Hd, int Wd, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, src && dst && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0 && C > 0,
+               "resize_bilinear_f32: bad arguments");
+  dim3 grid(ceil_div(Wd, 128), Hd);
+  resize_f32_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(src, Hs, Ws, C, dst, Hd, Wd);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+size_t bdrc_ocr_prepare_workspace_bytes(int L, int Ht, int Wt) {
+  return align_up((size_t)L * Ht * Wt, 256) + align_up((size_t)L * sizeof(int), 256);
+}
+
+int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* crop_hw,
+                           const int64_t* crop_off, int L, int Ht, int Wt, int pre_pad, int Cpad,
+                           void* lines_bf16, float* lines_f32, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  if (L == 0) return 0;
+  BDRC_REQUIRE(ctx, crops && crop_hw && crop_off && L > 0 && Ht > 0 && Wt > 0 && Cpad >= Ht,
+               "ocr_prepare_lines: bad arguments");
+  BDRC_REQUIRE(ctx, workspace && workspace_bytes >= bdrc_ocr_prepare_workspace_bytes(L, Ht, Wt),
+               "ocr_prepare_lines: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* canvas = reinterpret_cast<uint8_t*>(workspace);
+  int* status = reinterpret_cast<int*>(canvas + align_up((size_t)L * Ht * Wt, 256));
+  BDRC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)L * sizeof(int), s));
+  dim3 grid(ceil_div(Wt, 128), Ht, L);
+  ocr_canvas_kernel<<<grid, 128, 0, s>>>(crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status);
+  BDRC_CHECK_LAUNCH(ctx);
+  if (lines_bf16 && Cpad > Ht)   // zero the padding channels Ht..Cpad-1
+    BDRC_CUDA(ctx, cudaMemsetAsync(lines_bf16, 0, (size_t)L * Wt * Cpad * sizeof(bf16), s));
+  adaptive::SrcGrayBatch src{canvas, Ht, Wt};
+  adaptive::SinkOcrLines sink{reinterpret_cast<bf16*>(lines_bf16), lines_f32, Ht, Wt, Cpad};
+  return adaptive::launch(ctx, src, sink, L, Ht, Wt, s);
+}
+
+int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout, int blank,
+                    int32_t* ids, int32_t* lens, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  if (L == 0) return 0;
+  BDRC_REQUIRE(ctx, logits && ids && lens && V > 0 && T > 0 && T <= 20000 &&
+                        (layout == BDRC_LAYOUT_TV || layout == BDRC_LAYOUT_VT),
+               "ctc_greedy: bad arguments (V=%d T=%d)", V, T);
+  const size_t smem = (size_t)2 * T * sizeof(int);
+  if (smem > 48 * 1024)
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+  ctc_greedy_kernel<<<L, 512, smem, (cudaStream_t)stream>>>(logits, V, T, layout, blank, ids, lens);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+}  // extern "C"

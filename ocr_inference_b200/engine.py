@@ -1,0 +1,251 @@
+"""Thin device-side engine over the C ABI: torch owns memory and streams, libbdrc_b200.so does the work.
+
+Every method takes / returns torch CUDA tensors.  No method has a CPU fallback; constructing an
+Engine without a B200 raises (ocr_inference_b200._lib.Context).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import write_blob
+
+SEG, OCR = 1, 2
+POST_SIGMOID, POST_SOFTMAX = 0, 1
+LAYOUT_TV, LAYOUT_VT = 0, 1
+OCR_CPAD = 128
+PATCH = 512
+
+
+def clamp_size(H: int, W: int, patch: int = PATCH, clamp_w: int = 4096, clamp_h: int = 2048):
+    """Target size of the clamp / upsize branch of utils.preprocess_image (BDRC/utils.py:764-773);
+    resize_to_width/height truncate the free side with int() (:473, :491)."""
+    if W > H and W > clamp_w:
+        return int(H * (clamp_w / W)), clamp_w
+    if H > W and H > clamp_h:
+        return clamp_h, int(W * (clamp_h / H))
+    if H < patch:
+        return patch, int(W * (patch / H))
+    return H, W
+
+
+def clamp_size_torch(H: int, W: int, patch: int = PATCH, max_w: int = 4096, max_h: int = 2048):
+    """utils.resize_clamp (BDRC/utils.py:967-987): same branches, but round() instead of int()."""
+    if W > H and W > max_w:
+        sc = max_w / W
+    elif H > W and H > max_h:
+        sc = max_h / H
+    elif H < patch:
+        sc = patch / H
+    else:
+        return H, W
+    return int(round(H * sc)), int(round(W * sc))
+
+
+class Model:
+    def __init__(self, eng: "Engine", kind: int, handle, n_out: int):
+        self.eng, self.kind, self.h, self.n_out = eng, kind, handle, n_out
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.eng.lib.bdrc_free_model(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.BdrcError("no CUDA device: ocr_inference_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.ctx = _lib.Context(device)
+        self.lib = self.ctx.lib
+        self._ws: dict[str, torch.Tensor] = {}
+
+    # ---- plumbing ------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        self.ctx.check(rc, what)
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        t = self._ws.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def launch_count(self) -> int:
+        return self.ctx.launch_count()
+
+    def set_conv_engine(self, engine: int):
+        self._check(self.lib.bdrc_set_conv_engine(self.ctx.h, engine), "set_conv_engine")
+
+    def profile(self, on: bool):
+        self._check(self.lib.bdrc_profile_enable(self.ctx.h, int(on)), "profile_enable")
+        self._check(self.lib.bdrc_profile_reset(self.ctx.h), "profile_reset")
+
+    def profile_results(self):
+        out = []
+        for i in range(self.lib.bdrc_profile_count(self.ctx.h)):
+            name, ms, fl = C.c_char_p(), C.c_float(), C.c_double()
+            self._check(self.lib.bdrc_profile_get(self.ctx.h, i, C.byref(name), C.byref(ms), C.byref(fl)),
+                        "profile_get")
+            out.append((name.value.decode(), ms.value, fl.value))
+        self._check(self.lib.bdrc_profile_reset(self.ctx.h), "profile_reset")
+        return out
+
+    # ---- models --------------------------------------------------------------------------
+    def load_model(self, kind: int, weights: dict[str, np.ndarray] | bytes, n_out: int) -> Model:
+        blob = weights if isinstance(weights, (bytes, bytearray)) else write_blob(weights)
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        h = C.c_void_p()
+        self._check(self.lib.bdrc_load_weights(self.ctx.h, kind, buf, len(blob), n_out, C.byref(h)),
+                    "load_weights")
+        return Model(self, kind, h, n_out)
+
+    # ---- a-1 -----------------------------------------------------------------------------
+    def resize_u8(self, img: torch.Tensor, Hd: int, Wd: int) -> torch.Tensor:
+        """cv2.resize(INTER_LINEAR) on an HWC (or HW) u8 tensor."""
+        img = img.contiguous()
+        Hs, Ws = img.shape[:2]
+        Cn = img.shape[2] if img.dim() == 3 else 1
+        out = torch.empty((Hd, Wd) + ((Cn,) if img.dim() == 3 else ()), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.bdrc_resize_bilinear_u8(self.ctx.h, img.data_ptr(), Hs, Ws, Cn, out.data_ptr(),
+                                                     Hd, Wd, self.stream), "resize_bilinear_u8")
+        return out
+
+    def seg_preprocess(self, page: torch.Tensor, patch: int = PATCH):
+        """page u8 HWC on device -> (tiles u8 {0,1} [N,P,P], meta) as Detection._preprocess_image."""
+        H0, W0 = int(page.shape[0]), int(page.shape[1])
+        Hc, Wc = clamp_size(H0, W0, patch)
+        page = page.contiguous()
+        if (Hc, Wc) != (H0, W0):
+            page = self.resize_u8(page, Hc, Wc)
+        nty, ntx = math.ceil(Hc / patch), math.ceil(Wc / patch)
+        tiles = torch.empty((nty * ntx, patch, patch), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.bdrc_seg_preprocess(self.ctx.h, page.data_ptr(), Hc, Wc, patch, tiles.data_ptr(),
+                                                 self.stream), "seg_preprocess")
+        meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)
+        return tiles, meta
+
+    def seg_tile_rgb(self, page: torch.Tensor, patch: int = PATCH):
+        """torch-path collate (utils.multi_image_collate_fn): fp32 RGB tiles [N,P,P,3] in [0,255]."""
+        H0, W0 = int(page.shape[0]), int(page.shape[1])
+        Hc, Wc = clamp_size_torch(H0, W0, patch)
+        page = page.contiguous()
+        nty, ntx = math.ceil(Hc / patch), math.ceil(Wc / patch)
+        tiles = torch.empty((nty * ntx, patch, patch, 3), dtype=torch.float32, device=self.device)
+        self._check(self.lib.bdrc_seg_tile_rgb(self.ctx.h, page.data_ptr(), H0, W0, Hc, Wc, patch,
+                                               tiles.data_ptr(), self.stream), "seg_tile_rgb")
+        meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)
+        return tiles, meta
+
+    # ---- a-2 -----------------------------------------------------------------------------
+    def seg_forward(self, model: Model, tiles: torch.Tensor, lowres: bool = False) -> torch.Tensor:
+        n = int(tiles.shape[0])
+        cin = 1 if tiles.dtype == torch.uint8 else 3
+        Cn = model.n_out
+        ws = self._workspace("seg", int(self.lib.bdrc_seg_workspace_bytes(model.h, n)))
+        tiles = tiles.contiguous()
+        if lowres:
+            out = torch.empty((n, 128, 128, Cn), dtype=torch.float32, device=self.device)
+            fn = self.lib.bdrc_seg_forward_lowres
+        else:
+            out = torch.empty((n, Cn, PATCH, PATCH), dtype=torch.float32, device=self.device)
+            fn = self.lib.bdrc_seg_forward
+        self._check(fn(self.ctx.h, model.h, tiles.data_ptr(), n, cin, out.data_ptr(), ws.data_ptr(),
+                       ws.numel(), self.stream), "seg_forward")
+        return out
+
+    # ---- a-3 -----------------------------------------------------------------------------
+    def seg_postprocess(self, logits: torch.Tensor, meta: dict, mode: int, thr: float,
+                        lowres: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+        Cn = int(logits.shape[3] if lowres else logits.shape[1])
+        H0, W0 = meta["H0"], meta["W0"]
+        if lowres and (meta["Hc"], meta["Wc"]) != (H0, W0):
+            raise _lib.BdrcError("low-res post-processing does not resize; use the full-res path")
+        shape = (H0, W0) if Cn == 1 else (H0, W0, Cn)
+        mask = out if out is not None else torch.empty(shape, dtype=torch.uint8, device=self.device)
+        logits = logits.contiguous()
+        if lowres:
+            rc = self.lib.bdrc_seg_postprocess_lowres(self.ctx.h, logits.data_ptr(), meta["nty"], meta["ntx"], Cn,
+                                                      PATCH, meta["Hc"], meta["Wc"], mode, thr, mask.data_ptr(),
+                                                      self.stream)
+        else:
+            rc = self.lib.bdrc_seg_postprocess(self.ctx.h, logits.data_ptr(), meta["nty"], meta["ntx"], Cn, PATCH,
+                                               meta["Hc"], meta["Wc"], H0, W0, mode, thr, mask.data_ptr(),
+                                               self.stream)
+        self._check(rc, "seg_postprocess")
+        return mask
+
+    def seg_postprocess_torch(self, logits: torch.Tensor, meta: dict, thr: float) -> torch.Tensor:
+        Cn = int(logits.shape[1])
+        mask = torch.empty((Cn, meta["H0"], meta["W0"]), dtype=torch.uint8, device=self.device)
+        logits = logits.contiguous()
+        self._check(self.lib.bdrc_seg_postprocess_torch(self.ctx.h, logits.data_ptr(), meta["nty"], meta["ntx"], Cn,
+                                                        PATCH, meta["Hc"], meta["Wc"], meta["H0"], meta["W0"], thr,
+                                                        mask.data_ptr(), self.stream), "seg_postprocess_torch")
+        return mask
+
+    # ---- a-7 -----------------------------------------------------------------------------
+    def pack_crops(self, crops: list[np.ndarray]):
+        """Host list of ragged HWC u8 crops -> (device buffer, hw int32 [L,2], off int64 [L])."""
+        hw = np.array([[c.shape[0], c.shape[1]] for c in crops], dtype=np.int32).reshape(-1, 2)
+        sizes = [int(c.shape[0]) * int(c.shape[1]) * 3 for c in crops]
+        off = np.zeros(len(crops), dtype=np.int64)
+        if len(crops) > 1:
+            off[1:] = np.cumsum([(s + 15) // 16 * 16 for s in sizes[:-1]])
+        total = int(off[-1] + sizes[-1]) if crops else 0
+        host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for c, o, s in zip(crops, off, sizes):
+            if s:
+                hv[o:o + s] = np.ascontiguousarray(c[..., :3]).reshape(-1)
+        dev = host.to(self.device, non_blocking=True)
+        return dev, torch.from_numpy(hw).to(self.device), torch.from_numpy(off).to(self.device)
+
+    def ocr_prepare_lines(self, crops_dev, hw_dev, off_dev, L: int, Ht: int, Wt: int, pre_pad: bool,
+                          want_f32: bool = False):
+        lines = torch.empty((L, Wt, OCR_CPAD), dtype=torch.bfloat16, device=self.device)
+        f32 = torch.empty((L, Ht, Wt), dtype=torch.float32, device=self.device) if want_f32 else None
+        ws = self._workspace("ocr_prep", int(self.lib.bdrc_ocr_prepare_workspace_bytes(L, Ht, Wt)))
+        self._check(self.lib.bdrc_ocr_prepare_lines(
+            self.ctx.h, crops_dev.data_ptr(), hw_dev.data_ptr(), off_dev.data_ptr(), L, Ht, Wt, int(pre_pad),
+            OCR_CPAD, lines.data_ptr(), f32.data_ptr() if want_f32 else None, ws.data_ptr(), ws.numel(),
+            self.stream), "ocr_prepare_lines")
+        return lines, f32
+
+    # ---- a-8 / a-9 -----------------------------------------------------------------------
+    def ocr_forward(self, model: Model, lines: torch.Tensor) -> torch.Tensor:
+        L, Wt = int(lines.shape[0]), int(lines.shape[1])
+        T, V = Wt // 4, model.n_out
+        logits = torch.empty((L, T, V), dtype=torch.float32, device=self.device)
+        ws = self._workspace("ocr", int(self.lib.bdrc_ocr_workspace_bytes(model.h, L, Wt)))
+        lines = lines.contiguous()
+        self._check(self.lib.bdrc_ocr_forward(self.ctx.h, model.h, lines.data_ptr(), L, Wt, logits.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), self.stream), "ocr_forward")
+        return logits
+
+    def ctc_greedy(self, logits: torch.Tensor, layout: int = LAYOUT_TV, blank: int = 0):
+        logits = logits.contiguous()
+        L = int(logits.shape[0])
+        T, V = (int(logits.shape[1]), int(logits.shape[2])) if layout == LAYOUT_TV else \
+            (int(logits.shape[2]), int(logits.shape[1]))
+        ids = torch.empty((L, T), dtype=torch.int32, device=self.device)
+        lens = torch.zeros((L,), dtype=torch.int32, device=self.device)
+        self._check(self.lib.bdrc_ctc_greedy(self.ctx.h, logits.data_ptr(), L, V, T, layout, blank, ids.data_ptr(),
+                                             lens.data_ptr(), self.stream), "ctc_greedy")
+        return ids, lens

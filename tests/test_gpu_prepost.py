@@ -1,0 +1,127 @@
+"""GPU parity: pre/post-processing kernels vs the CPU oracle, bit-exact (integer / byte work)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hostops as ho
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(600, 700), (512, 512), (472, 2550), (2100, 1500), (1300, 4500), (1024, 1536)])
+def test_seg_preprocess_bit_exact(engine, shape):
+    page, _ = synth.page(7 + shape[0], *shape)
+    tiles, meta = engine.seg_preprocess(_dev(page))
+    ref, rmeta = ho.seg_preprocess(page, closed_form=False)   # cv2 path, exactly what the reference runs
+    for k in ("Hc", "Wc", "pad_x", "pad_y"):
+        assert meta[k] == rmeta[k]
+    got = tiles.cpu().numpy()
+    assert got.shape == ref.shape
+    assert int((got != ref).sum()) == 0
+
+
+def test_seg_preprocess_full_page_properties(engine):
+    """BASELINE size (2048x3072): identical to the oracle on a subset of tiles + value range."""
+    page, _ = synth.page(2002, 2048, 3072)
+    tiles, meta = engine.seg_preprocess(_dev(page))
+    got = tiles.cpu().numpy()
+    assert got.shape == (24, 512, 512) and set(np.unique(got)) <= {0, 1}
+    ref, _ = ho.seg_preprocess(page, closed_form=False)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("src,dst", [((100, 300), (80, 240)), ((60, 1500), (80, 2000)), ((472, 2550), (512, 2766)),
+                                      ((300, 200), (150, 100)), ((61, 61), (80, 80)), ((2100, 1500), (2048, 1462))])
+def test_resize_u8_matches_cv2(engine, src, dst):
+    import cv2
+
+    rng = np.random.default_rng(src[0] * 7 + dst[1])
+    img = rng.integers(0, 256, (*src, 3), dtype=np.uint8)
+    got = engine.resize_u8(_dev(img), dst[0], dst[1]).cpu().numpy()
+    ref = cv2.resize(img, (dst[1], dst[0]), interpolation=cv2.INTER_LINEAR)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("shape", [(600, 700), (2048, 3072), (472, 2550), (2100, 1500), (1300, 4500)])
+def test_line_postprocess_bit_exact(engine, shape):
+    """sigmoid > 0.9 -> stitch -> crop -> (cv2 float resize) -> u8*255, on seeded fp32 logits."""
+    H0, W0 = shape
+    Hc, Wc = ho.clamp_size(H0, W0)
+    nty, ntx = -(-Hc // 512), -(-Wc // 512)
+    rng = np.random.default_rng(H0 + W0)
+    # smooth blobs around the threshold so both decisions occur in runs (exercises the resize)
+    low = rng.normal(1.5, 3.0, (nty * ntx, 1, 64, 64)).astype(np.float32)
+    logits = torch.nn.functional.interpolate(torch.from_numpy(low), size=(512, 512), mode="bilinear").numpy()
+    logits[0, 0, :4, :4] = np.float32(2.1972246)   # exactly the last "False" logit and the first "True"
+    logits[0, 0, 4:8, :4] = np.float32(2.1972249)
+    meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, y_steps=nty, x_steps=ntx,
+                pad_x=ntx * 512 - Wc, pad_y=nty * 512 - Hc)
+    got = engine.seg_postprocess(_dev(logits), meta, 0, 0.9).cpu().numpy()
+    ref = ho.line_postprocess(logits, meta, 0.9, closed_form=False)
+    assert got.shape == ref.shape and got.dtype == np.uint8
+    assert int((got != ref).sum()) == 0
+    assert 0.05 < (ref == 255).mean() < 0.95
+
+
+@pytest.mark.parametrize("shape", [(600, 700), (472, 2550), (2100, 1500)])
+def test_layout_postprocess(engine, shape):
+    H0, W0 = shape
+    Hc, Wc = ho.clamp_size(H0, W0)
+    nty, ntx = -(-Hc // 512), -(-Wc // 512)
+    rng = np.random.default_rng(H0 * 3 + W0)
+    low = rng.normal(0, 3.0, (nty * ntx, 5, 32, 32)).astype(np.float32)
+    logits = torch.nn.functional.interpolate(torch.from_numpy(low), size=(512, 512), mode="bilinear").numpy()
+    meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, y_steps=nty, x_steps=ntx,
+                pad_x=ntx * 512 - Wc, pad_y=nty * 512 - Hc)
+    got = engine.seg_postprocess(_dev(logits), meta, 1, 0.8).cpu().numpy()
+    ref = ho.layout_postprocess(logits, meta, 0.8, closed_form=False)
+    assert got.shape == ref.shape
+    # softmax is fp32 transcendental: decisions may differ only where p is within 1e-6 of 0.8
+    from scipy.special import softmax
+    p = softmax(np.transpose(logits, (0, 2, 3, 1)), axis=-1)
+    near = int((np.abs(p - 0.8) < 1e-6).sum())
+    assert int((got != ref).sum()) <= 4 * near
+    assert (ref == 255).mean() > 0.02
+
+
+@pytest.mark.parametrize("pre_pad", [False, True])
+def test_ocr_prepare_lines_bit_exact(engine, pre_pad):
+    crops = synth.line_crops(1001, 12) + [synth.line_crop(5, 80, 2000), synth.line_crop(6, 30, 400),
+                                          synth.line_crop(7, 200, 900), synth.line_crop(8, 40, 4100),
+                                          synth.line_crop(9, 160, 4000)]
+    dev, hw, off = engine.pack_crops(crops)
+    lines, f32 = engine.ocr_prepare_lines(dev, hw, off, len(crops), 80, 2000, pre_pad, want_f32=True)
+    got = f32.cpu().numpy()
+    bf = lines.float().cpu().numpy()
+    for i, c in enumerate(crops):
+        ref = ho.prepare_ocr_line(c, 80, 2000, pre_pad=pre_pad, closed_form=False)[0]
+        assert set(np.unique(got[i])) <= {-1.0, 1.0}
+        assert int((got[i] != ref).sum()) == 0, f"line {i} shape {c.shape}"
+        # network layout: [W][Cpad] time-major, zero padded channels
+        assert np.array_equal(bf[i, :, :80], ref.T)
+        assert not bf[i, :, 80:].any()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("L,V,T", [(1, 77, 500), (7, 77, 500), (3, 5, 33), (2, 200, 1000), (4, 77, 1)])
+def test_ctc_greedy_bit_exact(engine, layout, L, V, T):
+    rng = np.random.default_rng(L * 1000 + V + T)
+    logits = rng.normal(0, 1, (L, T, V)).astype(np.float32)
+    logits[:, :, 0] += 1.5                       # blank prior -> runs of blanks and repeats
+    logits[0, : min(T, 10), :] = 0.25           # exact ties -> lowest index must win
+    if T > 40:
+        logits[0, 20:30, 3] = 9.0               # a repeated label that must collapse
+        logits[0, 30, 0] = 20.0
+        logits[0, 31:35, 3] = 9.0               # same label after a blank must be emitted again
+    dev = _dev(logits if layout == 0 else np.ascontiguousarray(logits.transpose(0, 2, 1)))
+    ids, lens = engine.ctc_greedy(dev, layout=layout, blank=0)
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    for l in range(L):
+        ref = ho.ctc_greedy_ids(logits[l], V + 1000)   # V+1000: never transpose, input is [T,V]
+        assert lens[l] == len(ref)
+        assert ids[l, : lens[l]].tolist() == ref
