@@ -127,15 +127,18 @@ class Engine:
                                                      Hd, Wd, self.stream), "resize_bilinear_u8")
         return out
 
-    def seg_preprocess(self, page: torch.Tensor, patch: int = PATCH):
-        """page u8 HWC on device -> (tiles u8 {0,1} [N,P,P], meta) as Detection._preprocess_image."""
+    def seg_preprocess(self, page: torch.Tensor, patch: int = PATCH, out: torch.Tensor | None = None):
+        """page u8 HWC on device -> (tiles u8 {0,1} [N,P,P], meta) as Detection._preprocess_image.
+        `out` (optional) is a preallocated [N,P,P] u8 slice of a larger tile batch."""
         H0, W0 = int(page.shape[0]), int(page.shape[1])
         Hc, Wc = clamp_size(H0, W0, patch)
         page = page.contiguous()
         if (Hc, Wc) != (H0, W0):
             page = self.resize_u8(page, Hc, Wc)
         nty, ntx = math.ceil(Hc / patch), math.ceil(Wc / patch)
-        tiles = torch.empty((nty * ntx, patch, patch), dtype=torch.uint8, device=self.device)
+        tiles = out if out is not None else torch.empty((nty * ntx, patch, patch), dtype=torch.uint8,
+                                                        device=self.device)
+        assert tiles.shape[0] == nty * ntx and tiles.is_contiguous()
         self._check(self.lib.bdrc_seg_preprocess(self.ctx.h, page.data_ptr(), Hc, Wc, patch, tiles.data_ptr(),
                                                  self.stream), "seg_preprocess")
         meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)

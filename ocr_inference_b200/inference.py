@@ -1,0 +1,243 @@
+"""Drop-in for the hot path of BDRC/inference.py: same class names, constructor signatures, stage
+methods and (OpStatus, payload) conventions -- the numpy/cv2/onnxruntime internals are replaced
+by libbdrc_b200.so kernels on a B200.  No CPU fallback: constructing any of these without the
+CUDA library / a B200 raises.
+
+Batched entry points (`predict_batch`, `run_batch`, `run_ocr_batch`) are additions for
+throughput; the single-image methods give identical results.
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from .data import (CharsetEncoder, DewarpingResult, Encoding, KenLMConfig, LayoutDetectionConfig,  # noqa: F401
+                   Line, LineDetectionConfig, OCRLine, OCRModelConfig, OpStatus)
+from .engine import LAYOUT_TV, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
+
+_ENGINES: dict[int, Engine] = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """One Engine (ctx + workspaces) per process and GPU. LOCAL_RANK selects the GPU by default."""
+    if device is None:
+        device = int(os.environ.get("BDRC_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def _read_weights(src):
+    if isinstance(src, dict) or isinstance(src, (bytes, bytearray)):
+        return src
+    with open(src, "rb") as f:
+        return f.read()
+
+
+class CTCDecoder:
+    """Greedy CTC decoder with the reference's vocabulary conventions (BDRC/inference.py:75-118):
+    index 0 is '<blk>' when add_blank, label i maps to charset[i-1]."""
+
+    def __init__(self, charset: str | list[str], add_blank: bool, kenlm_config: KenLMConfig | None = None):
+        self.blank_sign = "<blk>"
+        self.charset = list(charset) if isinstance(charset, str) else charset
+        self.ctc_vocab = self.charset.copy()
+        if add_blank:
+            self.ctc_vocab.insert(0, self.blank_sign)
+        self.blank_index = self.ctc_vocab.index(self.blank_sign) if self.blank_sign in self.ctc_vocab else 0
+        if kenlm_config is not None:
+            # LM-fused beam search lives in an un-vendored fork (requirements.txt:13): out of scope
+            print("KenLM disabled: beam search with a language model is not part of the B200 hot path")
+
+    def encode(self, label: str):
+        return [self.charset.index(x) + 1 for x in label]
+
+    def decode(self, inputs: Sequence[int]) -> str:
+        return "".join(self.charset[x - 1] for x in inputs)
+
+    def ids_to_text(self, ids: Sequence[int]) -> str:
+        return "".join(self.ctc_vocab[i] for i in ids).replace(self.blank_sign, "")
+
+    def ctc_decode(self, logits) -> str:
+        """logits (T, V) array-like -> text; runs the greedy kernel on the GPU."""
+        eng = get_engine()
+        t = torch.as_tensor(np.ascontiguousarray(logits, dtype=np.float32)).to(eng.device)[None]
+        ids, lens = eng.ctc_greedy(t, layout=LAYOUT_TV, blank=self.blank_index)
+        n = int(lens[0].item())
+        return self.ids_to_text(ids[0, :n].tolist())
+
+
+class Detection:
+    """BDRC/inference.py:121-163.  config.onnx_file names a BDRCW1 weight container."""
+
+    _mode = POST_SIGMOID
+    _default_threshold = 0.8
+
+    def __init__(self, config: LineDetectionConfig | LayoutDetectionConfig, engine: Engine | None = None):
+        self.config = config
+        self._config_file = config
+        self._onnx_model_file = config.onnx_file
+        self._patch_size = config.patch_size
+        if self._patch_size != 512:
+            raise ValueError("the B200 segmentation path is built for 512x512 patches")
+        self._classes = config.classes
+        self.engine = engine or get_engine()
+        n_out = 1 if self._mode == POST_SIGMOID else len(config.classes)
+        self._inference = self.engine.load_model(SEG, _read_weights(config.onnx_file), n_out)
+
+    # device-resident stages ----------------------------------------------------------------
+    def _predict_device(self, page_dev: torch.Tensor, class_threshold: float) -> torch.Tensor:
+        tiles, meta = self.engine.seg_preprocess(page_dev, self._patch_size)            # a-1
+        if (meta["Hc"], meta["Wc"]) == (meta["H0"], meta["W0"]):
+            low = self.engine.seg_forward(self._inference, tiles, lowres=True)           # a-2
+            return self.engine.seg_postprocess(low, meta, self._mode, class_threshold, lowres=True)   # a-3
+        logits = self.engine.seg_forward(self._inference, tiles)
+        return self.engine.seg_postprocess(logits, meta, self._mode, class_threshold)
+
+    def _predict_device_batch(self, pages_dev: Sequence[torch.Tensor], class_threshold: float) -> list[torch.Tensor]:
+        """Several device-resident pages through ONE forward call (tiles of all pages share the
+        batch dimension; per-tile reductions are per batch element, so this is exact)."""
+        eng = self.engine
+        from .engine import clamp_size
+        P = self._patch_size
+        geo = []
+        for p in pages_dev:
+            H0, W0 = int(p.shape[0]), int(p.shape[1])
+            Hc, Wc = clamp_size(H0, W0, P)
+            geo.append((-(-Hc // P)) * (-(-Wc // P)))
+        tiles = torch.empty((sum(geo), P, P), dtype=torch.uint8, device=eng.device)
+        metas, o = [], 0
+        for p, n in zip(pages_dev, geo):
+            _, meta = eng.seg_preprocess(p, P, out=tiles[o:o + n])
+            metas.append(meta)
+            o += n
+        need_full = any((m["Hc"], m["Wc"]) != (m["H0"], m["W0"]) for m in metas)
+        logits = eng.seg_forward(self._inference, tiles, lowres=not need_full)
+        outs, o = [], 0
+        for n, meta in zip(geo, metas):
+            outs.append(eng.seg_postprocess(logits[o:o + n], meta, self._mode, class_threshold, lowres=not need_full))
+            o += n
+        return outs
+
+    def predict(self, image: np.ndarray, class_threshold: float | None = None) -> np.ndarray:
+        thr = self._default_threshold if class_threshold is None else class_threshold
+        page = torch.from_numpy(np.ascontiguousarray(image[..., :3], dtype=np.uint8)).to(self.engine.device)
+        return self._predict_device(page, thr).cpu().numpy()
+
+    def predict_batch(self, images: Sequence[np.ndarray], class_threshold: float | None = None,
+                      pinned: Sequence[torch.Tensor] | None = None, copy: bool = True) -> list[np.ndarray]:
+        """Same result as [predict(i) for i in images]; uploads run ahead of compute on a copy
+        stream and masks come back through pinned buffers.  With copy=False the returned arrays
+        alias this object's pinned staging buffers and stay valid until the next predict_batch call
+        (the io-binding style of use); copy=True (default) hands out fresh arrays like the reference."""
+        thr = self._default_threshold if class_threshold is None else class_threshold
+        eng = self.engine
+        dev = eng.device
+        compute = torch.cuda.current_stream(dev)
+        copy_in = getattr(self, "_copy_in", None) or torch.cuda.Stream(dev)
+        self._copy_in = copy_in
+        ups, evs = [], []
+        copy_in.wait_stream(compute)
+        with torch.cuda.stream(copy_in):
+            for i, img in enumerate(images):
+                src = pinned[i] if pinned is not None else torch.from_numpy(
+                    np.ascontiguousarray(img[..., :3], dtype=np.uint8))
+                d = src.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+                ups.append(d)
+                evs.append(ev)
+        outs = []
+        group = 2   # 2 landscape pages = 48 tiles = one forward chunk; later groups upload meanwhile
+        for g0 in range(0, len(ups), group):
+            for d, ev in zip(ups[g0:g0 + group], evs[g0:g0 + group]):
+                compute.wait_event(ev)
+                d.record_stream(compute)
+            for m in self._predict_device_batch(ups[g0:g0 + group], thr):
+                key = ("mask_host", len(outs), tuple(m.shape))
+                h = self._host_bufs.get(key) if hasattr(self, "_host_bufs") else None
+                if h is None:
+                    if not hasattr(self, "_host_bufs"):
+                        self._host_bufs = {}
+                    h = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
+                    self._host_bufs[key] = h
+                h.copy_(m, non_blocking=True)
+                outs.append(h)
+        compute.synchronize()
+        return [o.numpy().copy() if copy else o.numpy() for o in outs]
+
+
+class LineDetection(Detection):
+    """BDRC/inference.py:166-183: sigmoid > 0.9 -> (H, W) u8 {0,255}."""
+
+    _mode = POST_SIGMOID
+    _default_threshold = 0.9
+
+
+class LayoutDetection(Detection):
+    """BDRC/inference.py:186-276: softmax > 0.8 -> (H, W, C) u8 {0,255}."""
+
+    _mode = POST_SOFTMAX
+    _default_threshold = 0.8
+
+    def __init__(self, config: LayoutDetectionConfig, debug: bool = False, engine: Engine | None = None):
+        super().__init__(config, engine)
+        self._debug = debug
+
+
+class OCRInference:
+    """BDRC/inference.py:279-429.  config.model_file names a BDRCW1 container of Easter2 weights."""
+
+    def __init__(self, ocr_config: OCRModelConfig, kenlm_config: KenLMConfig | None = None,
+                 engine: Engine | None = None):
+        self.config = ocr_config
+        self._onnx_model_file = ocr_config.model_file
+        self._input_width = ocr_config.input_width
+        self._input_height = ocr_config.input_height
+        self._input_layer = ocr_config.input_layer
+        self._output_layer = ocr_config.output_layer
+        self._characters = ocr_config.charset
+        self._squeeze_channel_dim = ocr_config.squeeze_channel
+        self._swap_hw = ocr_config.swap_hw
+        self._add_blank = ocr_config.add_blank
+        self.engine = engine or get_engine()
+        self.ctc_decoder = CTCDecoder(self._characters, self._add_blank, kenlm_config=None)
+        self.ctc_decoder_lm = None
+        vocab = len(self.ctc_decoder.ctc_vocab)
+        self.ocr_session = self.engine.load_model(OCR, _read_weights(ocr_config.model_file), vocab)
+
+    def _check_fit(self, img: np.ndarray, pre_pad: bool):
+        h, w = img.shape[:2]
+        if pre_pad:
+            w = w + 2 * h
+        Wt, Ht = self._input_width, self._input_height
+        wr, hr = Wt / w, Ht / h
+        rh, rw = (int(h * wr), Wt) if wr <= hr else (Ht, int(w * hr))
+        if rh <= 0 or rw <= 0:
+            # cv2.resize raises on an empty target in the reference (utils.py:468-476)
+            raise ValueError(f"line image {img.shape} collapses to an empty OCR input")
+
+    def run_batch(self, line_images: Sequence[np.ndarray], pre_pad: bool = True, use_lm: bool = False,
+                  return_ids: bool = False):
+        """All lines of a page (or many pages) in one pass: prep -> Easter2 -> greedy CTC."""
+        if len(line_images) == 0:
+            return []
+        for img in line_images:
+            self._check_fit(img, pre_pad)
+        eng = self.engine
+        dev, hw, off = eng.pack_crops(list(line_images))
+        lines, _ = eng.ocr_prepare_lines(dev, hw, off, len(line_images), self._input_height, self._input_width,
+                                         pre_pad)                                          # a-7
+        logits = eng.ocr_forward(self.ocr_session, lines)                                  # a-8
+        ids, lens = eng.ctc_greedy(logits, layout=LAYOUT_TV, blank=self.ctc_decoder.blank_index)   # a-9
+        ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+        seqs = [ids[i, : lens[i]].tolist() for i in range(len(line_images))]
+        if return_ids:
+            return seqs
+        return [self.ctc_decoder.ids_to_text(s) for s in seqs]
+
+    def run(self, line_image: np.ndarray, pre_pad: bool = True, use_lm: bool = False) -> str:
+        return self.run_batch([line_image], pre_pad, use_lm)[0]

@@ -1,70 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- deterministic synthetic pages / line crops.
-
-All generators are numpy.random.default_rng(seed) driven, u8, 3 identical channels unless noted.
-"""
-from __future__ import annotations
-
-import cv2
-import numpy as np
-
-CHARSET_76 = list("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789'+-./_~()[]|§&")
-assert len(CHARSET_76) == 76 and len(set(CHARSET_76)) == 76
-
-
-def _strokes(rng, canvas, y0, y1, x0, x1, n, dark=(20, 90)):
-    for _ in range(n):
-        cx = int(rng.integers(x0, max(x0 + 1, x1)))
-        cy = int(rng.integers(y0, max(y0 + 1, y1)))
-        w = int(rng.integers(3, 18))
-        h = int(rng.integers(3, max(4, (y1 - y0) // 2)))
-        col = int(rng.integers(*dark))
-        if rng.random() < 0.5:
-            cv2.ellipse(canvas, (cx, cy), (w, h), float(rng.integers(0, 180)), 0, 360, col, int(rng.integers(1, 4)))
-        else:
-            cv2.line(canvas, (cx - w, cy - h // 2), (cx + w, cy + h // 2), col, int(rng.integers(1, 4)))
-
-
-def page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (14, 22), rgb: bool = False):
-    """Synthetic page with horizontal text bands. Returns (u8 [H,W,3], list of band boxes (x,y,w,h))."""
-    rng = np.random.default_rng(seed)
-    g = np.clip(rng.normal(215, 12, (H, W)), 0, 255).astype(np.uint8)
-    n = int(rng.integers(n_lines[0], n_lines[1] + 1))
-    band_h = max(12, min(70, int(H / (n * 2.2))))
-    ys = np.linspace(band_h, H - 2 * band_h, n).astype(int)
-    boxes = []
-    for y in ys:
-        h = int(rng.integers(max(10, int(band_h * 0.6)), band_h + 1))
-        x0 = int(rng.integers(W // 40, W // 10))
-        x1 = W - int(rng.integers(W // 40, W // 10))
-        _strokes(rng, g, y, y + h, x0, x1, n=max(20, (x1 - x0) // 12))
-        boxes.append((x0, int(y), x1 - x0, h))
-    g = cv2.GaussianBlur(g, (3, 3), 0)
-    if rgb:
-        img = np.stack([g, np.clip(g.astype(int) - 6, 0, 255).astype(np.uint8),
-                        np.clip(g.astype(int) - 14, 0, 255).astype(np.uint8)], axis=-1)
-    else:
-        img = np.stack([g, g, g], axis=-1)
-    return np.ascontiguousarray(img), boxes
-
-
-def band_mask(boxes, H: int, W: int, grow: int = 4) -> np.ndarray:
-    """u8 {0,255} mask with one rounded blob per text band (a trained line model's output shape)."""
-    m = np.zeros((H, W), np.uint8)
-    for (x, y, w, h) in boxes:
-        cv2.rectangle(m, (x, max(0, y - grow)), (x + w, min(H - 1, y + h + grow)), 255, -1)
-    return m
-
-
-def line_crop(seed: int, h: int | None = None, w: int | None = None) -> np.ndarray:
-    """One ragged line crop u8 [h,w,3]: bright background, dark strokes, sigma=1 blur (C1 inputs)."""
-    rng = np.random.default_rng(seed)
-    h = int(rng.integers(60, 141)) if h is None else h
-    w = int(rng.integers(900, 2901)) if w is None else w
-    g = np.clip(rng.normal(225, 10, (h, w)), 0, 255).astype(np.uint8)
-    _strokes(rng, g, h // 6, h - h // 6, 10, w - 10, n=int(rng.integers(20, 61)) * max(1, w // 900), dark=(10, 90))
-    g = cv2.GaussianBlur(g, (0, 0), 1.0)
-    return np.ascontiguousarray(np.stack([g, g, g], axis=-1))
-
-
-def line_crops(seed: int, n: int, fixed: tuple[int, int] | None = None) -> list[np.ndarray]:
-    return [line_crop(seed * 100003 + i, *(fixed if fixed else (None, None))) for i in range(n)]
+"""TEST INFRASTRUCTURE ONLY -- re-export of the deterministic synthetic page / line generators
+(they live in ocr_inference_b200/synthetic.py because bench.py's product arm needs them too)."""
+from ocr_inference_b200.synthetic import *  # noqa: F401,F403
+from ocr_inference_b200.synthetic import CHARSET_76, band_mask, line_crop, line_crops, page  # noqa: F401

@@ -1,10 +1,13 @@
 """GPU parity: the two network forward passes (bf16 operands, fp32 accumulate on tcgen05) vs the
 torch-CPU fp32 oracle with the same seeded weights.
 
-Tolerance (stated, as north_star asks): bf16 has 8 mantissa bits, every layer rounds its output
-once; we accept |delta| <= 0.03 * std(oracle logits) + 0.03 * |oracle| per element for >= 99.9 % of
-the elements and require the decisions (mask bit / argmax) to agree wherever the oracle's margin to
-the decision boundary exceeds that tolerance.
+Tolerance (stated, as north_star asks): bf16 keeps 8 mantissa bits (relative rounding error 2^-9)
+and both weights and every layer output are rounded once, so ~35-50 roundings accumulate to a few
+per cent of the logit scale.  We require
+    rms(delta) <= 0.03 * std(oracle logits)                      (aggregate error)
+    |delta|    <= 0.08 * std(oracle) + 0.05 * |oracle|           for >= 99.9 % of the elements
+and that the decisions (mask bit / argmax) agree wherever the oracle's margin to the decision
+boundary exceeds that per-element tolerance.
 """
 import numpy as np
 import pytest
@@ -16,10 +19,16 @@ from oracle import nets, synth
 pytestmark = pytest.mark.gpu
 
 
-def _tol_check(got, ref, frac=0.999, rel=0.03):
-    tol = rel * ref.std() + rel * np.abs(ref)
-    ok = np.abs(got - ref) <= tol
-    assert ok.mean() >= frac, f"only {ok.mean():.5f} within tolerance; max err {np.abs(got - ref).max():.4f}, std {ref.std():.4f}"
+def _tol_check(got, ref, frac=0.999):
+    err = np.abs(got - ref)
+    std = float(ref.std())
+    rms = float(np.sqrt((err.astype(np.float64) ** 2).mean()))
+    tol = 0.08 * std + 0.05 * np.abs(ref)
+    ok = err <= tol
+    print(f"parity: rms_err/std={rms / std:.4f} max_err/std={err.max() / std:.4f} within_tol={ok.mean():.6f}")
+    assert np.isfinite(got).all()
+    assert rms <= 0.03 * std, f"rms error {rms:.4f} vs std {std:.4f}"
+    assert ok.mean() >= frac, f"only {ok.mean():.5f} within tolerance; max err {err.max():.4f}, std {std:.4f}"
     return tol
 
 
