@@ -135,26 +135,46 @@ int bdrc_warp_affine_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
 int bdrc_remap_bilinear_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
                            const float* coords, uint8_t* dst, void* stream);
 /* fused thin-plate-spline evaluate + bilinear sample (image_dewarping.py:55-72): ctrl_host
- * [n][2] control points (row,col), params_host [(n+3)][2] solved spline parameters. */
+ * [n][2] control points (row,col), params_host [(n+3)][2] solved spline parameters
+ * (tps.ThinPlateSpline: radial weights, then the affine rows [1, row, col]); n <= 64.
+ * workspace: bdrc_tps_workspace_bytes() bytes of device memory. */
+size_t bdrc_tps_workspace_bytes(void);
 int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
                       const double* ctrl_host, const double* params_host, int n_ctrl,
-                      uint8_t* dst, void* stream);
+                      uint8_t* dst, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a-5: extract_line_images  BDRC/line_detection.py:330-359 --------------------------- */
-/* One call per attempt-set: for each line l the caller supplies the filled-contour mask as
- * run-length spans (host cv2.drawContours is replaced by a device polygon fill from the
- * contour points): poly_xy int32 [sum n_pts][2], poly_off int32 [L+1].  For line l the SE is
- * kw[l] x kh[l] (cv2.getStructuringElement(MORPH_RECT,(k, int(k*kf))), anchor at centre).
- * Output: crops packed back to back in `crops` (u8 HWC, 3 channels), crop_hw[l] = (h,w),
- * crop_off[l] = byte offset.  Rows/cols where ANY channel is all-zero over the masked page are
- * deleted (mask_n_crop :79-104). `crops_capacity` bytes available; returns BDRC_ERR_ARG if
- * exceeded (crop_hw is still valid so the caller can retry). */
-size_t bdrc_extract_lines_workspace_bytes(int H, int W, int L);
-int bdrc_extract_lines(bdrc_ctx* ctx, const uint8_t* page, int H, int W, const int32_t* poly_xy,
-                       const int32_t* poly_off, int L, const int32_t* kw, const int32_t* kh,
-                       uint8_t* crops, size_t crops_capacity, int32_t* crop_hw,
-                       int64_t* crop_off, void* workspace, size_t workspace_bytes,
-                       void* stream);
+/* Inputs shared by both calls: page u8 HWC [H][W][C] (C = 1 or 3, device); for each line l the
+ * filled-contour mask of its bounding-box ROI roi_host[l] = (x, y, w, h) -- rasterised by the
+ * caller with cv2.drawContours exactly as line_detection.py:349-351 does, but into the ROI only
+ * -- packed in `masks` (device) at byte offset mask_off_host[l], row-major h x w, non-zero = set.
+ *
+ * bdrc_line_crop_heights: for every line and every candidate structuring element j
+ * (kw_host/kh_host [L][n_cand], cv2.getStructuringElement(MORPH_RECT, (k, int(k*kf))), anchor at
+ * the centre, line_detection.py:280-285) the height of the crop mask_n_crop (:79-104) would
+ * produce -- what get_line_image's shrink-k loop (:311-318) looks at.  heights: device int32
+ * [L][n_cand].
+ *
+ * bdrc_extract_lines: dilate, AND with the page, delete rows / columns in which ANY channel is
+ * all zero (rows first, then columns of the remaining rows), and gather the ragged crops back
+ * to back into `crops` (16-byte aligned starts): crop_hw[l] = (h, w), crop_off[l] = byte offset
+ * (device arrays).  If the crops do not fit `crops_capacity` nothing is gathered (crop_hw is
+ * still valid, so the caller can size the buffer and call again).
+ *
+ * workspace: bdrc_extract_lines_workspace_bytes(H, W, n_items, sat_elems) with n_items = L *
+ * n_cand (or L) and sat_elems = sum_l (w_l + 1) * (h_l + 1). */
+size_t bdrc_extract_lines_workspace_bytes(int H, int W, int n_items, int64_t sat_elems);
+int bdrc_line_crop_heights(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int C,
+                           const uint8_t* masks, const int32_t* roi_host,
+                           const int64_t* mask_off_host, int L, int n_cand,
+                           const int32_t* kw_host, const int32_t* kh_host, int32_t* heights,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int bdrc_extract_lines(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int C,
+                       const uint8_t* masks, const int32_t* roi_host,
+                       const int64_t* mask_off_host, int L, const int32_t* kw_host,
+                       const int32_t* kh_host, uint8_t* crops, size_t crops_capacity,
+                       int32_t* crop_hw, int64_t* crop_off, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* ---- a-7: OCRInference._prepare_ocr_line  BDRC/inference.py:313-357 --------------------- */
 /* crops: L ragged HWC u8 (3 ch) images at byte offsets crop_off, sizes crop_hw (h,w).

@@ -49,16 +49,20 @@ _SIGS = {
                                         c_int, c_void_p]),
     "bdrc_resize_bilinear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                          c_int, c_void_p]),
-    "bdrc_warp_affine_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_double),
-                                    c_void_p, c_void_p]),
+    "bdrc_warp_affine_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
     "bdrc_remap_bilinear_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),
-    "bdrc_tps_remap_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, C.POINTER(c_double),
-                                  C.POINTER(c_double), c_int, c_void_p, c_void_p]),
-    "bdrc_extract_lines_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "bdrc_extract_lines": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
-                                   c_void_p, c_size_t, c_void_p]),
+    "bdrc_tps_workspace_bytes": (c_size_t, []),
+    "bdrc_tps_remap_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bdrc_extract_lines_workspace_bytes": (c_size_t, [c_int, c_int, c_int, C.c_int64]),
+    "bdrc_line_crop_heights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "bdrc_extract_lines": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "bdrc_ocr_prepare_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bdrc_ocr_prepare_lines": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

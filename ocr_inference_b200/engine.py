@@ -203,6 +203,105 @@ class Engine:
                                                         mask.data_ptr(), self.stream), "seg_postprocess_torch")
         return mask
 
+    # ---- a-4 / a-6 -----------------------------------------------------------------------
+    def warp_affine(self, img: torch.Tensor, M: np.ndarray) -> torch.Tensor:
+        """cv2.warpAffine(img, M, (W, H), INTER_LINEAR, borderValue=0) on an HWC / HW u8 tensor."""
+        img = img.contiguous()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        Cn = int(img.shape[2]) if img.dim() == 3 else 1
+        out = torch.empty_like(img)
+        Mh = np.ascontiguousarray(M, dtype=np.float64).reshape(6)
+        self._check(self.lib.bdrc_warp_affine_u8(self.ctx.h, img.data_ptr(), H, W, Cn, Mh.ctypes.data, out.data_ptr(),
+                                                 self.stream), "warp_affine_u8")
+        return out
+
+    def remap_bilinear(self, img: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
+        """map_coordinates(order=1, mode='constant', cval=0); coords fp32 [2,H,W] = (row, col)."""
+        img, coords = img.contiguous(), coords.contiguous().float()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        Cn = int(img.shape[2]) if img.dim() == 3 else 1
+        out = torch.empty_like(img)
+        self._check(self.lib.bdrc_remap_bilinear_u8(self.ctx.h, img.data_ptr(), H, W, Cn, coords.data_ptr(),
+                                                    out.data_ptr(), self.stream), "remap_bilinear_u8")
+        return out
+
+    def tps_remap(self, img: torch.Tensor, ctrl: np.ndarray, params: np.ndarray) -> torch.Tensor:
+        """Thin-plate-spline dewarp: output(row, col) = bilinear(img, tps(row, col))."""
+        img = img.contiguous()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        Cn = int(img.shape[2]) if img.dim() == 3 else 1
+        out = torch.empty_like(img)
+        c = np.ascontiguousarray(ctrl, dtype=np.float64)
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ws = self._workspace("tps", int(self.lib.bdrc_tps_workspace_bytes()))
+        self._check(self.lib.bdrc_tps_remap_u8(self.ctx.h, img.data_ptr(), H, W, Cn, c.ctypes.data, p.ctypes.data,
+                                               int(c.shape[0]), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               self.stream), "tps_remap_u8")
+        return out
+
+    # ---- a-5 -----------------------------------------------------------------------------
+    def pack_masks(self, masks: list[np.ndarray], rois: list[tuple[int, int, int, int]]):
+        """ROI masks (filled contours) -> one device buffer + host geometry arrays."""
+        roi = np.array(rois, dtype=np.int32).reshape(-1, 4)
+        sizes = [int(m.shape[0]) * int(m.shape[1]) for m in masks]
+        off = np.zeros(len(masks), dtype=np.int64)
+        if len(masks) > 1:
+            off[1:] = np.cumsum([(s + 15) // 16 * 16 for s in sizes[:-1]])
+        total = int(off[-1] + sizes[-1]) if masks else 0
+        host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for m, o, s in zip(masks, off, sizes):
+            hv[o:o + s] = np.ascontiguousarray(m, dtype=np.uint8).reshape(-1)
+        dev = host.to(self.device, non_blocking=True)
+        return dict(dev=dev, roi=roi, off=off)
+
+    def _sub_pack(self, pack, idx):
+        roi = np.ascontiguousarray(pack["roi"][idx])
+        off = np.ascontiguousarray(pack["off"][idx])
+        sat = int(((roi[:, 2].astype(np.int64) + 1) * (roi[:, 3].astype(np.int64) + 1)).sum())
+        return roi, off, sat
+
+    def line_crop_heights(self, page: torch.Tensor, pack, idx: list[int], cand: list[list[tuple[int, int]]]):
+        """Crop heights for lines pack[idx] x candidate SEs; returns host int32 [len(idx), n_cand]."""
+        page = page.contiguous()
+        H, W = int(page.shape[0]), int(page.shape[1])
+        Cn = int(page.shape[2]) if page.dim() == 3 else 1
+        roi, off, sat = self._sub_pack(pack, idx)
+        L, NC = len(idx), len(cand[0])
+        kw = np.array([[c[0] for c in row] for row in cand], dtype=np.int32)
+        kh = np.array([[c[1] for c in row] for row in cand], dtype=np.int32)
+        heights = torch.empty((L, NC), dtype=torch.int32, device=self.device)
+        ws = self._workspace("extract", int(self.lib.bdrc_extract_lines_workspace_bytes(H, W, L * NC, sat)))
+        self._check(self.lib.bdrc_line_crop_heights(
+            self.ctx.h, page.data_ptr(), H, W, Cn, pack["dev"].data_ptr(), roi.ctypes.data, off.ctypes.data, L, NC,
+            kw.ctypes.data, kh.ctypes.data, heights.data_ptr(), ws.data_ptr(), ws.numel(), self.stream),
+            "line_crop_heights")
+        return heights.cpu().numpy()
+
+    def extract_lines(self, page: torch.Tensor, pack, idx: list[int], ses: list[tuple[int, int]]):
+        """Masked ragged crops for lines pack[idx] with SE ses[i]; returns (crops u8, hw [L,2], off [L])."""
+        page = page.contiguous()
+        H, W = int(page.shape[0]), int(page.shape[1])
+        Cn = int(page.shape[2]) if page.dim() == 3 else 1
+        roi, off, sat = self._sub_pack(pack, idx)
+        L = len(idx)
+        kw = np.array([s[0] for s in ses], dtype=np.int32)
+        kh = np.array([s[1] for s in ses], dtype=np.int32)
+        cap = 0
+        for (x, y, w, h), a, b in zip(roi.tolist(), kw.tolist(), kh.tolist()):
+            bw = min(W - 1, x + w - 1 + a // 2) - max(0, x - (a - 1 - a // 2)) + 1
+            bh = min(H - 1, y + h - 1 + b // 2) - max(0, y - (b - 1 - b // 2)) + 1
+            cap += (max(bw, 0) * max(bh, 0) * Cn + 15) // 16 * 16
+        crops = torch.empty(max(cap, 16), dtype=torch.uint8, device=self.device)
+        hw = torch.empty((L, 2), dtype=torch.int32, device=self.device)
+        coff = torch.empty((L,), dtype=torch.int64, device=self.device)
+        ws = self._workspace("extract", int(self.lib.bdrc_extract_lines_workspace_bytes(H, W, L, sat)))
+        self._check(self.lib.bdrc_extract_lines(
+            self.ctx.h, page.data_ptr(), H, W, Cn, pack["dev"].data_ptr(), roi.ctypes.data, off.ctypes.data, L,
+            kw.ctypes.data, kh.ctypes.data, crops.data_ptr(), crops.numel(), hw.data_ptr(), coff.data_ptr(),
+            ws.data_ptr(), ws.numel(), self.stream), "extract_lines")
+        return crops, hw, coff
+
     # ---- a-7 -----------------------------------------------------------------------------
     def pack_crops(self, crops: list[np.ndarray]):
         """Host list of ragged HWC u8 crops -> (device buffer, hw int32 [L,2], off int64 [L])."""

@@ -241,3 +241,196 @@ class OCRInference:
 
     def run(self, line_image: np.ndarray, pre_pad: bool = True, use_lm: bool = False) -> str:
         return self.run_batch([line_image], pre_pad, use_lm)[0]
+
+    def run_packed(self, crops_dev, hw_dev, off_dev, n: int, pre_pad: bool):
+        """Lines already resident on the GPU (from extract_line_images): ids per line."""
+        eng = self.engine
+        lines, _ = eng.ocr_prepare_lines(crops_dev, hw_dev, off_dev, n, self._input_height, self._input_width, pre_pad)
+        logits = eng.ocr_forward(self.ocr_session, lines)
+        ids, lens = eng.ctc_greedy(logits, layout=LAYOUT_TV, blank=self.ctc_decoder.blank_index)
+        ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+        return [self.ctc_decoder.ids_to_text(ids[i, : lens[i]].tolist()) for i in range(n)]
+
+
+class _IdentityConverter:
+    """Stand-in for pyewts.pyewts() (Wylie <-> Unicode conversion is third-party host code outside
+    the hot path); a real converter can be assigned to OCRPipeline.converter."""
+
+    def toUnicode(self, s):
+        return s
+
+    def toWylie(self, s):
+        return s
+
+
+class OCRPipeline:
+    """BDRC/inference.py:432-826 -- same constructor, stage methods and (OpStatus, payload) returns."""
+
+    def __init__(self, ocr_config: OCRModelConfig, line_config: LineDetectionConfig | LayoutDetectionConfig,
+                 kenlm_config: KenLMConfig | None = None, use_line_prepadding: bool = False,
+                 engine: Engine | None = None):
+        self.ready = False
+        self.ocr_model_config = ocr_config
+        self.line_config = line_config
+        self.encoder = ocr_config.encoder
+        self.engine = engine or get_engine()
+        self.ocr_inference = OCRInference(self.ocr_model_config, kenlm_config=kenlm_config, engine=self.engine)
+        try:
+            import pyewts  # type: ignore
+
+            self.converter = pyewts.pyewts()
+        except Exception:  # noqa: BLE001
+            self.converter = _IdentityConverter()
+        self.use_line_prepadding = use_line_prepadding
+        if isinstance(self.line_config, LineDetectionConfig):
+            self.line_inference = LineDetection(self.line_config, engine=self.engine)
+            self.ready = True
+        elif isinstance(self.line_config, LayoutDetectionConfig):
+            self.line_inference = LayoutDetection(self.line_config, engine=self.engine)
+            self.ready = True
+        else:
+            self.line_inference = None
+            self.ready = False
+
+    def update_ocr_model(self, config: OCRModelConfig, kenlm_config: KenLMConfig | None = None):
+        self.ocr_model_config = config
+        self.ocr_inference = OCRInference(config, kenlm_config, engine=self.engine)
+
+    def update_line_detection(self, config):
+        # inference.py:469-482: only swaps when the config TYPE changes
+        if isinstance(config, LineDetectionConfig) and isinstance(self.line_config, LayoutDetectionConfig):
+            self.line_inference = LineDetection(config, engine=self.engine)
+        elif isinstance(config, LayoutDetectionConfig) and isinstance(self.line_config, LineDetectionConfig):
+            self.line_inference = LayoutDetection(config, engine=self.engine)
+
+    # ---- stage 1 (inference.py:488-506) --------------------------------------------------
+    def detect_lines(self, image: np.ndarray):
+        if isinstance(self.line_config, LineDetectionConfig) and self.line_inference is not None:
+            line_mask = self.line_inference.predict(image)
+        elif isinstance(self.line_config, LayoutDetectionConfig) and self.line_inference is not None:
+            layout_mask = self.line_inference.predict(image)
+            line_mask = layout_mask[:, :, self.line_config.classes.index("line")]
+        return OpStatus.SUCCESS, line_mask
+
+    # ---- stage 2 (inference.py:508-533) --------------------------------------------------
+    def build_lines(self, image: np.ndarray, line_mask: np.ndarray):
+        from .line_detection import build_raw_line_data, filter_line_contours
+
+        rot_img, rot_mask, line_contours, page_angle = build_raw_line_data(image, line_mask)
+        if len(line_contours) == 0:
+            return OpStatus.FAILED, "No lines detected"
+        filtered = filter_line_contours(rot_mask, line_contours)
+        if len(filtered) == 0:
+            return OpStatus.FAILED, "No valid lines after filtering"
+        return OpStatus.SUCCESS, (rot_img, rot_mask, line_contours, filtered, page_angle)
+
+    # ---- stage 3 (inference.py:535-589) --------------------------------------------------
+    def apply_dewarping(self, rot_img, rot_mask, filtered_contours, page_angle, use_tps: bool = False,
+                        tps_threshold: float = 0.25):
+        import cv2
+
+        from .image_dewarping import apply_global_tps, check_for_tps
+        from .line_detection import build_raw_line_data, filter_line_contours
+
+        if not use_tps:
+            return OpStatus.SUCCESS, DewarpingResult(rot_img, rot_mask, filtered_contours, page_angle, False)
+        ratio, tps_line_data = check_for_tps(rot_img, filtered_contours)
+        if ratio <= tps_threshold:
+            return OpStatus.SUCCESS, DewarpingResult(rot_img, rot_mask, filtered_contours, page_angle, False,
+                                                     tps_ratio=ratio)
+        dew_img, dew_mask = apply_global_tps(rot_img, rot_mask, tps_line_data)
+        if dew_mask.ndim == 3:
+            dew_mask = cv2.cvtColor(dew_mask, cv2.COLOR_RGB2GRAY)
+        d_img, d_mask, contours, new_angle = build_raw_line_data(dew_img, dew_mask)
+        return OpStatus.SUCCESS, DewarpingResult(d_img, d_mask, filter_line_contours(d_mask, contours), new_angle,
+                                                 True, tps_ratio=ratio, dewarped_img=dew_img, dewarped_mask=dew_mask)
+
+    # ---- stage 4 (inference.py:591-616) --------------------------------------------------
+    def extract_lines(self, work_img, rot_mask, filtered_contours, merge_lines: bool = True, k_factor: float = 2.5,
+                      bbox_tolerance: float = 4.0):
+        from .line_detection import build_line_data, extract_line_images, sort_lines_by_threshold2
+
+        line_data = [build_line_data(c) for c in filtered_contours]
+        sorted_lines, _ = sort_lines_by_threshold2(rot_mask, line_data, group_lines=merge_lines)
+        line_images = extract_line_images(work_img, sorted_lines, k_factor, bbox_tolerance)
+        if not line_images:
+            return OpStatus.FAILED, "No valid line images extracted"
+        return OpStatus.SUCCESS, (sorted_lines, line_images)
+
+    # ---- stage 5 (inference.py:618-666) --------------------------------------------------
+    def _convert(self, pred: str, target_encoding) -> str:
+        if self.encoder == CharsetEncoder.WYLIE and target_encoding == Encoding.UNICODE:
+            return self.converter.toUnicode(pred)
+        if self.encoder == CharsetEncoder.STACK and target_encoding == Encoding.WYLIE:
+            return self.converter.toWylie(pred)
+        return pred
+
+    def run_text_recognition(self, line_images: list, sorted_lines: list, target_encoding: Encoding = Encoding.UNICODE):
+        """All non-empty lines of the page go through the recogniser as ONE batch."""
+        keep = [(img, ln) for img, ln in zip(line_images, sorted_lines) if img.shape[0] != 0 and img.shape[1] != 0]
+        texts = self.ocr_inference.run_batch([k[0] for k in keep], self.use_line_prepadding) if keep else []
+        ocr_lines = []
+        for (_, ln), t in zip(keep, texts):
+            pred = self._convert(t.strip().replace("§", " "), target_encoding)
+            ocr_lines.append(OCRLine(
+                guid=ln.guid, text=pred,
+                # (sic) the reference compares the enum with its name, so this is always UNICODE (:655-659)
+                encoding=Encoding.WYLIE.name if target_encoding == Encoding.WYLIE.name else Encoding.UNICODE.name,
+                ctc_conf=None, logits=None, lm_scores=None))
+        return OpStatus.SUCCESS, ocr_lines
+
+    # ---- whole page (inference.py:732-826) ------------------------------------------------
+    def run_ocr(self, image: np.ndarray, k_factor: float = 2.5, bbox_tolerance: float = 4.0, merge_lines: bool = True,
+                use_tps: bool = False, tps_threshold: float = 0.25, target_encoding: Encoding = Encoding.UNICODE,
+                eval_mode: bool = False):
+        try:
+            if not self.ready:
+                return OpStatus.FAILED, "OCR pipeline not ready"
+            if image is None:
+                return OpStatus.FAILED, "Input image is None"
+            if eval_mode:
+                return OpStatus.FAILED, "OCR processing failed: eval_mode (beam search) is not part of the B200 hot path"
+            try:
+                status, result = self.detect_lines(image)
+                if status == OpStatus.FAILED:
+                    return status, result
+                line_mask = result
+            except Exception as e:  # noqa: BLE001
+                return OpStatus.FAILED, f"Line detection failed: {str(e)}"
+            try:
+                status, result = self.build_lines(image, line_mask)
+                if status == OpStatus.FAILED:
+                    return status, result
+                rot_img, rot_mask, _, filtered_contours, page_angle = result
+            except Exception as e:  # noqa: BLE001
+                return OpStatus.FAILED, f"Line data building failed: {str(e)}"
+            try:
+                status, result = self.apply_dewarping(rot_img, rot_mask, filtered_contours, page_angle, use_tps=use_tps,
+                                                      tps_threshold=tps_threshold)
+                if status == OpStatus.FAILED:
+                    return status, result
+                dew = result
+            except Exception as e:  # noqa: BLE001
+                return OpStatus.FAILED, f"Line processing failed: {str(e)}"
+            try:
+                status, result = self.extract_lines(dew.work_img, rot_mask, dew.filtered_contours, merge_lines=merge_lines,
+                                                    k_factor=k_factor, bbox_tolerance=bbox_tolerance)
+                if status == OpStatus.FAILED:
+                    return status, result
+                sorted_lines, line_images = result
+            except Exception as e:  # noqa: BLE001
+                return OpStatus.FAILED, f"Line extraction failed: {str(e)}"
+            try:
+                status, result = self.run_text_recognition(line_images, sorted_lines, target_encoding=target_encoding)
+                if status == OpStatus.FAILED:
+                    return status, result
+                ocr_lines = result
+            except Exception as e:  # noqa: BLE001
+                return OpStatus.FAILED, f"OCR processing failed: {str(e)}"
+            return OpStatus.SUCCESS, [rot_mask, sorted_lines, ocr_lines, float(page_angle)]
+        except Exception as e:  # noqa: BLE001
+            return OpStatus.FAILED, f"OCR pipeline failed: {str(e)}"
+
+    def run_ocr_batch(self, images: Sequence[np.ndarray], **kw):
+        """Pages are independent units: same results as [run_ocr(i) for i in images]."""
+        return [self.run_ocr(img, **kw) for img in images]

@@ -1,0 +1,393 @@
+"""Drop-in for BDRC/line_detection.py.
+
+Host geometry (contours, rotation angle, reading-order sort: tens of contours per page) stays on
+the CPU with cv2, as SURVEY.md 8(a)-10 scopes it; everything that touches page-sized pixel data
+-- rotation (cv2.warpAffine), dilation, masking, row/column deletion and crop gathering -- runs
+in libbdrc_b200.so on the GPU.  Function names, arguments and return values follow the reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+from uuid import uuid1
+
+import cv2
+import numpy as np
+import torch
+
+from .data import BBox, Line
+
+# ------------------------------------------------------------------------------------------------
+# small host helpers (BDRC/line_detection.py:20-59)
+# ------------------------------------------------------------------------------------------------
+
+
+def generate_guid(clock_seq: int):
+    return uuid1(clock_seq=clock_seq)
+
+
+def get_contours(image: np.ndarray):
+    found, _ = cv2.findContours(image, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    return found
+
+
+def optimize_countour(cnt, e: float = 0.001):
+    return cv2.approxPolyDP(cnt, e * cv2.arcLength(cnt, True), True)
+
+
+def _engine():
+    from .inference import get_engine
+
+    return get_engine()
+
+
+# ------------------------------------------------------------------------------------------------
+# a-4 rotation (BDRC/line_detection.py:62-76, 107-142, 212-244)
+# ------------------------------------------------------------------------------------------------
+
+
+def rotate_from_angle(image: np.ndarray, angle: float) -> np.ndarray:
+    """cv2.warpAffine about the centre (bilinear, black border, same size) on the GPU."""
+    rows, cols = image.shape[:2]
+    M = cv2.getRotationMatrix2D((cols / 2, rows / 2), angle, 1)
+    eng = _engine()
+    src = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
+    return eng.warp_affine(src, M).cpu().numpy()
+
+
+def get_rotation_angle_from_lines(line_mask: np.ndarray, max_angle: float = 5.0, debug_angles: bool = False) -> float:
+    """Mean minAreaRect angle of the big blobs (> 0.1 % of the page), :107-142."""
+    blobs = [c for c in get_contours(line_mask) if cv2.contourArea(c) > line_mask.shape[0] * line_mask.shape[1] * 0.001]
+    angles = [cv2.minAreaRect(c)[2] for c in blobs]
+    low = [a for a in angles if abs(a) != 0.0 and a < max_angle]
+    high = [a for a in angles if abs(a) != 90.0 and a > (90 - max_angle)]
+    if debug_angles:
+        print(f"All Angles: {angles}")
+    if len(low) > len(high) and len(low) > 0:
+        return np.mean(low)
+    if len(high) > 0:
+        return -(90 - np.mean(high))
+    return 0
+
+
+def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold: float = 0.5):
+    """:212-244 -> (rotated image, rotated 3-channel mask, contours with area > 10, angle)."""
+    if line_mask.ndim == 3:
+        line_mask = cv2.cvtColor(line_mask, cv2.COLOR_BGR2GRAY)
+    angle = get_rotation_angle_from_lines(line_mask)
+    if angle > rot_threshold:
+        out_mask = rotate_from_angle(line_mask, angle)
+        out_img = rotate_from_angle(image, angle)
+    else:
+        out_mask, out_img = line_mask, image
+    contours = [c for c in get_contours(out_mask) if cv2.contourArea(c) > 10]
+    return out_img, cv2.cvtColor(out_mask, cv2.COLOR_GRAY2RGB), contours, angle
+
+
+def filter_line_contours(image: np.ndarray, line_contours, threshold: float = 0.01) -> list:
+    """:247-264: keep contours wider than `threshold` of the page and taller than 10 px."""
+    keep = []
+    for c in line_contours:
+        _, _, w, h = cv2.boundingRect(c)
+        if w > image.shape[1] * threshold and h > 10:
+            keep.append(c)
+    return keep
+
+
+def build_line_data(contour: np.ndarray, optimize: bool = True) -> Line:
+    """:188-209."""
+    if optimize:
+        contour = optimize_countour(contour)
+    x, y, w, h = cv2.boundingRect(contour)
+    return Line(generate_guid(clock_seq=23), contour, BBox(x, y, w, h), (x + (w // 2), y + (h // 2)))
+
+
+# ------------------------------------------------------------------------------------------------
+# a-10 reading order (BDRC/line_detection.py:362-634)
+# ------------------------------------------------------------------------------------------------
+
+
+def get_line_threshold(line_prediction: np.ndarray, slice_width: int = 20) -> float:
+    """:362-421: census of contours in vertical slices; median centre-y of the fullest slice // n."""
+    if line_prediction.ndim == 3:
+        line_prediction = cv2.cvtColor(line_prediction, cv2.COLOR_BGR2GRAY)
+    x, y, w, h = cv2.boundingRect(line_prediction)
+    x_steps = (w // slice_width) // 2
+    census = []
+    for step in range(1, x_steps + 1):
+        x0 = x + x_steps * step
+        found, _ = cv2.findContours(line_prediction[y:y + h, x0:x0 + slice_width], cv2.RETR_LIST,
+                                    cv2.CHAIN_APPROX_SIMPLE)
+        census.append((len(found), found))
+    if not census:
+        return 0.0
+    n, found = sorted(census, key=lambda t: t[0], reverse=True)[0]
+    if n == 0:
+        print("number of contours is 0")
+        return 0.0
+    centers = []
+    for c in found:
+        _, cy, _, ch = cv2.boundingRect(c)
+        centers.append(cy + (ch // 2))
+    return float(np.median(centers) // n) if centers else 0.0
+
+
+def sort_bbox_centers(bbox_centers: list[tuple[int, int]], line_threshold: float = 20) -> list:
+    """:424-486: greedy grouping by the running mean y of the current row; rows sorted by x;
+    the row list is returned reversed."""
+    if not bbox_centers:
+        return []
+    rows, cur = [], []
+    for c in bbox_centers:
+        if cur:
+            if abs(np.mean([p[1] for p in cur]) - c[1]) > line_threshold:
+                cur.sort(key=lambda p: p[0])
+                rows.append(cur.copy())
+                cur.clear()
+            cur.append(c)
+        else:
+            cur.append(c)
+    if cur:
+        rows.append(cur)
+    for r in rows:
+        r.sort(key=lambda p: p[0])
+    return list(reversed(rows))
+
+
+def group_line_chunks(sorted_bbox_centers, lines: list[Line], adaptive_grouping: bool = True) -> list[Line]:
+    """:489-548: rows with several chunks are merged into the convex hull of their contours."""
+    out = []
+    for centers in sorted_bbox_centers:
+        if len(centers) > 1:
+            stack = []
+            for c in centers:
+                for ln in lines:
+                    if c == ln.center:
+                        stack.append(ln.contour)
+                        break
+            hull = cv2.convexHull(np.vstack(stack))
+            x, y, w, h = cv2.boundingRect(hull)
+            out.append(Line(generate_guid(clock_seq=23), hull, BBox(x, y, w, h), (x + (w // 2), y + (h // 2))))
+        else:
+            for c in centers:
+                for ln in lines:
+                    if c == ln.center:
+                        out.append(ln)
+                        break
+    return out
+
+
+def sort_lines_by_threshold2(line_mask: np.ndarray, lines: list[Line], threshold: int = 20,
+                             calculate_threshold: bool = True, group_lines: bool = True):
+    """:594-634."""
+    thr = get_line_threshold(line_mask) if calculate_threshold else threshold
+    rows = sort_bbox_centers([ln.center for ln in lines], line_threshold=thr)
+    if group_lines:
+        return group_line_chunks(rows, lines), thr
+    out = []
+    for c in [p for r in rows for p in r]:
+        for ln in lines:
+            if c == ln.center:
+                out.append(ln)
+    return out, thr
+
+
+sort_lines_by_threshold = sort_lines_by_threshold2   # :551-591 is the same algorithm
+
+
+# ------------------------------------------------------------------------------------------------
+# a-5 per-line masked crops (BDRC/line_detection.py:79-104, 267-359) on the GPU
+# ------------------------------------------------------------------------------------------------
+
+
+class LineImages(list):
+    """list[np.ndarray] of crops that also remembers the packed device copy, so that
+    OCRPipeline.run_text_recognition does not upload them again."""
+
+    device_pack = None
+
+
+def _roi_mask(contour: np.ndarray, H: int, W: int):
+    """Filled contour rasterised into its (page-clipped) bounding box, as cv2.drawContours with
+    thickness=-1 does on the full page (line_detection.py:349-351)."""
+    x, y, w, h = cv2.boundingRect(contour)
+    x0, y0 = max(x, 0), max(y, 0)
+    x1, y1 = min(x + w, W), min(y + h, H)
+    if x1 <= x0 or y1 <= y0:
+        return (x0, y0, 0, 0), np.zeros((0, 0), np.uint8), h
+    m = np.zeros((y1 - y0, x1 - x0), np.uint8)
+    cv2.drawContours(m, [contour], -1, 255, -1, offset=(-x0, -y0))
+    return (x0, y0, x1 - x0, y1 - y0), m, h
+
+
+def _se_for(bbox_h: int, k: float):
+    """Structuring element of extract_line (:280-283); None where cv2 would raise."""
+    ks = int(bbox_h * k)
+    kh = int(ks * k)
+    return (ks, kh) if ks >= 1 and kh >= 1 else None
+
+
+def _extract_on_device(page_dev: torch.Tensor, rois, masks, bbox_hs, default_k: float, bbox_tolerance: float):
+    """The shrink-k search of get_line_image/extract_line_images (:291-359) for all lines of a page.
+
+    The candidate factors form ONE sequence k0, k0-0.1, ... shared by all lines (the adapted factor
+    carries over to the next line), so crop heights are evaluated on the GPU for a window of
+    candidates per line and the sequential decision is replayed on the host from those numbers.
+    Returns (chosen (kw,kh) or None per line, crops ...).
+    """
+    eng = _engine()
+    L = len(rois)
+    H, W, C = int(page_dev.shape[0]), int(page_dev.shape[1]), int(page_dev.shape[2]) if page_dev.dim() == 3 else 1
+    kseq = [default_k]
+    while len(kseq) < 64:
+        kseq.append(kseq[-1] - 0.1)
+    valid = [i for i in range(L) if rois[i][2] > 0 and rois[i][3] > 0]
+    pack = eng.pack_masks([masks[i] for i in valid], [rois[i] for i in valid]) if valid else None
+    vpos = {i: p for p, i in enumerate(valid)}
+    heights: dict[tuple[int, int], int] = {}
+    NC = 11
+
+    def fetch(from_line: int, cur: int):
+        todo = [i for i in valid if i >= from_line]
+        if not todo:
+            return
+        cand = []
+        for i in todo:
+            row = []
+            for j in range(cur, cur + NC):
+                se = _se_for(bbox_hs[i], kseq[j]) if j < len(kseq) else None
+                row.append(se if se else (1, 1))
+            cand.append(row)
+        hs = eng.line_crop_heights(page_dev, pack, [vpos[i] for i in todo], cand)
+        for r, i in enumerate(todo):
+            for c, j in enumerate(range(cur, cur + NC)):
+                heights[(i, j)] = int(hs[r, c])
+
+    def height(i: int, j: int):
+        """Crop height for line i at candidate j, or raises ValueError where cv2 would."""
+        if _se_for(bbox_hs[i], kseq[j]) is None:
+            raise ValueError("empty structuring element")
+        if i not in vpos:
+            return 0
+        if (i, j) not in heights:
+            fetch(i, j)
+        return heights[(i, j)]
+
+    chosen: list[tuple[int, int] | None] = [None] * L
+    cur = 0
+    for i in range(L):
+        j = cur
+        try:
+            hgt = height(i, j)
+            pick, attempts = j, 0
+            while hgt > bbox_hs[i] * bbox_tolerance and attempts < 10:
+                j += 1
+                if kseq[j] <= 0.1:
+                    break
+                hgt = height(i, j)
+                pick = j
+                attempts += 1
+            chosen[i] = _se_for(bbox_hs[i], kseq[pick])
+            if kseq[cur] != kseq[j]:
+                cur = j
+        except ValueError as e:   # the reference prints and returns a black fallback image (:322-327)
+            print(f"Error in get_line_image: {e}")
+            chosen[i] = None
+    real = [i for i in range(L) if chosen[i] is not None and i in vpos]
+    crops_dev = hw = off = None
+    if real:
+        crops_dev, hw, off = eng.extract_lines(page_dev, pack, [vpos[i] for i in real], [chosen[i] for i in real])
+    return chosen, real, crops_dev, hw, off, C
+
+
+def extract_line_images(image: np.ndarray, line_data: list[Line], default_k: float = 1.7,
+                        bbox_tolerance: float = 3, page_dev: torch.Tensor | None = None) -> LineImages:
+    """:330-359.  `page_dev` (optional) is the same image already resident on the GPU."""
+    eng = _engine()
+    if image.ndim == 2:
+        image = image[..., None]
+    if page_dev is None:
+        page_dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
+    H, W = image.shape[:2]
+    rois, masks, hs = [], [], []
+    for ln in line_data:
+        roi, m, h = _roi_mask(ln.contour, H, W)
+        rois.append(roi)
+        masks.append(m)
+        hs.append(h)
+    chosen, real, crops_dev, hw, off, C = _extract_on_device(page_dev, rois, masks, hs, default_k, bbox_tolerance)
+    out = LineImages()
+    host = {}
+    if real:
+        hw_h, off_h = hw.cpu().numpy(), off.cpu().numpy()
+        total = int(off_h[-1] + ((int(hw_h[-1, 0]) * int(hw_h[-1, 1]) * C + 15) // 16) * 16)
+        buf = crops_dev[:max(total, 1)].cpu().numpy()
+        for p, i in enumerate(real):
+            h, w = int(hw_h[p, 0]), int(hw_h[p, 1])
+            host[i] = buf[off_h[p]:off_h[p] + h * w * C].reshape(h, w, C).copy()
+        out.device_pack = (crops_dev, hw, off, real)
+    for i in range(len(line_data)):
+        if i in host:
+            out.append(host[i])
+        elif chosen[i] is None:
+            out.append(np.zeros((hs[i], hs[i] * 2, 3), np.uint8))     # fallback of :325-327
+        else:
+            out.append(np.zeros((0, 0, C), np.uint8))                 # nothing left after mask_n_crop
+    return out
+
+
+def mask_n_crop(image: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """:79-104 on the GPU: AND with the mask, delete rows/cols where any channel is all zero."""
+    eng = _engine()
+    image = image.astype(np.uint8)
+    if image.ndim == 2:
+        image = image[..., None]
+    C = image.shape[2]
+    ys, xs = np.nonzero(mask)
+    if len(ys) == 0:
+        return np.zeros((0, 0, C), np.uint8)
+    y0, y1, x0, x1 = ys.min(), ys.max() + 1, xs.min(), xs.max() + 1
+    page_dev = torch.from_numpy(np.ascontiguousarray(image)).to(eng.device)
+    pack = eng.pack_masks([np.ascontiguousarray(mask[y0:y1, x0:x1]).astype(np.uint8)], [(x0, y0, x1 - x0, y1 - y0)])
+    crops_dev, hw, off = eng.extract_lines(page_dev, pack, [0], [(1, 1)])
+    h, w = (int(v) for v in hw.cpu().numpy()[0])
+    return crops_dev[: h * w * C].cpu().numpy().reshape(h, w, C).copy()
+
+
+def extract_line(image: np.ndarray, mask: np.ndarray, bbox_h: int, k_factor: float = 1.2):
+    """:267-288 for one full-page mask."""
+    se = _se_for(bbox_h, k_factor)
+    if se is None:
+        raise ValueError("empty structuring element")
+    eng = _engine()
+    if image.ndim == 2:
+        image = image[..., None]
+    C = image.shape[2]
+    ys, xs = np.nonzero(mask)
+    if len(ys) == 0:
+        return np.zeros((0, 0, C), np.uint8)
+    y0, y1, x0, x1 = ys.min(), ys.max() + 1, xs.min(), xs.max() + 1
+    page_dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
+    pack = eng.pack_masks([np.ascontiguousarray(mask[y0:y1, x0:x1]).astype(np.uint8)], [(x0, y0, x1 - x0, y1 - y0)])
+    crops_dev, hw, off = eng.extract_lines(page_dev, pack, [0], [se])
+    h, w = (int(v) for v in hw.cpu().numpy()[0])
+    return crops_dev[: h * w * C].cpu().numpy().reshape(h, w, C).copy()
+
+
+def get_line_image(image: np.ndarray, mask: np.ndarray, bbox_h: int, bbox_tolerance: float = 2.5,
+                   k_factor: float = 1.2):
+    """:291-327 for one full-page mask -> (line image, adapted k)."""
+    try:
+        k = k_factor
+        img = extract_line(image, mask, bbox_h, k)
+        attempts = 0
+        while img.shape[0] > bbox_h * bbox_tolerance and attempts < 10:
+            k = k - 0.1
+            if k <= 0.1:
+                break
+            img = extract_line(image, mask, bbox_h, k)
+            attempts += 1
+        return img, k
+    except Exception as e:  # noqa: BLE001
+        print(f"Error in get_line_image: {e}")
+        return np.zeros((bbox_h, bbox_h * 2, 3), dtype=np.uint8), k_factor
