@@ -18,7 +18,7 @@ struct LinCoef {
 
 __device__ __forceinline__ LinCoef lin_coef(int d, int ssize, int dsize, bool vertical) {
   const double scale = 1.0 / ((double)dsize / (double)ssize);
-  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  float fx = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
   int sx = (int)floorf(fx);
   fx = fx - (float)sx;
   if (!vertical) {
@@ -30,6 +30,29 @@ __device__ __forceinline__ LinCoef lin_coef(int d, int ssize, int dsize, bool ve
   c.i1 = min(max(sx + 1, 0), ssize - 1);
   c.w0 = 1.0f - fx;
   c.w1 = fx;
+  return c;
+}
+
+// CV_64F variant: the fraction stays in double (see oracle/hostops.py:_linear_coefs_f64)
+struct LinCoef64 {
+  int i0, i1;
+  double f;
+};
+
+__device__ __forceinline__ LinCoef64 lin_coef64(int d, int ssize, int dsize, bool vertical) {
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  // explicit rn intrinsics: no FMA contraction, same roundings as the numpy oracle / OpenCV
+  double fx = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+  int sx = (int)floor(fx);
+  fx = fx - (double)sx;
+  if (!vertical) {
+    if (sx < 0) { fx = 0.0; sx = 0; }
+    if (sx >= ssize - 1) { fx = 0.0; sx = ssize - 1; }
+  }
+  LinCoef64 c;
+  c.i0 = min(max(sx, 0), ssize - 1);
+  c.i1 = min(max(sx + 1, 0), ssize - 1);
+  c.f = fx;
   return c;
 }
 
@@ -179,17 +202,37 @@ __global__ void seg_post_kernel(const PostParams p) {
   if (p.Hc == p.H0 && p.Wc == p.W0) {
     m = decide(p, y, x);
   } else {
-    // cv2.resize of the float64 {0,1} map then astype(u8): 1 only where the double-precision
-    // bilinear value reaches 1.0 (inference.py:148,180; oracle resize_linear_f64)
-    const LinCoef cx = lin_coef(x, p.Wc, p.W0, false), cy = lin_coef(y, p.Hc, p.H0, true);
-    const uint32_t m00 = decide(p, cy.i0, cx.i0), m01 = decide(p, cy.i0, cx.i1);
-    const uint32_t m10 = decide(p, cy.i1, cx.i0), m11 = decide(p, cy.i1, cx.i1);
-    m = 0;
-    for (int c = 0; c < p.C; ++c) {
-      const double r0 = (double)((m00 >> c) & 1) * (double)cx.w0 + (double)((m01 >> c) & 1) * (double)cx.w1;
-      const double r1 = (double)((m10 >> c) & 1) * (double)cx.w0 + (double)((m11 >> c) & 1) * (double)cx.w1;
-      const double v = r0 * (double)cy.w0 + r1 * (double)cy.w1;
-      m |= (v >= 1.0 ? 1u : 0u) << c;
+    // cv2.resize of the float64 {0,1} map then astype(u8) (inference.py:148,180): the bilinear
+    // value survives the truncating cast only where it is exactly 1, i.e. where every tap with a
+    // non-zero weight is 1.  cv2 keeps the fraction in double for CV_64F data
+    // (oracle/hostops.py:resize_linear_f64, pinned against cv2).
+    if (p.C == 1 || p.C == 3 || p.C == 4) {
+      // 1/3/4-channel CV_64F images take cv2's IPP route: double fraction, lerp form
+      const LinCoef64 cx = lin_coef64(x, p.Wc, p.W0, false), cy = lin_coef64(y, p.Hc, p.H0, true);
+      const uint32_t all = (1u << p.C) - 1u;
+      const uint32_t m00 = decide(p, cy.i0, cx.i0);
+      const uint32_t m01 = cx.f == 0.0 ? all : decide(p, cy.i0, cx.i1);
+      m = m00 & m01;
+      if (cy.f != 0.0) {
+        const uint32_t m10 = decide(p, cy.i1, cx.i0);
+        const uint32_t m11 = cx.f == 0.0 ? all : decide(p, cy.i1, cx.i1);
+        m &= m10 & m11;
+      }
+    } else {
+      // other channel counts (the 5-class layout map) take OpenCV's generic route: float32
+      // weights, double accumulation, value >= 1.0 survives the cast
+      const LinCoef cx = lin_coef(x, p.Wc, p.W0, false), cy = lin_coef(y, p.Hc, p.H0, true);
+      const uint32_t m00 = decide(p, cy.i0, cx.i0), m01 = decide(p, cy.i0, cx.i1);
+      const uint32_t m10 = decide(p, cy.i1, cx.i0), m11 = decide(p, cy.i1, cx.i1);
+      m = 0;
+      for (int c = 0; c < p.C; ++c) {
+        const double r0 = __dadd_rn(__dmul_rn((double)((m00 >> c) & 1), (double)cx.w0),
+                                    __dmul_rn((double)((m01 >> c) & 1), (double)cx.w1));
+        const double r1 = __dadd_rn(__dmul_rn((double)((m10 >> c) & 1), (double)cx.w0),
+                                    __dmul_rn((double)((m11 >> c) & 1), (double)cx.w1));
+        const double v = __dadd_rn(__dmul_rn(r0, (double)cy.w0), __dmul_rn(r1, (double)cy.w1));
+        m |= (v >= 1.0 ? 1u : 0u) << c;
+      }
     }
   }
   uint8_t* o = p.mask + ((size_t)y * p.W0 + x) * p.C;

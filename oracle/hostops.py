@@ -116,25 +116,55 @@ def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return out[..., 0] if squeeze else out
 
 
+def _linear_coefs_f64(ssize: int, dsize: int, vertical: bool):
+    """cv2.resize on CV_64F data keeps the interpolation fraction in double precision (measured:
+    cv2 4.13 agrees with a double-fraction lerp to 1e-14 and disagrees with float32 weights at 1e-5)."""
+    scale = 1.0 / (np.float64(dsize) / np.float64(ssize))
+    d = np.arange(dsize, dtype=np.float64)
+    fx = (d + 0.5) * scale - 0.5
+    sx = np.floor(fx).astype(np.int64)
+    fx = fx - sx
+    if not vertical:
+        lo = sx < 0
+        fx[lo] = 0
+        sx[lo] = 0
+        hi = sx >= ssize - 1
+        fx[hi] = 0
+        sx[hi] = ssize - 1
+    return np.clip(sx, 0, ssize - 1), np.clip(sx + 1, 0, ssize - 1), fx
+
+
 def resize_linear_f64(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
-    """cv2.resize(src float64, (dw, dh)) -- the call in Detection._crop_prediction
-    (inference.py:148): float32 weights, double accumulation, no rounding."""
+    """cv2.resize(float64 {0,1} map, (dw, dh)) FOLLOWED BY astype(uint8) -- the pair of calls in
+    Detection._crop_prediction + predict (inference.py:148, 180).  Returned as float64 {0., 1.}.
+
+    The bilinear value of a {0,1} map reaches 1.0 (and survives the truncating cast) exactly when
+    every tap with a non-zero weight is 1:  v = s0 + (s1 - s0) * f  is 1 iff s0 == 1 and
+    (s1 == 1 or f == 0), horizontally then vertically.  Pinned bit-exact against cv2 on 20 M pixels
+    (tests/test_oracle_closed_forms.py)."""
     squeeze = src.ndim == 2
     if squeeze:
         src = src[..., None]
-    H, W = src.shape[:2]
+    H, W, C = src.shape
     if (dw, dh) == (W, H):
-        out = src.astype(np.float64).copy()
-    elif W == 2 * dw and H == 2 * dh:
-        s = src.astype(np.float64)
-        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2]) * 0.25
+        out = (src >= 1.0)
+    elif C in (1, 3, 4):
+        # cv2's IPP route for 1/3/4-channel CV_64F images: double fraction, lerp form
+        x0, x1, fx = _linear_coefs_f64(W, dw, False)
+        y0, y1, fy = _linear_coefs_f64(H, dh, True)
+        b = src >= 1.0
+        row_one = b[:, x0, :] & (b[:, x1, :] | (fx == 0)[None, :, None])
+        out = row_one[y0] & (row_one[y1] | (fy == 0)[:, None, None])
     else:
+        # other channel counts (the 5-class layout map): OpenCV's generic route -- float32 weights,
+        # double accumulation; the value must reach 1.0 to survive the truncating cast
         x0, x1, a0, a1 = _linear_coefs(W, dw, False)
         y0, y1, b0, b1 = _linear_coefs(H, dh, True)
         s = src.astype(np.float64)
-        rows = s[:, x0, :] * a0.astype(np.float64)[None, :, None] + \
-            s[:, x1, :] * a1.astype(np.float64)[None, :, None]
-        out = rows[y0] * b0.astype(np.float64)[:, None, None] + rows[y1] * b1.astype(np.float64)[:, None, None]
+        rows = s[:, x0, :] * a0.astype(np.float64)[None, :, None] + s[:, x1, :] * a1.astype(np.float64)[None, :, None]
+        v = rows[y0] * b0.astype(np.float64)[:, None, None] + rows[y1] * b1.astype(np.float64)[:, None, None]
+        out = v >= 1.0
+    out = out.astype(np.float64)
     return out[..., 0] if squeeze else out
 
 

@@ -1,0 +1,110 @@
+"""Host-side logic of the product package on CPU: geometry mirror vs the oracle, size clamps,
+page sharding over a world_size-2 gloo group."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ocr_inference_b200 import engine as E
+from ocr_inference_b200 import line_detection as ld
+from ocr_inference_b200 import sharding, synthetic
+from oracle import geometry as og
+from oracle import hostops as ho
+
+
+@pytest.mark.parametrize("hw", [(2048, 3072), (472, 2550), (3300, 2550), (700, 4600), (400, 1500), (512, 512), (600, 4096)])
+def test_clamp_sizes_match_oracle(hw):
+    assert E.clamp_size(*hw) == ho.clamp_size(*hw)
+    chw = np.zeros((3, *hw), np.uint8)
+    _, meta = ho.torch_path_pre(chw)
+    assert E.clamp_size_torch(*hw) == (meta["Hc"], meta["Wc"])
+
+
+def test_host_geometry_mirror_matches_oracle():
+    page, boxes = synthetic.page(700, 800, 1200)
+    mask = synthetic.band_mask(boxes, 800, 1200)
+    mask[300:340, 580:620] = 0          # split one band into two chunks -> exercises the hull merge
+    img, rot_mask, contours, angle = ld.build_raw_line_data(page, mask)
+    o_img, o_mask, o_contours, o_angle = og.build_raw_line_data(page, mask)
+    assert angle == o_angle and np.array_equal(rot_mask, o_mask) and len(contours) == len(o_contours)
+    filt = ld.filter_line_contours(rot_mask, contours)
+    assert len(filt) == len(og.filter_line_contours(o_mask, o_contours))
+    lines = [ld.build_line_data(c) for c in filt]
+    got, thr = ld.sort_lines_by_threshold2(rot_mask, lines, group_lines=True)
+    want, othr = og.sort_lines(o_mask, [og.build_line(c) for c in filt], True)
+    assert thr == othr and len(got) == len(want) < len(lines)
+    assert [g.center for g in got] == [w.center for w in want]
+    assert [(g.bbox.x, g.bbox.y, g.bbox.w, g.bbox.h) for g in got] == [w.bbox for w in want]
+    assert all(np.array_equal(g.contour, w.contour) for g, w in zip(got, want))
+    flat, _ = ld.sort_lines_by_threshold2(rot_mask, lines, group_lines=False)
+    oflat, _ = og.sort_lines(o_mask, [og.build_line(c) for c in filt], False)
+    assert [g.center for g in flat] == [w.center for w in oflat]
+
+
+def test_sort_bbox_centers_edge_cases():
+    assert ld.sort_bbox_centers([]) == []
+    c = [(50, 10), (10, 12), (30, 60), (5, 58), (7, 120)]
+    assert ld.sort_bbox_centers(c, 20) == og.sort_centers(c, 20) == [[(7, 120)], [(5, 58), (30, 60)], [(10, 12), (50, 10)]]
+
+
+def test_roi_mask_equals_full_page_fill():
+    page, boxes = synthetic.page(9, 400, 600)
+    mask = synthetic.band_mask(boxes, 400, 600)
+    cs, _ = cv2.findContours(mask, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    for c in cs:
+        c = ld.optimize_countour(c)
+        full = np.zeros((400, 600), np.uint8)
+        cv2.drawContours(full, [c], -1, (255, 255, 255), -1)
+        (x, y, w, h), roi, bh = ld._roi_mask(c, 400, 600)
+        assert bh == cv2.boundingRect(c)[3]
+        assert np.array_equal(full[y:y + h, x:x + w], roi)
+        assert full.sum() == roi.sum()
+
+
+def test_se_for_matches_reference_arithmetic():
+    for h in (11, 37, 60, 140):
+        for k in (2.5, 2.4, 1.7, 0.3, 0.1):
+            ks = int(h * k)
+            se = ld._se_for(h, k)
+            assert se == ((ks, int(ks * k)) if ks >= 1 and int(ks * k) >= 1 else None)
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 16, 10000):
+        for world in (1, 2, 3, 8):
+            got = [i for r in range(world) for i in sharding.shard_range(n, world, r)]
+            assert got == list(range(n))
+            sizes = [len(sharding.shard_range(n, world, r)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = sharding.run_sharded(11, lambda i: i * 10, lambda pages: [(p, rank) for p in pages], chunk=4)
+        if rank == 0:
+            q.put(res)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_page_sharding_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [i * 10 for i in range(11)]
+    assert [r[1] for r in res] == [0] * 5 + [1] * 6
