@@ -131,6 +131,12 @@ int conv_simt_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cud
 int conv_launch(bdrc_ctx* ctx, const char* name, const ConvWeights& w, const ConvArgs& a,
                 cudaStream_t s) {
   const double flops = 2.0 * a.N * a.Hout * a.Wout * (double)w.Cout * w.R * w.S * w.Cin;
+  char label[160];
+  if (ctx->profile) {
+    snprintf(label, sizeof(label), "%s %d->%d @%dx%d k%dx%d s%d d%d", name, w.Cin, w.Cout, a.Hout, a.Wout, w.R, w.S,
+             a.stride_w, a.dil_w);
+    name = label;
+  }
   int rc;
   if (ctx->conv_engine == 0 && conv_tc_supported(w, a)) {
     bdrc_prof_begin(ctx, name, flops, s);

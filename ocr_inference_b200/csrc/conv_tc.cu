@@ -14,8 +14,10 @@
 //   D         :  fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of
 //                tile i overlaps the MMAs of tile i+1.
 //   Roles     :  warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-//                allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/residual/ReLU ->
-//                bf16 NHWC).  Persistent grid, one CTA per SM, static round-robin tile schedule.
+//                allocator, warps 4..11 = epilogue (TMEM -> registers -> bias/residual/ReLU ->
+//                bf16 NHWC; lane quarter x column half per warp).  Persistent grid, one CTA per SM, static round-robin tile schedule.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -23,13 +25,15 @@ namespace {
 constexpr int BM = 128;          // pixels per tile (UMMA M, cta_group::1)
 constexpr int BK = 64;           // channels per K step: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_G = 4;           // pixel tiles per super tile (interleaved accumulators)
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t OUT_STAGE_BYTES = BM * 128;     // epilogue staging: 128 rows x 64 bf16
 
 struct TcParams {
   int tiles_n, tiles_w, tiles_h, n_img, total_tiles;
-  int BW, BH, BN, stages;
+  int BW, BH, BN, stages, G;
   int R, S, kchunks;
   int stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   int par_c;                       // channel offset of the odd-w pixel in the folded view
@@ -41,8 +45,10 @@ struct TcParams {
   const bf16* residual;
   int res_ld;
   void* out;
-  int out_ld, out_coff, out_fp32, relu;
+  int out_ld, out_coff, out_fp32, relu, out_tma;
   int* errflag;
+  int dbg_skip;   // timing experiments only -- bit 0: skip A loads, 1: skip B loads, 2: skip epilogue math + I/O,
+                  // 3: skip the TMA stores, 4: skip the residual loads
 };
 
 // ---------------------------------------------------------------------------------------
@@ -147,6 +153,18 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return d;
 }
 
+// one lane of a fully converged warp; warp-uniform control flow lets ptxas keep descriptors and
+// barrier addresses in uniform registers (no per-instruction R2UR / ELECT loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
@@ -155,15 +173,31 @@ __device__ __forceinline__ int floordiv(int a, int b) {
 // ---------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------
+// A CTA works on "super tiles": G consecutive 128-pixel tiles x one BN-column tile.  The G pixel
+// tiles share one B (weight) tile per K step and own G independent TMEM accumulators; their MMAs
+// are issued interleaved (k-step outer, tile inner), so that back-to-back tcgen05.mma instructions
+// never accumulate into the same TMEM columns (a dependent accumulate costs ~130 cycles on the
+// tensor pipe whatever N is: measured, see profiles/README.md).  G = 4/2/1 for BN <= 64/128/256.
+__device__ __forceinline__ void decode_mtile(const TcParams& p, int mt, int& img, int& oy0, int& ox0) {
+  const int wt = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int ht = mt % p.tiles_h;
+  img = mt / p.tiles_h;
+  ox0 = wt * p.BW;
+  oy0 = ht * p.BH;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
+  const int G = p.G;
   const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 2;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const uint32_t a_bytes = (uint32_t)G * A_STAGE_BYTES;
+  const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -185,7 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[i]), 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -203,17 +237,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   const int k_iters = p.R * p.S * p.kchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) ==========
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % p.tiles_n; t /= p.tiles_n;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h;
-        const int img = t / p.tiles_h;
-        const int ox0 = wt * p.BW, oy0 = ht * p.BH, n0 = nt * p.BN;
+      for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
+        const int nt = st % p.tiles_n;
+        const int mg = st / p.tiles_n;
+        const int n0 = nt * p.BN;
+        int img[MAX_G], oy0[MAX_G], ox0[MAX_G];
+#pragma unroll
+        for (int g = 0; g < MAX_G; ++g)
+          if (g < G) decode_mtile(p, mg * G + g, img[g], oy0[g], ox0[g]);
         for (int r = 0; r < p.R; ++r) {
           const int th = r * p.dil_h - p.pad_h;
           const int par_h = ((th % p.stride_h) + p.stride_h) % p.stride_h;
@@ -225,12 +260,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             for (int kc = 0; kc < p.kchunks; ++kc) {
               mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.errflag, 1);
               const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_arrive_expect_tx(fb, stage_bytes);
               const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-              tma_load_5d(a_dst, &tmapA, fb, par_w * p.par_c + kc * BK, ox0 + off_w, par_h,
-                          oy0 + off_h, img);
-              tma_load_2d(a_dst + A_STAGE_BYTES, &tmapB, fb,
-                          ((r * p.S + s) * p.kchunks + kc) * BK, n0);
+              const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : a_bytes) + ((p.dbg_skip & 2) ? 0u : b_stage_bytes);
+              if (elect_one()) {
+                if (bytes) mbar_arrive_expect_tx(fb, bytes); else mbar_arrive(fb);
+                if (!(p.dbg_skip & 1)) {
+#pragma unroll
+                  for (int g = 0; g < MAX_G; ++g)
+                    if (g < G)
+                      tma_load_5d(a_dst + (uint32_t)g * A_STAGE_BYTES, &tmapA, fb, par_w * p.par_c + kc * BK,
+                                  ox0[g] + off_w, par_h, oy0[g] + off_h, img[g]);
+                }
+                if (!(p.dbg_skip & 2))
+                  tma_load_2d(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
+              }
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -238,61 +282,122 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) ============
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G * p.BN);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(smem_u32(&full_bar[stage]), phase, p.errflag, 3);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_sdesc(a_addr);
-          const uint64_t bdesc = make_sdesc(a_addr + A_STAGE_BYTES);
+          const uint64_t bdesc = make_sdesc(a_addr + a_bytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in 16-B units
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                        (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in 16-B units
+#pragma unroll
+              for (int g = 0; g < MAX_G; ++g)
+                if (g < G)
+                  tc_mma_bf16(d_tmem + (uint32_t)(g * p.BN),
+                              make_sdesc(a_addr + (uint32_t)g * A_STAGE_BYTES) + (uint64_t)(2 * k),
+                              bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(smem_u32(&empty_bar[stage]));   // frees the smem slot when the MMAs retire
           }
-          tc_commit(smem_u32(&empty_bar[stage]));   // frees the smem slot when the MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));       // accumulator complete -> epilogue
+        if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));   // accumulators complete -> epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int wrank = warp & 3;                // TMEM lane quarter this warp may access
+    // 8 warps in two groups of 4 (warp % 4 = TMEM lane quarter, hardware rule).  The work of one
+    // super tile is a list of units (pixel tile g, 64-column group j), dealt round-robin to the two
+    // groups.  bf16 outputs are staged in shared memory in the SWIZZLE_128B layout and written with
+    // one TMA tensor store per unit (full 128-byte lines; a 16-bytes-per-thread direct store pattern
+    // cost 2x the MMA time: measured).  The residual of this thread's rows is prefetched into
+    // registers BEFORE waiting for the accumulators.
+    const int wrank = warp & 3;
+    const int egrp = (warp - 4) >> 2;
+    const int ngrp64 = (p.BN + 63) / 64;
+    const int units = G * ngrp64;              // <= 4 by construction (host)
     const int m = wrank * 32 + lane;           // row of the tile = pixel
     const int hl = m / p.BW, wl = m % p.BW;
+    const bool res_vec = p.residual != nullptr && (p.res_ld & 7) == 0;
+    const bool issuer = (threadIdx.x == 128 + 128 * egrp);
+    uint8_t* stage_out = smem + (size_t)p.stages * stage_bytes + 1024 + (size_t)egrp * 2 * OUT_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int nt = t % p.tiles_n; t /= p.tiles_n;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h;
-      const int img = t / p.tiles_h;
-      const int ox = wt * p.BW + wl, oy = ht * p.BH + hl, n0 = nt * p.BN;
-      const bool valid = (ox < p.Wout) && (oy < p.Hout);
-      const size_t pix = ((size_t)img * p.Hout + oy) * p.Wout + ox;
-      const float* bias = p.bias + (size_t)img * p.bias_img_stride + n0;
+    uint32_t use = 0;                          // staging buffer toggle
+    for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
+      const int nt = st % p.tiles_n;
+      const int mg = st / p.tiles_n;
+      const int n0 = nt * p.BN;
+      // this group's units: u = egrp, egrp + 2  ->  local index ul = 0, 1
+      size_t pix[2];
+      bool valid[2];
+      int imgs[2], oxs[2], oys[2], cg0[2];
+#pragma unroll
+      for (int ul = 0; ul < 2; ++ul) {
+        const int u = egrp + 2 * ul;
+        pix[ul] = 0; valid[ul] = false; imgs[ul] = 0; oxs[ul] = 0; oys[ul] = 0; cg0[ul] = 0;
+        if (u < units) {
+          const int g = u / ngrp64;
+          cg0[ul] = (u - g * ngrp64) * 64;
+          int img, oy0, ox0;
+          decode_mtile(p, mg * G + g, img, oy0, ox0);
+          const int ox = ox0 + wl, oy = oy0 + hl;
+          valid[ul] = (ox < p.Wout) && (oy < p.Hout);
+          pix[ul] = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+          imgs[ul] = img; oxs[ul] = ox0; oys[ul] = oy0;
+        }
+      }
+      uint4 rres[16];
+      if (res_vec && !(p.dbg_skip & (4 | 16))) {
+#pragma unroll
+        for (int ul = 0; ul < 2; ++ul) {
+          if (egrp + 2 * ul < units && valid[ul]) {
+            const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + cg0[ul];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (n0 + cg0[ul] + q * 8 + 8 <= p.Cout)
+                rres[ul * 8 + q] = *reinterpret_cast<const uint4*>(rp + q * 8);   // plain load: may alias out
+          }
+        }
+      }
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(taddr + (uint32_t)c0, v);
-        tc_wait_ld();
-        if (valid && n0 + c0 < p.Cout) {
+      const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * G * p.BN);
+#pragma unroll
+      for (int ul = 0; ul < 2; ++ul) {
+        const int u = egrp + 2 * ul;
+        if (u >= units) break;
+        const int g = u / ngrp64;
+        uint8_t* sbuf = stage_out + (size_t)(use & 1) * OUT_STAGE_BYTES;
+        if (p.out_tma) {
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+        }
+        const float* bias = p.bias + (size_t)imgs[ul] * p.bias_img_stride + n0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = cg0[ul] + q * 16;
+          if (c0 >= p.BN) break;
+          uint32_t v[16];
+          tc_ld16(tbase + (uint32_t)(g * p.BN + c0), v);
+          tc_wait_ld();
+          if (p.dbg_skip & 4) continue;
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -302,52 +407,74 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
             f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
-          const bool full16 = (n0 + c0 + 16 <= p.Cout);
-          if (p.residual) {
-            const bf16* rp = p.residual + pix * p.res_ld + n0 + c0;
-            if (full16 && (p.res_ld & 7) == 0) {
-              // plain loads: the residual may alias the output (in-place shortcut add)
-              const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          if (p.residual && valid[ul]) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                f[2 * j] += __low2float(h);
-                f[2 * j + 1] += __high2float(h);
+            for (int hq = 0; hq < 2; ++hq) {
+              if (res_vec && n0 + c0 + hq * 8 + 8 <= p.Cout) {
+                const uint4 rv = rres[ul * 8 + q * 2 + hq];
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                  f[hq * 8 + 2 * j] += __low2float(h);
+                  f[hq * 8 + 2 * j + 1] += __high2float(h);
+                }
+              } else {
+                const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + c0 + hq * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)   // static indices only: keeps f[] in registers
+                  if (n0 + c0 + hq * 8 + j < p.Cout) f[hq * 8 + j] += __bfloat162float(rp[j]);
               }
-            } else {
-              for (int j = 0; j < 16 && n0 + c0 + j < p.Cout; ++j) f[j] += __bfloat162float(rp[j]);
             }
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (p.out_fp32) {
-            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + p.out_coff + n0 + c0;
-            if (full16 && ((p.out_ld | p.out_coff) & 3) == 0) {
+          if (p.out_tma) {
+            uint32_t w[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 16 && n0 + c0 + j < p.Cout; ++j) op[j] = f[j];
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&h);
             }
-          } else {
-            bf16* op = reinterpret_cast<bf16*>(p.out) + pix * p.out_ld + p.out_coff + n0 + c0;
-            if (full16 && ((p.out_ld | p.out_coff) & 7) == 0) {
-              uint32_t w[8];
+            // row m, 16-byte chunks 2q and 2q+1 of the 128-byte row, XOR-swizzled with (m & 7)
+            uint8_t* rowp = sbuf + (size_t)m * 128;
+            *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else if (valid[ul] && n0 + c0 < p.Cout) {
+            const bool full16 = (n0 + c0 + 16 <= p.Cout);
+            if (p.out_fp32) {
+              float* op = reinterpret_cast<float*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
+              if (full16 && ((p.out_ld | p.out_coff) & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c0 + j < p.Cout) op[j] = f[j];
               }
-              *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
-              *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
             } else {
-              for (int j = 0; j < 16 && n0 + c0 + j < p.Cout; ++j) op[j] = __float2bfloat16(f[j]);
+              bf16* op = reinterpret_cast<bf16*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < p.Cout) op[j] = __float2bfloat16(f[j]);
             }
           }
+        }
+        if (p.out_tma) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+          if (issuer && !(p.dbg_skip & (4 | 8))) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tmapO)), "r"(smem_u32(sbuf)), "r"(n0 + cg0[ul]), "r"(oxs[ul]),
+                "r"(oys[ul]), "r"(imgs[ul])
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++use;
         }
       }
       tc_fence_before();
@@ -355,6 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -389,7 +517,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 struct TcPlan {
-  int BW, BH, BN, tiles_w, tiles_h, tiles_n, stages;
+  int BW, BH, BN, tiles_w, tiles_h, tiles_n, stages, G;
   uint32_t tmem_cols;
   size_t smem_bytes;
 };
@@ -420,15 +548,27 @@ bool make_plan(const ConvWeights& w, const ConvArgs& a, TcPlan* pl) {
     pl->BN = 128;
   }
   pl->tiles_n = ceil_div(w.Cout_pad, pl->BN);
+  // pixel tiles per super tile: as many as TMEM (2 buffers x G x BN <= 512 columns), the epilogue's
+  // 4-unit budget (G x ceil(BN/64) <= 4) and divisibility of the pixel-tile count allow
+  const long long m_tiles = (long long)pl->tiles_w * pl->tiles_h * a.N;
+  int G = 1;
+  for (int g = MAX_G; g >= 1; g >>= 1)
+    if (2 * g * pl->BN <= 512 && g * ((pl->BN + 63) / 64) <= 4 && m_tiles % g == 0) { G = g; break; }
+  if (const char* e = getenv("BDRC_TC_G")) {
+    const int want = atoi(e);
+    if (want >= 1 && want <= G && m_tiles % want == 0) G = want;
+  }
+  pl->G = G;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * pl->BN)) cols <<= 1;
+  while (cols < (uint32_t)(2 * G * pl->BN)) cols <<= 1;
   pl->tmem_cols = cols;
-  const size_t stage_bytes = A_STAGE_BYTES + (size_t)pl->BN * BK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t stage_bytes = (size_t)G * A_STAGE_BYTES + (size_t)pl->BN * BK * 2;
+  const size_t out_stage = a.out_fp32 ? 0 : 4 * (size_t)OUT_STAGE_BYTES;   // 2 groups x 2 buffers
+  int stages = (int)((224 * 1024 - out_stage) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return false;
   pl->stages = stages;
-  pl->smem_bytes = 1024 + stages * stage_bytes + 256;
+  pl->smem_bytes = 1024 + stages * stage_bytes + 1024 + out_stage;
   return true;
 }
 
@@ -475,10 +615,26 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
       return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
 
+  CUtensorMap mapO = mapB;
+  const int out_tma = (!a.out_fp32 && a.out_ld % 8 == 0 && a.out_coff % 8 == 0) ? 1 : 0;
+  if (out_tma) {
+    const cuuint64_t ld = (cuuint64_t)a.out_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)w.Cout, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)pl.BW, (cuuint32_t)pl.BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    void* base = reinterpret_cast<bf16*>(a.out) + a.out_coff;
+    CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+  }
+
   TcParams p;
   p.tiles_n = pl.tiles_n; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_img = a.N;
-  p.total_tiles = pl.tiles_n * pl.tiles_w * pl.tiles_h * a.N;
-  p.BW = pl.BW; p.BH = pl.BH; p.BN = pl.BN; p.stages = pl.stages;
+  p.total_tiles = pl.tiles_n * ((pl.tiles_w * pl.tiles_h * a.N) / pl.G);   // super tiles
+  p.BW = pl.BW; p.BH = pl.BH; p.BN = pl.BN; p.stages = pl.stages; p.G = pl.G;
   p.R = w.R; p.S = w.S; p.kchunks = w.Cin_pad / BK;
   p.stride_h = sh; p.stride_w = sw; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
   p.dil_h = a.dil_h; p.dil_w = a.dil_w;
@@ -493,16 +649,21 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
   p.residual = a.residual; p.res_ld = a.res_ld;
   p.out = a.out; p.out_ld = a.out_ld; p.out_coff = a.out_coff; p.out_fp32 = a.out_fp32;
   p.relu = a.relu;
+  p.out_tma = out_tma;
   p.errflag = ctx->d_errflag;
+  {
+    const char* e = getenv("BDRC_DBG_SKIP");
+    p.dbg_skip = e ? atoi(e) : 0;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
     BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        220 * 1024));
+                                        226 * 1024));
     attr_set = true;
   }
   int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-  conv_tc_kernel<<<grid, NUM_THREADS, pl.smem_bytes, s>>>(mapA, mapB, p);
+  conv_tc_kernel<<<grid, NUM_THREADS, pl.smem_bytes, s>>>(mapA, mapB, mapO, p);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

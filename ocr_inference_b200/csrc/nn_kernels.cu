@@ -167,6 +167,128 @@ __global__ void depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_
   *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * out_ld + out_coff + c8 * 8) = pack8(acc);
 }
 
+// dilation-1 variant: each thread walks a vertical strip of DW_STRIP output rows for 8 channels,
+// keeping the three live input rows in registers (3 loads per output instead of 9)
+constexpr int DW_STRIP = 8;
+__global__ void __launch_bounds__(256)
+depthwise_strip_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int H, int W, int C,
+                       const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff) {
+  const int C8 = C / 8;
+  const int strips = (H + DW_STRIP - 1) / DW_STRIP;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * strips * W * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  size_t p = idx / C8;
+  const int x = (int)(p % W); p /= W;
+  const int st = (int)(p % strips);
+  const int n = (int)(p / strips);
+  const bf16* base = in + (size_t)n * H * W * in_ld + in_coff + c8 * 8;
+  const float* wb = w9c + c8 * 8;
+  // the live 3x3 window stays packed (bf16) in registers; weights come from L1 on use
+  auto load_row = [&](int iy, uint4* row) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = x + s - 1;
+      row[s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                   ? __ldg(reinterpret_cast<const uint4*>(base + ((size_t)iy * W + ix) * in_ld))
+                   : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 r0[3], r1[3], r2[3];
+  const int y0 = st * DW_STRIP;
+  load_row(y0 - 1, r0);
+  load_row(y0, r1);
+  for (int i = 0; i < DW_STRIP; ++i) {
+    const int y = y0 + i;
+    if (y >= H) break;
+    load_row(y + 1, r2);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const uint4* row = r == 0 ? r0 : (r == 1 ? r1 : r2);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        float f[8];
+        unpack8(row[s], f);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wb + (r * 3 + s) * C));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wb + (r * 3 + s) * C + 4));
+        acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+        acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+        acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+        acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * out_ld + out_coff + c8 * 8) = pack8(acc);
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { r0[s] = r1[s]; r1[s] = r2[s]; }
+  }
+}
+
+// x4 (or xf) align_corners=True upsample, strip variant: each thread produces UP_STRIP consecutive
+// output rows of one column for 8 channels and re-loads a low-res row pair only when it changes
+constexpr int UP_STRIP = 8;
+__global__ void __launch_bounds__(256)
+upsample_ac_strip_kernel(const bf16* __restrict__ in, int N, int H, int W, int C, int f, bf16* __restrict__ out,
+                         int out_ld, int out_coff) {
+  const int Ho = H * f, Wo = W * f, C8 = C / 8;
+  const int strips = (Ho + UP_STRIP - 1) / UP_STRIP;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * strips * Wo * C8;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  size_t p = idx / C8;
+  const int x = (int)(p % Wo); p /= Wo;
+  const int st = (int)(p % strips);
+  const int n = (int)(p / strips);
+  const float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
+  const float fx = sx * (float)x;
+  const int x0 = (int)fx, x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+  const bf16* b = in + (size_t)n * H * W * C + c8 * 8;
+  int cy0 = -1, cy1 = -1;
+  float a0[8], a1[8];   // horizontally interpolated low-res rows cy0 / cy1
+  auto hrow = [&](int yy, float* dst) {
+    float v0[8], v1[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)yy * W + x0) * C)), v0);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)yy * W + x1) * C)), v1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = lx0 * v0[j] + lx1 * v1[j];
+  };
+#pragma unroll
+  for (int i = 0; i < UP_STRIP; ++i) {
+    const int y = st * UP_STRIP + i;
+    if (y >= Ho) break;
+    const float fy = sy * (float)y;
+    const int y0 = (int)fy, y1 = y0 + (y0 < H - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+    if (y0 != cy0) {
+      if (y0 == cy1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[j] = a1[j];
+      } else {
+        hrow(y0, a0);
+      }
+      cy0 = y0;
+    }
+    if (y1 != cy1) {
+      if (y1 == cy0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a1[j] = a0[j];
+      } else {
+        hrow(y1, a1);
+      }
+      cy1 = y1;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = ly0 * a0[j] + ly1 * a1[j];
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + y) * Wo + x) * out_ld + out_coff + c8 * 8) = pack8(r);
+  }
+}
+
 // align_corners=True bilinear, fp32 math in torch's operand order (UpSampleBilinear2d)
 __global__ void upsample_ac_kernel(const bf16* __restrict__ in, int N, int H, int W, int C, int f,
                                    bf16* __restrict__ out, int out_ld, int out_coff) {
@@ -218,7 +340,7 @@ __global__ void upsample_logits_kernel(const float* __restrict__ in, int N, int 
 }
 
 // one CTA per image: mean over HW -> 1x1 conv + ReLU -> tail of the projection conv
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 aspp_pool_bias_kernel(const bf16* __restrict__ x, int HW, int Cin, const float* __restrict__ Wp,
                       const float* __restrict__ bp, int Cmid, const float* __restrict__ Wtail,
                       const float* __restrict__ bproj, int Cout, int Cout_pad,
@@ -226,12 +348,34 @@ aspp_pool_bias_kernel(const bf16* __restrict__ x, int HW, int Cin, const float* 
   extern __shared__ float pb_smem[];
   float* g = pb_smem;          // [Cin]
   float* h = pb_smem + Cin;    // [Cmid]
+  float* part = h + Cmid;      // [slices][Cin] partial sums
   const int n = blockIdx.x;
   const bf16* xb = x + (size_t)n * HW * Cin;
-  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < HW; ++p) s += __bfloat162float(xb[(size_t)p * Cin + c]);
-    g[c] = s / (float)HW;
+  // mean over HW: thread = (8-channel group, pixel slice); 128-bit loads, smem atomics to combine
+  {
+    const int C8 = Cin / 8;
+    const int slices = blockDim.x / C8 > 0 ? blockDim.x / C8 : 1;
+    const int cg = threadIdx.x % C8, ps = threadIdx.x / C8;
+    if (ps < slices) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int p = ps; p < HW; p += slices) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)p * Cin + cg * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[(size_t)ps * Cin + cg * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    // fixed summation order -> bit-reproducible from run to run
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < slices; ++q) s += part[(size_t)q * Cin + c];
+      g[c] = s / (float)HW;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -261,12 +405,32 @@ se_gate_kernel(const bf16* __restrict__ d, int T, int C, const float* __restrict
   extern __shared__ float se_smem[];
   float* m = se_smem;        // [C]
   float* z = se_smem + C;    // [Cmid]
+  float* part = z + Cmid;    // [slices][C] partial sums
   const int l = blockIdx.x;
   const bf16* db = d + (size_t)l * T * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += __bfloat162float(db[(size_t)t * C + c]);
-    m[c] = s / (float)T;
+  {
+    const int C8 = C / 8;
+    const int slices = blockDim.x / C8 > 0 ? blockDim.x / C8 : 1;
+    const int cg = threadIdx.x % C8, ps = threadIdx.x / C8;
+    if (ps < slices) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int t = ps; t < T; t += slices) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(db + (size_t)t * C + cg * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[(size_t)ps * C + cg * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < slices; ++q) s += part[(size_t)q * C + c];
+      m[c] = s / (float)T;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -336,9 +500,15 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                         cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
                "depthwise: channel counts must be multiples of 8");
-  const size_t total = (size_t)N * H * W * (C / 8);
-  depthwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil,
-                                                                 w9c, out, out_ld, out_coff);
+  if (dil == 1) {
+    const size_t total = (size_t)N * ((H + DW_STRIP - 1) / DW_STRIP) * W * (C / 8);
+    depthwise_strip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, w9c, out,
+                                                                         out_ld, out_coff);
+  } else {
+    const size_t total = (size_t)N * H * W * (C / 8);
+    depthwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil, w9c, out,
+                                                                   out_ld, out_coff);
+  }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -346,9 +516,8 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
 int upsample_bilinear_ac_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, int f,
                                 bf16* out, int out_ld, int out_coff, cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0, "upsample: C %% 8 != 0");
-  const size_t total = (size_t)N * H * f * W * f * (C / 8);
-  upsample_ac_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, H, W, C, f, out, out_ld,
-                                                                   out_coff);
+  const size_t total = (size_t)N * ((H * f + UP_STRIP - 1) / UP_STRIP) * W * f * (C / 8);
+  upsample_ac_strip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, H, W, C, f, out, out_ld, out_coff);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
@@ -364,7 +533,7 @@ int upsample_logits_launch(bdrc_ctx* ctx, const float* in, int N, int h, int w, 
 int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, const float* Wp,
                           const float* bp, int Cmid, const float* Wtail, const float* bproj,
                           int Cout, int Cout_pad, float* bias_eff, cudaStream_t s) {
-  aspp_pool_bias_kernel<<<N, 256, (size_t)(Cin + Cmid) * sizeof(float), s>>>(
+  aspp_pool_bias_kernel<<<N, 512, (size_t)(Cin + Cmid + (512 / (Cin / 8)) * Cin) * sizeof(float), s>>>(
       x, HW, Cin, Wp, bp, Cmid, Wtail, bproj, Cout, Cout_pad, bias_eff);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
@@ -373,7 +542,7 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
 int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
                    const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
                    cudaStream_t s) {
-  se_gate_kernel<<<L, 256, (size_t)(C + Cmid) * sizeof(float), s>>>(d, T, C, W1, b1, Cmid, W2, b2, gate);
+  se_gate_kernel<<<L, 256, (size_t)(C + Cmid + (256 / (C / 8)) * C) * sizeof(float), s>>>(d, T, C, W1, b1, Cmid, W2, b2, gate);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
