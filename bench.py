@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -45,33 +44,52 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region, read in-process through NVML
+    (forking nvidia-smi from a process that holds a CUDA context stalls the launch thread for tens
+    of milliseconds and would perturb the very region being timed)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.err = index, [], False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES, NVML indexes physical GPUs
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        if self.nv is None:
+            return
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.2)
+                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, mask))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        sm = sorted(r[0] for r in self.rows)
+        seen = 0
+        for _, m in self.rows:
+            seen |= m
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [n for bit, n in self.REASONS.items() if seen & bit], "samples": len(self.rows)}
 
 
 def make_pages(n: int, seed: int):
@@ -183,7 +201,6 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    eng.profile(True)
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -194,9 +211,22 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
+    checksum = int(sum(int(m.sum().item()) for m in masks) % (1 << 31))
+
+    # ---- roofline: the same K steps again with a CUDA-event pair around every network launch ----
+    # (recorded on the launching stream by bdrc_profile_*; kept out of `value` because ~1400 event
+    # records per step cost a few per cent)
+    eng.profile(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        step_device()
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
     prof = eng.profile_results()
     eng.profile(False)
-    checksum = int(sum(int(m.sum().item()) for m in masks) % (1 << 31))
 
     # ---- e2e: host numpy pages in, host numpy masks out -----------------------------------
     for _ in range(max(1, args.warmup // 2)):
@@ -239,6 +269,8 @@ def run_ours(args, rank, world, local_rank):
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
         "traffic": None, "launches": len(tc), "avg_launch_ms": tc_ms / max(1, len(tc)),
         "share_of_network_time": tc_ms / all_ms if all_ms else None,
+        "share_of_step": tc_ms / ms_profiled if ms_profiled else None,
+        "profiled_ms_per_step": ms_profiled / args.steps,
         "by_kernel": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
                           "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 and v[1] > 0 else None)}
                       for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},

@@ -434,3 +434,66 @@ class OCRPipeline:
     def run_ocr_batch(self, images: Sequence[np.ndarray], **kw):
         """Pages are independent units: same results as [run_ocr(i) for i in images]."""
         return [self.run_ocr(img, **kw) for img in images]
+
+
+class ModernBookFormatLayoutDetection:
+    """BDRC/inference.py:860-961 (torch path, config C4): float-bilinear resize_clamp, pad 255,
+    tile, /255, DeepLabV3+ forward, softmax, stitch, crop, bilinear resize back, > thr, per-class
+    union bounding box written as {output_dir}/{image_name}.json.  config.checkpoint (or
+    config.onnx_file) names a BDRCW1 container of the same network."""
+
+    def __init__(self, config: LayoutDetectionConfig, engine: Engine | None = None):
+        self.config = config
+        self.classes = config.classes
+        self.engine = engine or get_engine()
+        self.device = "cuda"
+        src = config.checkpoint if config.checkpoint else config.onnx_file
+        self.model = self.engine.load_model(SEG, _read_weights(src), len(self.classes))
+
+    def predict_masks(self, image: np.ndarray, class_threshold: float = 0.8) -> np.ndarray:
+        """RGB HWC u8 page -> u8 {0,255} masks [C, H, W] (what run() thresholds, :949-956)."""
+        eng = self.engine
+        page = torch.from_numpy(np.ascontiguousarray(image[..., :3], dtype=np.uint8)).to(eng.device)
+        tiles, meta = eng.seg_tile_rgb(page)                                   # multi_image_collate_fn
+        logits = eng.seg_forward(self.model, tiles)
+        return eng.seg_postprocess_torch(logits, meta, class_threshold).cpu().numpy()
+
+    def post_process_sample(self, prediction: np.ndarray, class_index: int):
+        import cv2
+
+        contours, _ = cv2.findContours(prediction[class_index], cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+        if len(contours) == 0:
+            return None
+        x, y, w, h = cv2.boundingRect(np.vstack(contours))                     # utils.get_union_bbox :1081-1097
+        return {"bbox": {"x": x, "y": y, "w": w, "h": h}}
+
+    def extract_json_data(self, meta: dict, prediction: np.ndarray, filter_classes, output_dir: str):
+        import json
+
+        found = {}
+        for idx, name in enumerate(self.classes):
+            if filter_classes and name not in filter_classes:
+                continue
+            bbox = self.post_process_sample(prediction, idx)
+            if bbox is not None:
+                found[name] = bbox
+        stem = os.path.splitext(os.path.basename(meta["image_name"]))[0]
+        with open(f"{output_dir}/{stem}.json", "w", encoding="UTF-8") as f:
+            json.dump(found, f, ensure_ascii=False, indent=1)
+        return found
+
+    def run(self, directory: str, output_dir: str, filter_classes=None, batch_size: int = 4, num_workers: int = 4,
+            class_threshold: float = 0.8):
+        import cv2
+        from glob import glob
+
+        if filter_classes:
+            for c in filter_classes:
+                if c not in self.classes:
+                    raise ValueError(f"ERROR: provided filter classes: {filter_classes} are not part of the model's classes!")
+        os.makedirs(output_dir, exist_ok=True)
+        paths = sorted(p for p in glob(os.path.join(directory, "*")) if p.lower().endswith((".jpg", ".png", ".jpeg")))
+        for p in paths:
+            img = cv2.cvtColor(cv2.imread(p, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+            masks = self.predict_masks(img, class_threshold)
+            self.extract_json_data({"image_name": os.path.basename(p)}, masks, filter_classes, output_dir)

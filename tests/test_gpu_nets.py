@@ -125,3 +125,36 @@ def test_ocr_forward_and_decode(engine, conv_engine):
     for l in range(len(crops)):
         same += ids[l, : lens[l]].tolist() == ho.ctc_greedy_ids(ref[l], V)
     print("identical decoded lines:", same, "of", len(crops), "; safe steps:", safe.mean())
+
+
+def test_modern_layout_run_writes_json(engine, tmp_path):
+    """ModernBookFormatLayoutDetection.run (config C4): directory of images -> per-image bbox JSON,
+    masks equal to the oracle's torch-path post-processing of the oracle logits away from ties."""
+    import json
+
+    import cv2
+
+    from ocr_inference_b200.data import LayoutDetectionConfig
+    from ocr_inference_b200.inference import ModernBookFormatLayoutDetection
+
+    classes = ["background", "image", "line", "caption", "margin"]
+    w = nets.seg_weights(13, 5, 3)
+    det = ModernBookFormatLayoutDetection(LayoutDetectionConfig(w, "", "deeplabv3plus", 512, classes), engine=engine)
+    src = tmp_path / "in"
+    src.mkdir()
+    for i, (H, W) in enumerate([(600, 800), (400, 1500)]):
+        page, _ = synth.page(40 + i, H, W, rgb=True)
+        cv2.imwrite(str(src / f"p{i}.png"), cv2.cvtColor(page, cv2.COLOR_RGB2BGR))
+    det.run(str(src), str(tmp_path / "out"), None, class_threshold=0.3)
+    for i in range(2):
+        rec = json.load(open(tmp_path / "out" / f"p{i}.json"))
+        assert set(rec) <= set(classes)
+        for v in rec.values():
+            assert set(v["bbox"]) == {"x", "y", "w", "h"}
+    page, _ = synth.page(40, 600, 800, rgb=True)
+    masks = det.predict_masks(page, 0.3)
+    x, meta = ho.torch_path_pre(np.ascontiguousarray(page.transpose(2, 0, 1)))
+    ref_logits = nets.seg_forward(w, x)
+    mref = ho.torch_path_post(ref_logits, meta, 0.3)
+    assert masks.shape == mref.shape == (5, 600, 800)
+    assert (masks != mref).mean() < 0.02      # bf16 logits: only pixels near the 0.3 probability level differ
