@@ -21,7 +21,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -43,53 +42,84 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region, read in-process through NVML
-    (forking nvidia-smi from a process that holds a CUDA context stalls the launch thread for tens
-    of milliseconds and would perturb the very region being timed)."""
+_SAMPLER_SRC = r"""
+import sys, time
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+    print("max", float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)), flush=True)
+    while True:
+        mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = -1.0
+        print("s", time.time(), mhz, mask, pw, flush=True)
+        time.sleep(0.025)
+except Exception as e:
+    print("err", repr(e), flush=True)
+"""
+
+
+class ClockSampler:
+    """SM clock, power and throttle reasons during the timed regions, read through NVML by a SEPARATE
+    process started before the CUDA context exists: NVML calls (and nvidia-smi forks) made from the
+    process that launches kernels contend with the launch path and stalled it for tens of
+    milliseconds, perturbing the very region being timed.  Samples are time-stamped; summary() keeps
+    those inside the marked [t0, t1] windows."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.err = index, [], False, None
+        import subprocess
+
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES, NVML indexes physical GPUs
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        self.windows: list[tuple[float, float]] = []
         try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES, NVML indexes physical GPUs
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(phys)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except Exception as e:  # noqa: BLE001
-            self.nv, self.err = None, repr(e)
+            self.proc, self.err = None, repr(e)
 
-    def run(self):
-        if self.nv is None:
-            return
-        while not self.stop_flag:
-            try:
-                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:  # noqa: BLE001
-                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((mhz, mask))
-            except Exception as e:  # noqa: BLE001
-                self.err = repr(e)
-            time.sleep(0.05)
+    def mark(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
-        sm = sorted(r[0] for r in self.rows)
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler unavailable: {self.err}"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        max_mhz, rows, err = None, [], None
+        for ln in out.splitlines():
+            f = ln.split()
+            if f and f[0] == "max":
+                max_mhz = float(f[1])
+            elif f and f[0] == "s" and len(f) >= 5:
+                rows.append((float(f[1]), float(f[2]), int(f[3]), float(f[4])))
+            elif f and f[0] == "err":
+                err = ln
+        inside = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": max_mhz, "reasons": [f"no samples inside the timed region ({err})"],
+                    "samples": 0}
+        sm = sorted(r[1] for r in inside)
         seen = 0
-        for _, m in self.rows:
-            seen |= m
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz,
-                "reasons": [n for bit, n in self.REASONS.items() if seen & bit], "samples": len(self.rows)}
+        for r in inside:
+            seen |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max_mhz,
+                "power_w_max": max(r[3] for r in inside),
+                "reasons": [n for bit, n in self.REASONS.items() if seen & bit], "samples": len(inside)}
 
 
 def make_pages(n: int, seed: int):
@@ -170,6 +200,7 @@ def run_ours(args, rank, world, local_rank):
     from ocr_inference_b200.inference import LineDetection, get_engine
     from ocr_inference_b200.weights import write_blob
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # before the CUDA context exists
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -198,17 +229,17 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         masks = step_device()
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark(w0, time.time())
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
     checksum = int(sum(int(m.sum().item()) for m in masks) % (1 << 31))
@@ -232,12 +263,14 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup // 2)):
         det.predict_batch(pages, pinned=pinned, copy=False)
     barrier()
+    w0 = time.time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out = det.predict_batch(pages, pinned=pinned, copy=False)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True
+    if sampler:
+        sampler.mark(w0, time.time())
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -306,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
