@@ -97,6 +97,12 @@ int conv_simt_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cud
 int conv_launch(bdrc_ctx* ctx, const char* name, const ConvWeights& w, const ConvArgs& a,
                 cudaStream_t s);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link); nullptr if absent
+typedef CUresult (*BdrcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+BdrcEncodeTiledFn bdrc_tma_encode_fn();
+
 // pack fp32 OIHW host weights into device ConvWeights
 int conv_pack_weights(bdrc_ctx* ctx, const float* w_oihw, const float* bias, int Cout, int Cin,
                       int R, int S, ConvWeights* out);

@@ -66,6 +66,7 @@ struct bdrc_model {
   float* stem_w3 = nullptr;       // [49*3][64]
   float* stem_w1 = nullptr;       // [49][64]   (3 identical input channels folded)
   float* stem_b = nullptr;
+  bf16* stem_wb = nullptr;        // [64][64] bf16, k = 8 * row + col: folded weights for the tcgen05 stem
   float* proj_tail = nullptr;     // [256][256] fp32: projection columns of the pooled branch
   float* pool_w = nullptr;        // [256][512]
   float* pool_b = nullptr;
@@ -157,6 +158,15 @@ int load_seg(Loader& L, int n_classes) {
   BDRC_TRY(dev_copy(ctx, m, w3, &m->stem_w3));
   BDRC_TRY(dev_copy(ctx, m, w1, &m->stem_w1));
   BDRC_TRY(dev_copy(ctx, m, std::vector<float>(sb->data, sb->data + 64), &m->stem_b));
+  {
+    std::vector<bf16> wb((size_t)64 * 64, __float2bfloat16(0.f));
+    for (int o = 0; o < 64; ++o)
+      for (int r = 0; r < 7; ++r)
+        for (int c = 0; c < 7; ++c) wb[(size_t)o * 64 + r * 8 + c] = __float2bfloat16(w1[(size_t)(r * 7 + c) * 64 + o]);
+    BDRC_CUDA(ctx, cudaMalloc(&m->stem_wb, wb.size() * sizeof(bf16)));
+    m->owned.push_back(m->stem_wb);
+    BDRC_CUDA(ctx, cudaMemcpy(m->stem_wb, wb.data(), wb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
   int cin = 64;
   for (int li = 0; li < 4; ++li) {
     const int ch = R34_CH[li];
@@ -300,13 +310,20 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   if (!A.ok) return bdrc_fail(ctx, BDRC_ERR_ARG, "seg_forward: workspace too small");
 
   // stem + maxpool (ipynb:L233-L238)
-  bdrc_prof_begin(ctx, "stem7x7", 2.0 * n * 256 * 256 * 64 * 49 * 3, s);
-  BDRC_TRY(stem_conv_launch(ctx, tiles, cin, cin == 1 ? 1.f : 255.f, n, SEG_P, SEG_P,
-                            cin == 1 ? m->stem_w1 : m->stem_w3, m->stem_b, stem, s));
-  bdrc_prof_end(ctx, s);
-  bdrc_prof_begin(ctx, "maxpool", 0, s);
-  BDRC_TRY(maxpool3x3s2_launch(ctx, stem, n, 256, 256, 64, buf[0], s));
-  bdrc_prof_end(ctx, s);
+  if (cin == 1 && ctx->conv_engine == 0) {
+    // binarised tiles: tcgen05 stem fused with the max-pool, the 256x256x64 activation stays on chip
+    bdrc_prof_begin(ctx, "stem7x7+maxpool", 2.0 * n * 256 * 256 * 64 * 49 * 3, s);
+    BDRC_TRY(stem_tc_pool_launch(ctx, reinterpret_cast<const uint8_t*>(tiles), n, m->stem_wb, m->stem_b, buf[0], s));
+    bdrc_prof_end(ctx, s);
+  } else {
+    bdrc_prof_begin(ctx, "stem7x7", 2.0 * n * 256 * 256 * 64 * 49 * 3, s);
+    BDRC_TRY(stem_conv_launch(ctx, tiles, cin, cin == 1 ? 1.f : 255.f, n, SEG_P, SEG_P,
+                              cin == 1 ? m->stem_w1 : m->stem_w3, m->stem_b, stem, s));
+    bdrc_prof_end(ctx, s);
+    bdrc_prof_begin(ctx, "maxpool", 0, s);
+    BDRC_TRY(maxpool3x3s2_launch(ctx, stem, n, 256, 256, 64, buf[0], s));
+    bdrc_prof_end(ctx, s);
+  }
 
   // ResNet-34 body (ipynb:L239-L404).  x walks through three rotating buffers; the output of
   // layer1 is written to `skip`, which stays untouched until the decoder reads it.

@@ -1,6 +1,7 @@
 // Memory-bound network kernels between the implicit-GEMM convolutions (see nn_kernels.cuh).
 // All activations are bf16 NHWC; arithmetic is fp32.
 #include "nn_kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -131,48 +132,14 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in, int N, int H, int W,
   *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * C + c8 * 8) = pack8(m);
 }
 
-__global__ void depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int H,
-                                 int W, int C, int dil, const float* __restrict__ w9c,
-                                 bf16* __restrict__ out, int out_ld, int out_coff) {
-  const int C8 = C / 8;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)N * H * W * C8;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  size_t p = idx / C8;
-  const int x = (int)(p % W); p /= W;
-  const int y = (int)(p % H);
-  const int n = (int)(p / H);
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = y + (r - 1) * dil;
-    if (iy < 0 || iy >= H) continue;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int ix = x + (s - 1) * dil;
-      if (ix < 0 || ix >= W) continue;
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * H + iy) * W + ix) * in_ld + in_coff + c8 * 8)), f);
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9c + (r * 3 + s) * C + c8 * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9c + (r * 3 + s) * C + c8 * 8 + 4));
-      acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
-      acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-      acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
-      acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
-    }
-  }
-  *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * out_ld + out_coff + c8 * 8) = pack8(acc);
-}
-
-// dilation-1 variant: each thread walks a vertical strip of DW_STRIP output rows for 8 channels,
-// keeping the three live input rows in registers (3 loads per output instead of 9)
-constexpr int DW_STRIP = 8;
+// Depthwise 3x3: each thread owns 8 channels of one column and walks a vertical strip of DW_STRIP
+// output rows.  The 72 weights of its channel group live in registers for the whole strip (the
+// first version re-read them from L1 for every output: 18 of its 21 loads per output were weights).
+// DIL1: the three live input rows stay in registers (3 loads per output instead of 9).
+template <bool DIL1, int DW_STRIP>
 __global__ void __launch_bounds__(256)
-depthwise_strip_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int H, int W, int C,
-                       const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff) {
+depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int H, int W, int C, int dil,
+                 const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff) {
   const int C8 = C / 8;
   const int strips = (H + DW_STRIP - 1) / DW_STRIP;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,46 +151,148 @@ depthwise_strip_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int 
   const int st = (int)(p % strips);
   const int n = (int)(p / strips);
   const bf16* base = in + (size_t)n * H * W * in_ld + in_coff + c8 * 8;
-  const float* wb = w9c + c8 * 8;
-  // the live 3x3 window stays packed (bf16) in registers; weights come from L1 on use
-  auto load_row = [&](int iy, uint4* row) {
+  bf16* obase = out + (size_t)n * H * W * out_ld + out_coff + c8 * 8;
+  float w[9][8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c8 * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c8 * 8 + 4));
+    w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+    w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+  }
+  auto load_px = [&](int iy, int ix) -> uint4 {
+    return (iy >= 0 && iy < H && ix >= 0 && ix < W)
+               ? __ldg(reinterpret_cast<const uint4*>(base + ((size_t)iy * W + ix) * in_ld))
+               : make_uint4(0u, 0u, 0u, 0u);
+  };
+  auto fma_px = [&](const uint4& v, int k, float* acc) {
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[k][j], acc[j]);
+  };
+  const int y0 = st * DW_STRIP;
+  if (DIL1) {
+    uint4 r0[3], r1[3], r2[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { r0[s] = load_px(y0 - 1, x + s - 1); r1[s] = load_px(y0, x + s - 1); }
+#pragma unroll 4
+    for (int i = 0; i < DW_STRIP; ++i) {
+      const int y = y0 + i;
+      if (y >= H) break;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) r2[s] = load_px(y + 1, x + s - 1);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) { fma_px(r0[s], s, acc); fma_px(r1[s], 3 + s, acc); fma_px(r2[s], 6 + s, acc); }
+      *reinterpret_cast<uint4*>(obase + ((size_t)y * W + x) * out_ld) = pack8(acc);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) { r0[s] = r1[s]; r1[s] = r2[s]; }
+    }
+  } else {
+#pragma unroll 2
+    for (int i = 0; i < DW_STRIP; ++i) {
+      const int y = y0 + i;
+      if (y >= H) break;
+      uint4 v[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) v[r * 3 + s] = load_px(y + (r - 1) * dil, x + (s - 1) * dil);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) fma_px(v[k], k, acc);
+      *reinterpret_cast<uint4*>(obase + ((size_t)y * W + x) * out_ld) = pack8(acc);
+    }
+  }
+}
+
+// Depthwise 3x3, dilation 1, TMA-fed row ring.  A CTA owns (image, 64-channel chunk, 32-pixel column
+// band, segment of DWR_ROWS output rows).  Input rows (34 px x 64 ch = 4352 B, halo and channel tail
+// zero-filled by TMA out-of-bounds handling) stream through an 8-slot shared-memory ring, each loaded
+// exactly once; thread (px, 8-channel group) reads its 3 neighbours of the arriving row and feeds the
+// three output rows that row contributes to, so an output costs 3 LDS.128 + 72 FMA and the 72 weights
+// stay in registers.  Summation order per output is (r, s) row-major as in the direct kernel.
+constexpr int DWR_PX = 32, DWR_SLOTS = 8, DWR_ROWS = 32;
+constexpr int DWR_SLOT_BYTES = (DWR_PX + 2) * 128;
+
+__global__ void __launch_bounds__(256)
+depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, int W, int C,
+                      const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff, int* errflag) {
+  extern __shared__ __align__(128) uint8_t dwr_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwr_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[DWR_SLOTS];
+  const int xt_n = W / DWR_PX, chunks = (C + 63) / 64, segs = (H + DWR_ROWS - 1) / DWR_ROWS;
+  int item = blockIdx.x;
+  const int xt = item % xt_n; item /= xt_n;
+  const int seg = item % segs; item /= segs;
+  const int ch = item % chunks;
+  const int n = item / chunks;
+  const int x0 = xt * DWR_PX, c0 = ch * 64;
+  const int ya = seg * DWR_ROWS, yb = min(H, ya + DWR_ROWS);
+  const int rows_in = yb - ya + 2;             // input rows ya-1 .. yb
+  const int tid = threadIdx.x;
+  const int c8 = tid & 7, px = tid >> 3;
+  const bool cvalid = c0 + c8 * 8 < C;
+
+  if (tid == 0) {
+    for (int i = 0; i < DWR_SLOTS; ++i) tcptx::mbar_init(tcptx::smem_u32(&full_bar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int k) {   // input row ya - 1 + k -> slot k % SLOTS
+    const uint32_t bar = tcptx::smem_u32(&full_bar[k % DWR_SLOTS]);
+    tcptx::mbar_arrive_expect_tx(bar, DWR_SLOT_BYTES);
+    tcptx::tma_load_4d(tcptx::smem_u32(ring + (size_t)(k % DWR_SLOTS) * DWR_SLOT_BYTES), &tmap, bar, c0, x0 - 1,
+                       ya - 1 + k, n);
+  };
+  if (tid == 0)
+    for (int k = 0; k < DWR_SLOTS && k < rows_in; ++k) issue(k);
+
+  float w[9][8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (cvalid) {
+      w0 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c0 + c8 * 8));
+      w1 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c0 + c8 * 8 + 4));
+    }
+    w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+    w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+  }
+  float a_prev[8], a_cur[8], a_next[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a_prev[j] = a_cur[j] = a_next[j] = 0.f;
+  bf16* obase = out + ((size_t)n * H * W + x0 + px) * out_ld + out_coff + c0 + c8 * 8;
+
+  for (int k = 0; k < rows_in; ++k) {
+    const int i = ya - 1 + k;                  // input row
+    tcptx::mbar_wait(tcptx::smem_u32(&full_bar[k % DWR_SLOTS]), (uint32_t)((k / DWR_SLOTS) & 1), errflag, 9);
+    const uint8_t* row = ring + (size_t)(k % DWR_SLOTS) * DWR_SLOT_BYTES + px * 128 + c8 * 16;
+    uint4 v[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) v[s] = *reinterpret_cast<const uint4*>(row + s * 128);
+    __syncthreads();                           // every thread holds its 3 pixels: the slot can be refilled
+    if (tid == 0 && k + DWR_SLOTS < rows_in) issue(k + DWR_SLOTS);
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      const int ix = x + s - 1;
-      row[s] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                   ? __ldg(reinterpret_cast<const uint4*>(base + ((size_t)iy * W + ix) * in_ld))
-                   : make_uint4(0u, 0u, 0u, 0u);
-    }
-  };
-  uint4 r0[3], r1[3], r2[3];
-  const int y0 = st * DW_STRIP;
-  load_row(y0 - 1, r0);
-  load_row(y0, r1);
-  for (int i = 0; i < DW_STRIP; ++i) {
-    const int y = y0 + i;
-    if (y >= H) break;
-    load_row(y + 1, r2);
-    float acc[8];
+      float f[8];
+      unpack8(v[s], f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const uint4* row = r == 0 ? r0 : (r == 1 ? r1 : r2);
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        float f[8];
-        unpack8(row[s], f);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wb + (r * 3 + s) * C));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wb + (r * 3 + s) * C + 4));
-        acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
-        acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
-        acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
-        acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+      for (int j = 0; j < 8; ++j) {
+        a_next[j] = fmaf(f[j], w[s][j], a_next[j]);          // this row is the r = 0 row of output i + 1
+        a_cur[j] = fmaf(f[j], w[3 + s][j], a_cur[j]);        //             the r = 1 row of output i
+        a_prev[j] = fmaf(f[j], w[6 + s][j], a_prev[j]);      //             the r = 2 row of output i - 1
       }
     }
-    *reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + x) * out_ld + out_coff + c8 * 8) = pack8(acc);
+    if (i - 1 >= ya && cvalid) *reinterpret_cast<uint4*>(obase + (size_t)(i - 1) * W * out_ld) = pack8(a_prev);
 #pragma unroll
-    for (int s = 0; s < 3; ++s) { r0[s] = r1[s]; r1[s] = r2[s]; }
+    for (int j = 0; j < 8; ++j) { a_prev[j] = a_cur[j]; a_cur[j] = a_next[j]; a_next[j] = 0.f; }
   }
 }
 
@@ -500,14 +569,31 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                         cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
                "depthwise: channel counts must be multiples of 8");
+  if (dil == 1 && W % DWR_PX == 0 && bdrc_tma_encode_fn() != nullptr) {
+    CUtensorMap map;
+    const cuuint64_t ld = (cuuint64_t)in_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(DWR_PX + 2), 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = bdrc_tma_encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in) + in_coff, dims,
+                                      strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "depthwise: cuTensorMapEncodeTiled failed: %d", (int)r);
+    const int items = N * ((C + 63) / 64) * ((H + DWR_ROWS - 1) / DWR_ROWS) * (W / DWR_PX);
+    depthwise_ring_kernel<<<items, 256, DWR_SLOTS * DWR_SLOT_BYTES + 128, s>>>(map, N, H, W, C, w9c, out, out_ld,
+                                                                              out_coff, ctx->d_errflag);
+    BDRC_CHECK_LAUNCH(ctx);
+    return 0;
+  }
   if (dil == 1) {
-    const size_t total = (size_t)N * ((H + DW_STRIP - 1) / DW_STRIP) * W * (C / 8);
-    depthwise_strip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, w9c, out,
-                                                                         out_ld, out_coff);
+    const size_t total = (size_t)N * ((H + 15) / 16) * W * (C / 8);
+    depthwise_kernel<true, 16><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil, w9c,
+                                                                              out, out_ld, out_coff);
   } else {
-    const size_t total = (size_t)N * H * W * (C / 8);
-    depthwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil, w9c, out,
-                                                                   out_ld, out_coff);
+    const size_t total = (size_t)N * ((H + 3) / 4) * W * (C / 8);
+    depthwise_kernel<false, 4><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_ld, in_coff, N, H, W, C, dil, w9c,
+                                                                              out, out_ld, out_coff);
   }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;

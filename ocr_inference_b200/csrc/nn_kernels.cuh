@@ -40,3 +40,8 @@ int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const floa
 // data = relu(res + d * gate)
 int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* gate, int L, int T,
                     int C, bf16* out, cudaStream_t s);
+
+// Stem + max-pool fused on the tensor cores (stem_tc.cu): u8 tiles [N][512][512] (3 identical channels
+// folded) -> bf16 NHWC [N][128][128][64].  w_bf16: [64 cout][64 k] with k = 8 * kernel_row + kernel_col.
+int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* w_bf16, const float* bias, bf16* out,
+                        cudaStream_t s);

@@ -1,0 +1,228 @@
+// Stem of the segmentation network on the tensor cores, fused with the max-pool that follows it:
+//   conv 7x7 stride 2 pad 3 (1 folded input channel -> 64) + bias + ReLU + maxpool 3x3 stride 2 pad 1
+//   (PyTorch-LineInference.ipynb:L233-L238), u8 tiles [N][512][512] -> bf16 NHWC [N][128][128][64].
+//
+// The three input channels of a binarised tile are identical (BDRC/utils.py:796-815 replicates the
+// mask), so the 3x49 stem weights fold to 49 per output channel and the conv is a GEMM with
+// K = 7 rows x 8 (7 taps + one zero column) = 56, padded to 64 = one 128-byte swizzle row.
+//
+// One CTA produces a 4 x 32 patch of POOLED outputs: it needs the 9 x 65 stem pixels around it
+//   1. stage the 23 x 144 byte input patch in shared memory (zero outside the image),
+//   2. im2col: 585 (-> 640) A rows x 64 bf16, written by the threads in the SWIZZLE_128B K-major layout
+//      (u8 -> bf16 is exact; the window of a stem pixel is 7 runs of 8 consecutive bytes),
+//   3. 5 M-tiles x 4 tcgen05.mma (M128 N64 K16), fp32 accumulators in TMEM,
+//   4. epilogue: TMEM -> +bias, ReLU, bf16 -> shared memory (aliasing the A tiles), zero for stem
+//      pixels outside the 256 x 256 stem image (exact: every pooled window holds a valid pixel >= 0),
+//   5. 3x3/s2 max over shared memory -> 16-byte stores of the pooled NHWC tile.
+// The 403 MB stem activation of a 48-tile chunk never exists in HBM.
+#include "nn_kernels.cuh"
+#include "tc_ptx.cuh"
+
+using namespace tcptx;
+
+namespace {
+
+constexpr int SP = 512;                 // input tile size
+constexpr int PT_H = 4, PT_W = 32;      // pooled outputs per CTA tile
+constexpr int SR_H = 2 * PT_H + 1;      // 9 stem rows
+constexpr int SR_W = 2 * PT_W + 1;      // 65 stem cols
+constexpr int M_VALID = SR_H * SR_W;    // 585
+constexpr int M_TILES = 5;              // 640 rows
+constexpr int PATCH_ROWS = 4 * PT_H + 7;     // 23 input rows
+constexpr int PATCH_PITCH = 144;             // bytes; 36 aligned words starting at image col 4*px0 - 8
+constexpr int STEM_THREADS = 512;
+constexpr uint32_t A_TILE_BYTES = 128 * 128;  // 16 KB
+constexpr uint32_t SMEM_A = M_TILES * A_TILE_BYTES;          // 80 KB (also the pooled staging S)
+constexpr uint32_t SMEM_B = 64 * 128;                        // 8 KB
+constexpr uint32_t SMEM_PATCH = PATCH_ROWS * PATCH_PITCH;    // 3312 B
+constexpr uint32_t SMEM_TOTAL = 1024 + SMEM_A + SMEM_B + 4096 + 256;
+
+__device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int k) {
+  // bytes k and k+1 of `word` -> two exact bf16 (0..255)
+  const float f0 = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 | k)) - 8388608.0f;
+  const float f1 = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 | (k + 1))) - 8388608.0f;
+  return __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
+}
+
+__global__ void __launch_bounds__(STEM_THREADS, 1)
+stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restrict__ wb, const float* __restrict__ bias,
+                    bf16* __restrict__ out, int* errflag) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                         // 5 x [128][128 B] swizzled; reused as S[640][128 B]
+  uint8_t* sB = smem + SMEM_A;                // [64][128 B] swizzled
+  uint8_t* sP = sB + SMEM_B;                  // input patch
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sP + 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* sBias = reinterpret_cast<float*>(sP + 3328);   // 64 floats after the patch (3312 -> 3328)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time set-up: weights into the swizzled B tile, bias, barrier, TMEM -----------------
+  for (int i = tid; i < 64 * 8; i += STEM_THREADS) {
+    const int o = i >> 3, c = i & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wb + o * 64 + c * 8));
+    *reinterpret_cast<uint4*>(sB + o * 128 + ((c ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sBias[tid] = __ldg(bias + tid);
+  if (tid == 0) {
+    mbar_init(smem_u32(mma_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // K columns 56..63 of every A row are never written by the im2col.  Their weights are zero, so they
+  // only have to be finite: zero them once (later tiles leave finite bf16 activations there)
+  for (int m = tid; m < M_TILES * 128; m += STEM_THREADS)
+    *reinterpret_cast<uint4*>(sA + (size_t)m * 128 + ((7 ^ (m & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_bf16(128, 64);
+
+  const int tiles_x = 128 / PT_W, tiles_y = 128 / PT_H;
+  const int total = N * tiles_y * tiles_x;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int n = tile / (tiles_x * tiles_y);
+    const int px0 = tx * PT_W, py0 = ty * PT_H;
+    const int x_org = 4 * px0 - 8, y_org = 4 * py0 - 5;
+    const uint8_t* img = in + (size_t)n * SP * SP;
+
+    // ---- 1. input patch ----------------------------------------------------------------------
+    for (int i = tid; i < PATCH_ROWS * (PATCH_PITCH / 4); i += STEM_THREADS) {
+      const int r = i / (PATCH_PITCH / 4), wq = i - r * (PATCH_PITCH / 4);
+      const int iy = y_org + r, ix = x_org + wq * 4;
+      uint32_t v = 0;
+      if (iy >= 0 && iy < SP && ix >= 0 && ix < SP) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)iy * SP + ix));
+      *reinterpret_cast<uint32_t*>(sP + r * PATCH_PITCH + wq * 4) = v;
+    }
+    __syncthreads();   // also orders the previous tile's pooling reads of S before the rewrite of A
+
+    // ---- 2. im2col: item = (kernel row r, A row m); chunk r of row m = 8 bytes -> 8 bf16 ----------
+    for (int i = tid; i < 7 * M_TILES * 128; i += STEM_THREADS) {
+      const int r = i / (M_TILES * 128), m = i - r * (M_TILES * 128);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (m < M_VALID) {
+        const int ry = m / SR_W, rx = m - ry * SR_W;
+        const int b0 = 3 + 2 * rx;                                   // first byte of the 8-byte window
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sP + (2 * ry + r) * PATCH_PITCH + (b0 & ~3));
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const int sh = (b0 & 3) * 8;
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        v.x = u8pair_to_bf16x2(lo, 0);
+        v.y = u8pair_to_bf16x2(lo, 2);
+        v.z = u8pair_to_bf16x2(hi, 0);
+        v.w = u8pair_to_bf16x2(hi, 2) & 0x0000FFFFu;                 // 8th tap column has no weight: keep it 0
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)m * 128 + ((r ^ (m & 7)) << 4)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- 3. MMAs ---------------------------------------------------------------------------------
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t bdesc = make_sdesc(smem_u32(sB));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int t = 0; t < M_TILES; ++t)   // tile-inner order: back-to-back MMAs hit different accumulators
+            tc_mma_bf16(tmem_base + (uint32_t)(t * 64), make_sdesc(smem_u32(sA) + t * A_TILE_BYTES) + (uint64_t)(2 * k),
+                        bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+        tc_commit(smem_u32(mma_bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(mma_bar), phase, errflag, 8);
+    phase ^= 1;
+    tc_fence_after();
+
+    // ---- 4. epilogue: warp w -> TMEM lanes 32*(w%4).., column group q = w/4 of every tile ------------
+    {
+      const int q = warp >> 2;
+      const int ml = (warp & 3) * 32 + lane;
+      float b[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = sBias[q * 16 + j];
+#pragma unroll
+      for (int t = 0; t < M_TILES; ++t) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * 64 + q * 16), v);
+        tc_wait_ld();
+        const int m = t * 128 + ml;
+        const int ry = m / SR_W, rx = m - ry * SR_W;
+        const bool ok = (m < M_VALID) && (2 * py0 - 1 + ry >= 0) && (2 * px0 - 1 + rx >= 0);
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f0 = ok ? fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], 0.f) : 0.f;
+          const float f1 = ok ? fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], 0.f) : 0.f;
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        uint8_t* rowp = sA + (size_t)m * 128;
+        *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- 5. 3x3 stride-2 max over S -> pooled NHWC ---------------------------------------------------
+    for (int i = tid; i < PT_H * PT_W * 8; i += STEM_THREADS) {
+      const int c8 = i & 7, pc = (i >> 3) % PT_W, pr = (i >> 3) / PT_W;
+      __nv_bfloat162 mx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx[j] = __floats2bfloat162_rn(0.f, 0.f);   // post-ReLU values are >= 0
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int m = (2 * pr + dy) * SR_W + 2 * pc + dx;
+          const uint4 v = *reinterpret_cast<const uint4*>(sA + (size_t)m * 128 + ((c8 ^ (m & 7)) << 4));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mx[j] = __hmax2(mx[j], h[j]);
+        }
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&mx[0]); o.y = *reinterpret_cast<uint32_t*>(&mx[1]);
+      o.z = *reinterpret_cast<uint32_t*>(&mx[2]); o.w = *reinterpret_cast<uint32_t*>(&mx[3]);
+      *reinterpret_cast<uint4*>(out + (((size_t)n * 128 + py0 + pr) * 128 + px0 + pc) * 64 + c8 * 8) = o;
+    }
+    // the next iteration's first __syncthreads orders these reads before A is rewritten
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* w_bf16, const float* bias, bf16* out,
+                        cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(stem_tc_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int total = N * (128 / PT_H) * (128 / PT_W);
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  stem_tc_pool_kernel<<<grid, STEM_THREADS, SMEM_TOTAL, s>>>(tiles, N, w_bf16, bias, out, ctx->d_errflag);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
