@@ -190,6 +190,143 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# secondary workloads: C1 (line recognition) and C3 (page -> text), reported next to the C2 headline
+# ------------------------------------------------------------------------------------------------
+C1_LINES = 64
+
+
+def _ocr_config():
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.data import CharsetEncoder, OCRModelConfig
+    from ocr_inference_b200.synthetic_weights import easter2_weights_fitted
+    from ocr_inference_b200.weights import write_blob
+
+    return OCRModelConfig(write_blob(easter2_weights_fitted()), "Easter2", 2000, 80, "input", "output", True, False,
+                          CharsetEncoder.WYLIE, synthetic.CHARSET_76, True, "fitted")
+
+
+def cpu_reference_lines_per_sec(n_lines: int):
+    """Oracle arm of C1: reference line prep (cv2) + torch-CPU fp32 Easter2 + greedy CTC."""
+    import cv2
+    import torch
+
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.synthetic_weights import easter2_weights_fitted
+    from oracle import hostops as ho
+    from oracle import nets
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(-1)
+    w = easter2_weights_fitted()
+    crops, _ = synthetic.glyph_lines(1001, n_lines)
+    t0 = time.perf_counter()
+    x = np.stack([ho.prepare_ocr_line(c, 80, 2000, pre_pad=False).reshape(80, 2000) for c in crops])
+    logits = nets.easter2_forward(w, x)
+    ids = [ho.ctc_greedy_ids(logits[i], 77) for i in range(n_lines)]
+    dt = time.perf_counter() - t0
+    return n_lines / dt, cores, ids
+
+
+def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
+    """64 ragged glyph-line crops -> a-7 prep -> Easter2 (tcgen05) -> greedy CTC -> text."""
+    import torch
+
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.inference import OCRInference
+    from ocr_inference_b200.synthetic_weights import easter2_flops_per_line
+
+    ocr = OCRInference(_ocr_config(), None, engine=eng)
+    crops, truth = synthetic.glyph_lines(1001, C1_LINES)
+    dev, hw, off = eng.pack_crops(crops)
+    blank = ocr.ctc_decoder.blank_index
+
+    def step_device():
+        lines, _ = eng.ocr_prepare_lines(dev, hw, off, C1_LINES, 80, 2000, False)
+        return eng.ctc_greedy(eng.ocr_forward(ocr.ocr_session, lines), blank=blank)
+
+    for _ in range(warmup):
+        step_device()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (eng.launch_count() - l0) // steps
+    eng.profile(True)
+    for _ in range(steps):
+        step_device()
+    torch.cuda.synchronize()
+    prof = eng.profile_results()
+    eng.profile(False)
+    tc = [(n, t, f) for (n, t, f) in prof if f > 0]
+    tc_ms, tc_fl = sum(x[1] for x in tc), sum(x[2] for x in tc)
+    for _ in range(2):
+        texts = ocr.run_batch(crops, pre_pad=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        texts = ocr.run_batch(crops, pre_pad=False)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    want = ["".join(synthetic.CHARSET_76[i] for i in t) for t in truth]
+    peak_tf, _, peak_src = peaks()
+    out = {
+        "workload": f"C1: {C1_LINES} ragged glyph-line crops -> resize/pad/binarise -> Easter2 (CTC-trained on synthetic "
+                    "glyphs) -> greedy CTC -> text",
+        "lines_per_sec": C1_LINES / (ms / 1e3), "ms_per_step": ms, "launches_per_step": int(launches),
+        "e2e_lines_per_sec": C1_LINES / (e2e_ms / 1e3), "e2e_ms_per_step": e2e_ms,
+        "e2e_api": "OCRInference.run_batch(host crops) -> list[str]",
+        "h2d_bytes_per_step": int(sum(c.nbytes for c in crops)),
+        "algorithmic_gflop_per_line": easter2_flops_per_line(77, 80, 2000) / 1e9,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (Easter2 conv1d layers)",
+                     "achieved": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (tc_fl / (tc_ms / 1e3) / 1e12) / peak_tf if tc_ms else 0.0, "peak_source": peak_src,
+                     "share_of_step": tc_ms / steps / ms if ms else None},
+        "lines_equal_to_truth": sum(a == b for a, b in zip(texts, want)) / C1_LINES,
+    }
+    if with_cpu:
+        v, cores, ref_ids = cpu_reference_lines_per_sec(16)
+        got_ids = ocr.run_batch(crops[:16], pre_pad=False, return_ids=True)
+        out["cpu_baseline"] = {"value": v, "unit": "lines/s", "cores": cores, "kind": "port",
+                               "sample": "16 of the 64 lines: cv2 prep + torch-CPU fp32 Easter2 + greedy CTC"}
+        out["lines_identical_to_cpu_oracle"] = sum(a == b for a, b in zip(got_ids, ref_ids)) / 16
+    return out
+
+
+def bench_c3(eng, steps: int, pages_per_step: int = 16, workers: int = 4):
+    """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (host numpy in, OCRLine text out)."""
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.data import LineDetectionConfig, OpStatus
+    from ocr_inference_b200.inference import OCRPipeline
+    from ocr_inference_b200.synthetic_weights import seg_weights_fitted
+    from ocr_inference_b200.weights import write_blob
+
+    pipe = OCRPipeline(_ocr_config(), LineDetectionConfig("", write_blob(seg_weights_fitted(11)), "deeplabv3plus-r34",
+                                                          512, ["line"]), None, engine=eng)
+    base = [synthetic.text_page(3003 + i) for i in range(4)]
+    pages = [base[i % 4][0] for i in range(pages_per_step)]
+    n_truth = sum(len(base[i % 4][2]) for i in range(pages_per_step))
+    pipe.run_ocr_batch(pages[:workers], workers=workers)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = pipe.run_ocr_batch(pages, workers=workers)
+    dt = (time.perf_counter() - t0) / steps
+    ok = [r for r in res if r[0] == OpStatus.SUCCESS]
+    n_lines = sum(len(r[1][2]) for r in ok)
+    return {
+        "workload": f"C3: {pages_per_step} synthetic 2048x3072 text pages per step through OCRPipeline.run_ocr_batch "
+                    "(tile/binarise, DeepLabV3+ with fitted head, mask, cv2 contours + reading order on the host, GPU line "
+                    "crops, line prep, Easter2, greedy CTC)",
+        "e2e_pages_per_sec": pages_per_step / dt, "e2e_lines_per_sec": n_lines / dt, "ms_per_page": dt * 1e3 / pages_per_step,
+        "host_threads": workers, "pages_ok": len(ok), "lines_found": n_lines, "lines_on_pages": n_truth,
+        "note": "host-bound: cv2.findContours + reading-order Python (SURVEY 8(a)-10) take ~25 ms/page/core; GPU stages ~7 ms/page",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
@@ -309,6 +446,13 @@ def run_ours(args, rank, world, local_rank):
                       for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},
     }
     cpu_v, cpu_s, cores = cpu_reference_pages_per_sec(1) if world >= 1 and args.cpu_baseline else (None, None, None)
+    extras = {}
+    if world == 1 and args.extras:
+        try:
+            extras["c1"] = bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline)
+            extras["c3"] = bench_c3(eng, 2)
+        except Exception as e:  # noqa: BLE001  (the headline must still print)
+            extras["error"] = repr(e)
     h2d = sum(p.nbytes for p in pages)
     d2h = sum(o.nbytes for o in out)
     line = {
@@ -330,6 +474,7 @@ def run_ours(args, rank, world, local_rank):
                                     "network), all host threads"} if cpu_v else None),
         "clocks": sampler.summary(),
         "mask_checksum": checksum,
+        "other_workloads": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -343,6 +488,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the C1 (lines/s) and C3 (page->text) side measurements of the default N=1 run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

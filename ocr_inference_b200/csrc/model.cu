@@ -263,8 +263,9 @@ size_t seg_bytes_per_tile(int C) {
   for (int i = 0; i < 3; ++i) add((size_t)128 * 128 * 64, 2);   // rotating block buffers
   add((size_t)128 * 128 * 64, 2);           // skip (layer1 output)
   add((size_t)32 * 32 * 1024, 2);           // ASPP concat
-  add((size_t)32 * 32 * 512, 2);            // depthwise scratch
+  add((size_t)3 * 32 * 32 * 512, 2);        // depthwise scratch (one per ASPP rate)
   add((size_t)256, 4);                      // per-tile projection bias
+  add((size_t)512, 4);                      // per-tile channel means (image-pooling branch)
   add((size_t)32 * 32 * 256, 2);            // projection out
   add((size_t)32 * 32 * 256, 2);            // aspp.1 depthwise
   add((size_t)32 * 32 * 256, 2);            // aspp.1 pointwise
@@ -296,8 +297,9 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   for (int i = 0; i < 3; ++i) buf[i] = A.take<bf16>((size_t)n * 128 * 128 * 64);
   bf16* skip = A.take<bf16>((size_t)n * 128 * 128 * 64);
   bf16* cat = A.take<bf16>((size_t)n * 32 * 32 * 1024);
-  bf16* dws = A.take<bf16>((size_t)n * 32 * 32 * 512);
+  bf16* dws = A.take<bf16>((size_t)3 * n * 32 * 32 * 512);
   float* pbias = A.take<float>((size_t)n * 256);
+  float* gmean = A.take<float>((size_t)n * 512);
   bf16* proj = A.take<bf16>((size_t)n * 32 * 32 * 256);
   bf16* a1dw = A.take<bf16>((size_t)n * 32 * 32 * 256);
   bf16* a1pw = A.take<bf16>((size_t)n * 32 * 32 * 256);
@@ -368,17 +370,24 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   BDRC_TRY(conv_launch(ctx, "aspp.1x1", m->conv["decoder.aspp.0.convs.0.0"],
                        mk(x, n, 32, 32, 512, 0, 1, 1, 1, cat, 1024, 0, 1), s));
   const int rates[3] = {12, 24, 36};
-  for (int i = 0; i < 3; ++i) {
-    const std::string p = "decoder.aspp.0.convs." + std::to_string(i + 1);
-    bdrc_prof_begin(ctx, "aspp.dw3x3", 2.0 * n * 32 * 32 * 512 * 9, s);
-    BDRC_TRY(depthwise3x3_launch(ctx, x, 512, 0, n, 32, 32, 512, rates[i], m->dw[p + ".0.0"].w9c, dws, 512, 0, s));
+  {
+    const size_t br = (size_t)n * 32 * 32 * 512;
+    const float* dww[3];
+    bf16* dwo[3];
+    for (int i = 0; i < 3; ++i) {
+      dww[i] = m->dw["decoder.aspp.0.convs." + std::to_string(i + 1) + ".0.0"].w9c;
+      dwo[i] = dws + i * br;
+    }
+    bdrc_prof_begin(ctx, "aspp.dw3x3", 2.0 * n * 32 * 32 * 512 * 9 * 3, s);
+    BDRC_TRY(aspp_dw3_launch(ctx, x, n, 512, rates, dww, dwo, gmean, s));
     bdrc_prof_end(ctx, s);
-    BDRC_TRY(conv_launch(ctx, "aspp.1x1", m->conv[p + ".0.1"],
-                         mk(dws, n, 32, 32, 512, 0, 1, 1, 1, cat, 1024, 256 * (i + 1), 1), s));
+    for (int i = 0; i < 3; ++i)
+      BDRC_TRY(conv_launch(ctx, "aspp.1x1", m->conv["decoder.aspp.0.convs." + std::to_string(i + 1) + ".0.1"],
+                           mk(dwo[i], n, 32, 32, 512, 0, 1, 1, 1, cat, 1024, 256 * (i + 1), 1), s));
   }
   bdrc_prof_begin(ctx, "aspp.pool", 2.0 * n * (256.0 * 512 + 256 * 256), s);
   BDRC_TRY(aspp_pool_bias_launch(ctx, x, n, 32 * 32, 512, m->pool_w, m->pool_b, 256, m->proj_tail,
-                                 m->proj_b, 256, 256, pbias, s));
+                                 m->proj_b, 256, 256, pbias, gmean, s));
   bdrc_prof_end(ctx, s);
   {
     ConvArgs a = mk(cat, n, 32, 32, 1024, 0, 1, 1, 1, proj, 256, 0, 1);

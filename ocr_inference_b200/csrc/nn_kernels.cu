@@ -296,6 +296,96 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
   }
 }
 
+// The three dilated depthwise 3x3 branches of the ASPP (rates 12 / 24 / 36 on a 32x32 map, ipynb:L411-L420)
+// in ONE launch: a CTA pulls the whole 32x32 map of one (image, 64-channel chunk) into shared memory
+// with a single TMA box (128 KB) and produces the three branch outputs from it, so the input is read
+// once instead of 3 x (up to) 9 times and two launches disappear.  Taps that fall outside the map are
+// skipped (at rate 36 only the centre tap survives).  Summation order per output is (r, s) row-major.
+constexpr int ASPP_HW = 32;
+__global__ void __launch_bounds__(256)
+aspp_dw3_kernel(const __grid_constant__ CUtensorMap tmap, int C, int r0, int r1, int r2,
+                const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2,
+                bf16* __restrict__ o0, bf16* __restrict__ o1, bf16* __restrict__ o2, float* __restrict__ mean_out,
+                int* errflag) {
+  extern __shared__ __align__(128) uint8_t aspp_smem_raw[];
+  uint8_t* slab = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aspp_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float part[32][64];
+  const int chunks = C / 64;
+  const int ch = blockIdx.x % chunks, n = blockIdx.x / chunks;
+  const int tid = threadIdx.x, c8 = tid & 7, g = tid >> 3;
+  if (tid == 0) {
+    tcptx::mbar_init(tcptx::smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tcptx::mbar_arrive_expect_tx(tcptx::smem_u32(&bar), ASPP_HW * ASPP_HW * 128);
+    tcptx::tma_load_4d(tcptx::smem_u32(slab), &tmap, tcptx::smem_u32(&bar), ch * 64, 0, 0, n);
+  }
+  tcptx::mbar_wait(tcptx::smem_u32(&bar), 0, errflag, 10);
+  if (mean_out) {
+    // global average of the map (the ASPP image-pooling branch, ipynb:L421) while it is in shared memory;
+    // fixed summation order: 32 pixels per thread, then the 32 thread groups in order
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int j = 0; j < ASPP_HW; ++j) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(slab + (size_t)(g + 32 * j) * 128 + c8 * 16), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) part[g][c8 * 8 + q] = acc[q];
+    __syncthreads();
+    if (tid < 64) {
+      float sum = 0.f;
+      for (int k = 0; k < 32; ++k) sum += part[k][tid];
+      mean_out[(size_t)n * C + ch * 64 + tid] = sum / (float)(ASPP_HW * ASPP_HW);
+    }
+  }
+  const int rates[3] = {r0, r1, r2};
+  const float* ws[3] = {w0, w1, w2};
+  bf16* outs[3] = {o0, o1, o2};
+#pragma unroll 1
+  for (int b = 0; b < 3; ++b) {
+    const int d = rates[b];
+    float w[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ws[b] + k * C + ch * 64 + c8 * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(ws[b] + k * C + ch * 64 + c8 * 8 + 4));
+      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+      w[k][4] = c.x; w[k][5] = c.y; w[k][6] = c.z; w[k][7] = c.w;
+    }
+    bf16* ob = outs[b] + (size_t)n * ASPP_HW * ASPP_HW * C + ch * 64 + c8 * 8;
+#pragma unroll 2
+    for (int j = 0; j < ASPP_HW; ++j) {
+      const int p = g + 32 * j;               // a warp covers 4 consecutive pixels: 512 contiguous bytes
+      const int y = p / ASPP_HW, x = p % ASPP_HW;
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int iy = y + (r - 1) * d;
+        if (iy < 0 || iy >= ASPP_HW) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ix = x + (s - 1) * d;
+          if (ix < 0 || ix >= ASPP_HW) continue;
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(slab + (size_t)(iy * ASPP_HW + ix) * 128 + c8 * 16), f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = fmaf(f[q], w[r * 3 + s][q], acc[q]);
+        }
+      }
+      *reinterpret_cast<uint4*>(ob + (size_t)p * C) = pack8(acc);
+    }
+  }
+}
+
 // x4 (or xf) align_corners=True upsample, strip variant: each thread produces UP_STRIP consecutive
 // output rows of one column for 8 channels and re-loads a low-res row pair only when it changes
 constexpr int UP_STRIP = 8;
@@ -413,15 +503,17 @@ __global__ void __launch_bounds__(512)
 aspp_pool_bias_kernel(const bf16* __restrict__ x, int HW, int Cin, const float* __restrict__ Wp,
                       const float* __restrict__ bp, int Cmid, const float* __restrict__ Wtail,
                       const float* __restrict__ bproj, int Cout, int Cout_pad,
-                      float* __restrict__ bias_eff) {
+                      float* __restrict__ bias_eff, const float* __restrict__ mean_in) {
   extern __shared__ float pb_smem[];
   float* g = pb_smem;          // [Cin]
   float* h = pb_smem + Cin;    // [Cmid]
   float* part = h + Cmid;      // [slices][Cin] partial sums
   const int n = blockIdx.x;
   const bf16* xb = x + (size_t)n * HW * Cin;
-  // mean over HW: thread = (8-channel group, pixel slice); 128-bit loads, smem atomics to combine
-  {
+  if (mean_in) {
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) g[c] = mean_in[(size_t)n * Cin + c];
+  } else {
+  // mean over HW: thread = (8-channel group, pixel slice); 128-bit loads, fixed-order combine
     const int C8 = Cin / 8;
     const int slices = blockDim.x / C8 > 0 ? blockDim.x / C8 : 1;
     const int cg = threadIdx.x % C8, ps = threadIdx.x / C8;
@@ -599,6 +691,30 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
   return 0;
 }
 
+int aspp_dw3_launch(bdrc_ctx* ctx, const bf16* x, int N, int C, const int rates[3], const float* const w9c[3],
+                    bf16* const out[3], float* mean_out, cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 64 == 0 && bdrc_tma_encode_fn() != nullptr, "aspp_dw3: C %% 64 != 0 or no TMA encoder");
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)C, ASPP_HW, ASPP_HW, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)ASPP_HW * C * 2, (cuuint64_t)ASPP_HW * ASPP_HW * C * 2};
+  cuuint32_t box[4] = {64, ASPP_HW, ASPP_HW, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = bdrc_tma_encode_fn()(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), dims, strides, box,
+                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "aspp_dw3: cuTensorMapEncodeTiled failed: %d", (int)r);
+  const size_t smem = (size_t)ASPP_HW * ASPP_HW * 128 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(aspp_dw3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  aspp_dw3_kernel<<<N * (C / 64), 256, smem, s>>>(map, C, rates[0], rates[1], rates[2], w9c[0], w9c[1], w9c[2], out[0],
+                                                 out[1], out[2], mean_out, ctx->d_errflag);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
 int upsample_bilinear_ac_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, int f,
                                 bf16* out, int out_ld, int out_coff, cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0, "upsample: C %% 8 != 0");
@@ -618,9 +734,9 @@ int upsample_logits_launch(bdrc_ctx* ctx, const float* in, int N, int h, int w, 
 
 int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, const float* Wp,
                           const float* bp, int Cmid, const float* Wtail, const float* bproj,
-                          int Cout, int Cout_pad, float* bias_eff, cudaStream_t s) {
+                          int Cout, int Cout_pad, float* bias_eff, const float* mean_in, cudaStream_t s) {
   aspp_pool_bias_kernel<<<N, 512, (size_t)(Cin + Cmid + (512 / (Cin / 8)) * Cin) * sizeof(float), s>>>(
-      x, HW, Cin, Wp, bp, Cmid, Wtail, bproj, Cout, Cout_pad, bias_eff);
+      x, HW, Cin, Wp, bp, Cmid, Wtail, bproj, Cout, Cout_pad, bias_eff, mean_in);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

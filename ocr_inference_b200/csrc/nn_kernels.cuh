@@ -31,7 +31,8 @@ int upsample_logits_launch(bdrc_ctx* ctx, const float* in, int N, int h, int w, 
 //   g = mean_hw(x) [Cin]; h = relu(Wp g + bp) [Cmid]; bias_eff = b_proj + Wtail h  [Cout_pad]
 int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, const float* Wp,
                           const float* bp, int Cmid, const float* Wtail, const float* bproj,
-                          int Cout, int Cout_pad, float* bias_eff, cudaStream_t s);
+                          int Cout, int Cout_pad, float* bias_eff, const float* mean_in, cudaStream_t s);
+// mean_in (optional): precomputed g [N][Cin] (aspp_dw3_launch produces it while the map is in shared memory)
 
 // Easter2 squeeze-excite over time: gate = sigmoid(W2 relu(W1 mean_T(d) + b1) + b2)
 int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
@@ -45,3 +46,8 @@ int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* 
 // folded) -> bf16 NHWC [N][128][128][64].  w_bf16: [64 cout][64 k] with k = 8 * kernel_row + kernel_col.
 int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* w_bf16, const float* bias, bf16* out,
                         cudaStream_t s);
+
+// The three dilated depthwise 3x3 ASPP branches (32x32 maps) in one launch: x [N][32][32][C] -> out[i] (same shape),
+// rate rates[i], weights w9c[i] fp32 [9][C].
+int aspp_dw3_launch(bdrc_ctx* ctx, const bf16* x, int N, int C, const int rates[3], const float* const w9c[3],
+                    bf16* const out[3], float* mean_out, cudaStream_t s);

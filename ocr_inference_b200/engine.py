@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 
 import numpy as np
 import torch
@@ -70,7 +71,10 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.ctx = _lib.Context(device)
         self.lib = self.ctx.lib
-        self._ws: dict[str, torch.Tensor] = {}
+        # workspaces and pinned staging buffers are per host thread: run_ocr_batch drives one page per
+        # worker thread, each on its own CUDA stream
+        self._ws: dict[tuple, torch.Tensor] = {}
+        self._pin: dict[tuple, list] = {}
 
     # ---- plumbing ------------------------------------------------------------------------
     @property
@@ -81,11 +85,32 @@ class Engine:
         self.ctx.check(rc, what)
 
     def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
-        t = self._ws.get(key)
+        k = (key, threading.get_ident())
+        t = self._ws.get(k)
         if t is None or t.numel() < nbytes:
             t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
-            self._ws[key] = t
+            self._ws[k] = t
         return t
+
+    def _pinned(self, key: str, nbytes: int) -> torch.Tensor:
+        """Grow-only pinned staging buffer of this thread (cudaHostAlloc per call costs milliseconds).
+        The previous asynchronous copy out of it is waited for before it is handed out again."""
+        k = (key, threading.get_ident())
+        ent = self._pin.get(k)
+        if ent is not None and ent[1] is not None:
+            ent[1].synchronize()
+        if ent is None or ent[0].numel() < nbytes:
+            ent = [torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, pin_memory=True), None]
+            self._pin[k] = ent
+        return ent[0][:max(nbytes, 1)]
+
+    def _upload(self, key: str, host: torch.Tensor) -> torch.Tensor:
+        """Asynchronous H2D of a buffer obtained from _pinned(key, ...)."""
+        dev = host.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pin[(key, threading.get_ident())][1] = ev
+        return dev
 
     def launch_count(self) -> int:
         return self.ctx.launch_count()
@@ -248,11 +273,11 @@ class Engine:
         if len(masks) > 1:
             off[1:] = np.cumsum([(s + 15) // 16 * 16 for s in sizes[:-1]])
         total = int(off[-1] + sizes[-1]) if masks else 0
-        host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        host = self._pinned("masks", total)
         hv = host.numpy()
         for m, o, s in zip(masks, off, sizes):
             hv[o:o + s] = np.ascontiguousarray(m, dtype=np.uint8).reshape(-1)
-        dev = host.to(self.device, non_blocking=True)
+        dev = self._upload("masks", host)
         return dict(dev=dev, roi=roi, off=off)
 
     def _sub_pack(self, pack, idx):
@@ -311,12 +336,12 @@ class Engine:
         if len(crops) > 1:
             off[1:] = np.cumsum([(s + 15) // 16 * 16 for s in sizes[:-1]])
         total = int(off[-1] + sizes[-1]) if crops else 0
-        host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        host = self._pinned("crops", total)
         hv = host.numpy()
         for c, o, s in zip(crops, off, sizes):
             if s:
                 hv[o:o + s] = np.ascontiguousarray(c[..., :3]).reshape(-1)
-        dev = host.to(self.device, non_blocking=True)
+        dev = self._upload("crops", host)
         return dev, torch.from_numpy(hw).to(self.device), torch.from_numpy(off).to(self.device)
 
     def ocr_prepare_lines(self, crops_dev, hw_dev, off_dev, L: int, Ht: int, Wt: int, pre_pad: bool,

@@ -9,6 +9,8 @@ throughput; the single-image methods give identical results.
 from __future__ import annotations
 
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import Sequence
 
 import numpy as np
@@ -87,6 +89,7 @@ class Detection:
         self.engine = engine or get_engine()
         n_out = 1 if self._mode == POST_SIGMOID else len(config.classes)
         self._inference = self.engine.load_model(SEG, _read_weights(config.onnx_file), n_out)
+        self._tls = threading.local()   # .last = (host image, its device copy) of this thread's latest predict()
 
     # device-resident stages ----------------------------------------------------------------
     def _predict_device(self, page_dev: torch.Tensor, class_threshold: float) -> torch.Tensor:
@@ -125,6 +128,7 @@ class Detection:
     def predict(self, image: np.ndarray, class_threshold: float | None = None) -> np.ndarray:
         thr = self._default_threshold if class_threshold is None else class_threshold
         page = torch.from_numpy(np.ascontiguousarray(image[..., :3], dtype=np.uint8)).to(self.engine.device)
+        self._tls.last = (image, page)
         return self._predict_device(page, thr).cpu().numpy()
 
     def predict_batch(self, images: Sequence[np.ndarray], class_threshold: float | None = None,
@@ -243,8 +247,10 @@ class OCRInference:
         return self.run_batch([line_image], pre_pad, use_lm)[0]
 
     def run_packed(self, crops_dev, hw_dev, off_dev, n: int, pre_pad: bool):
-        """Lines already resident on the GPU (from extract_line_images): ids per line."""
+        """Lines already resident on the GPU (from extract_line_images): text per line."""
         eng = self.engine
+        if n == 0:
+            return []
         lines, _ = eng.ocr_prepare_lines(crops_dev, hw_dev, off_dev, n, self._input_height, self._input_width, pre_pad)
         logits = eng.ocr_forward(self.ocr_session, lines)
         ids, lens = eng.ctc_greedy(logits, layout=LAYOUT_TV, blank=self.ctc_decoder.blank_index)
@@ -282,6 +288,7 @@ class OCRPipeline:
         except Exception:  # noqa: BLE001
             self.converter = _IdentityConverter()
         self.use_line_prepadding = use_line_prepadding
+        self._tls = threading.local()   # .fast: run_ocr keeps line crops on the device between stages 4 and 5
         if isinstance(self.line_config, LineDetectionConfig):
             self.line_inference = LineDetection(self.line_config, engine=self.engine)
             self.ready = True
@@ -352,7 +359,12 @@ class OCRPipeline:
 
         line_data = [build_line_data(c) for c in filtered_contours]
         sorted_lines, _ = sort_lines_by_threshold2(rot_mask, line_data, group_lines=merge_lines)
-        line_images = extract_line_images(work_img, sorted_lines, k_factor, bbox_tolerance)
+        # the page uploaded by detect_lines is still resident when the page was not rotated / dewarped
+        last = getattr(self.line_inference._tls, "last", None) if self.line_inference is not None else None
+        page_dev = last[1] if last is not None and last[0] is work_img and work_img.ndim == 3 \
+            and work_img.shape[2] == 3 else None
+        line_images = extract_line_images(work_img, sorted_lines, k_factor, bbox_tolerance, page_dev=page_dev,
+                                          download=not getattr(self._tls, "fast", False))
         if not line_images:
             return OpStatus.FAILED, "No valid line images extracted"
         return OpStatus.SUCCESS, (sorted_lines, line_images)
@@ -367,8 +379,16 @@ class OCRPipeline:
 
     def run_text_recognition(self, line_images: list, sorted_lines: list, target_encoding: Encoding = Encoding.UNICODE):
         """All non-empty lines of the page go through the recogniser as ONE batch."""
-        keep = [(img, ln) for img, ln in zip(line_images, sorted_lines) if img.shape[0] != 0 and img.shape[1] != 0]
-        texts = self.ocr_inference.run_batch([k[0] for k in keep], self.use_line_prepadding) if keep else []
+        keep_idx = [i for i, img in enumerate(line_images) if img.shape[0] != 0 and img.shape[1] != 0]
+        keep = [(line_images[i], sorted_lines[i]) for i in keep_idx]
+        pack = getattr(line_images, "device_pack", None)
+        if keep and pack is not None and list(pack[3]) == keep_idx and len(line_images) == len(sorted_lines):
+            # crops are still on the GPU in exactly this order: no download / re-upload
+            for img, _ in keep:
+                self.ocr_inference._check_fit(img, self.use_line_prepadding)
+            texts = self.ocr_inference.run_packed(pack[0], pack[1], pack[2], len(keep), self.use_line_prepadding)
+        else:
+            texts = self.ocr_inference.run_batch([np.asarray(k[0]) for k in keep], self.use_line_prepadding) if keep else []
         ocr_lines = []
         for (_, ln), t in zip(keep, texts):
             pred = self._convert(t.strip().replace("§", " "), target_encoding)
@@ -383,6 +403,14 @@ class OCRPipeline:
     def run_ocr(self, image: np.ndarray, k_factor: float = 2.5, bbox_tolerance: float = 4.0, merge_lines: bool = True,
                 use_tps: bool = False, tps_threshold: float = 0.25, target_encoding: Encoding = Encoding.UNICODE,
                 eval_mode: bool = False):
+        self._tls.fast = True    # line crops are not part of run_ocr's result: they can stay on the GPU
+        try:
+            return self._run_ocr(image, k_factor, bbox_tolerance, merge_lines, use_tps, tps_threshold, target_encoding,
+                                 eval_mode)
+        finally:
+            self._tls.fast = False
+
+    def _run_ocr(self, image, k_factor, bbox_tolerance, merge_lines, use_tps, tps_threshold, target_encoding, eval_mode):
         try:
             if not self.ready:
                 return OpStatus.FAILED, "OCR pipeline not ready"
@@ -431,9 +459,28 @@ class OCRPipeline:
         except Exception as e:  # noqa: BLE001
             return OpStatus.FAILED, f"OCR pipeline failed: {str(e)}"
 
-    def run_ocr_batch(self, images: Sequence[np.ndarray], **kw):
-        """Pages are independent units: same results as [run_ocr(i) for i in images]."""
-        return [self.run_ocr(img, **kw) for img in images]
+    def run_ocr_batch(self, images: Sequence[np.ndarray], workers: int | None = None, **kw):
+        """Pages are independent units: same results as [run_ocr(i) for i in images].  `workers` host threads
+        each drive one page at a time on their own CUDA stream, so the cv2 geometry of one page (which
+        releases the GIL) overlaps the kernels and copies of the others."""
+        if workers is None:
+            workers = max(1, min(len(images), len(os.sched_getaffinity(0)), 12))
+        if workers <= 1 or len(images) <= 1:
+            return [self.run_ocr(img, **kw) for img in images]
+        dev = self.engine.device
+        tls = self._tls
+
+        def one(img):
+            if not hasattr(tls, "stream"):
+                torch.cuda.set_device(dev)
+                tls.stream = torch.cuda.Stream(dev)
+            with torch.cuda.stream(tls.stream):
+                return self.run_ocr(img, **kw)
+
+        pool = getattr(self, "_pool", None)
+        if pool is None or pool._max_workers != workers:
+            pool = self._pool = ThreadPoolExecutor(workers, thread_name_prefix="bdrc-page")
+        return list(pool.map(one, images))
 
 
 class ModernBookFormatLayoutDetection:

@@ -55,9 +55,12 @@ def rotate_from_angle(image: np.ndarray, angle: float) -> np.ndarray:
     return eng.warp_affine(src, M).cpu().numpy()
 
 
-def get_rotation_angle_from_lines(line_mask: np.ndarray, max_angle: float = 5.0, debug_angles: bool = False) -> float:
-    """Mean minAreaRect angle of the big blobs (> 0.1 % of the page), :107-142."""
-    blobs = [c for c in get_contours(line_mask) if cv2.contourArea(c) > line_mask.shape[0] * line_mask.shape[1] * 0.001]
+def get_rotation_angle_from_lines(line_mask: np.ndarray, max_angle: float = 5.0, debug_angles: bool = False,
+                                  _contours=None) -> float:
+    """Mean minAreaRect angle of the big blobs (> 0.1 % of the page), :107-142.  `_contours` (internal):
+    the result of get_contours(line_mask) when the caller already has it."""
+    found = get_contours(line_mask) if _contours is None else _contours
+    blobs = [c for c in found if cv2.contourArea(c) > line_mask.shape[0] * line_mask.shape[1] * 0.001]
     angles = [cv2.minAreaRect(c)[2] for c in blobs]
     low = [a for a in angles if abs(a) != 0.0 and a < max_angle]
     high = [a for a in angles if abs(a) != 90.0 and a > (90 - max_angle)]
@@ -74,13 +77,16 @@ def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold:
     """:212-244 -> (rotated image, rotated 3-channel mask, contours with area > 10, angle)."""
     if line_mask.ndim == 3:
         line_mask = cv2.cvtColor(line_mask, cv2.COLOR_BGR2GRAY)
-    angle = get_rotation_angle_from_lines(line_mask)
+    found = get_contours(line_mask)
+    angle = get_rotation_angle_from_lines(line_mask, _contours=found)
     if angle > rot_threshold:
         out_mask = rotate_from_angle(line_mask, angle)
         out_img = rotate_from_angle(image, angle)
+        found = get_contours(out_mask)
     else:
+        # unrotated: the reference runs the identical findContours call a second time (:238); reuse it
         out_mask, out_img = line_mask, image
-    contours = [c for c in get_contours(out_mask) if cv2.contourArea(c) > 10]
+    contours = [c for c in found if cv2.contourArea(c) > 10]
     return out_img, cv2.cvtColor(out_mask, cv2.COLOR_GRAY2RGB), contours, angle
 
 
@@ -207,6 +213,20 @@ class LineImages(list):
     device_pack = None
 
 
+class DeviceCrop:
+    """A line crop that stays on the GPU (run_ocr's internal fast path): has .shape like the ndarray the
+    reference returns and turns into one (one D2H copy) when numpy asks for it."""
+
+    def __init__(self, crops_dev: torch.Tensor, offset: int, shape: tuple[int, int, int]):
+        self._dev, self._off, self.shape = crops_dev, offset, shape
+        self.ndim, self.dtype = 3, np.dtype(np.uint8)
+
+    def __array__(self, dtype=None, copy=None):
+        h, w, c = self.shape
+        a = self._dev[self._off:self._off + h * w * c].cpu().numpy().reshape(h, w, c)
+        return a.astype(dtype) if dtype is not None else a
+
+
 def _roi_mask(contour: np.ndarray, H: int, W: int):
     """Filled contour rasterised into its (page-clipped) bounding box, as cv2.drawContours with
     thickness=-1 does on the full page (line_detection.py:349-351)."""
@@ -301,8 +321,10 @@ def _extract_on_device(page_dev: torch.Tensor, rois, masks, bbox_hs, default_k: 
 
 
 def extract_line_images(image: np.ndarray, line_data: list[Line], default_k: float = 1.7,
-                        bbox_tolerance: float = 3, page_dev: torch.Tensor | None = None) -> LineImages:
-    """:330-359.  `page_dev` (optional) is the same image already resident on the GPU."""
+                        bbox_tolerance: float = 3, page_dev: torch.Tensor | None = None,
+                        download: bool = True) -> LineImages:
+    """:330-359.  `page_dev` (optional) is the same image already resident on the GPU; with
+    download=False the crops stay on the device (DeviceCrop placeholders) for the recogniser."""
     eng = _engine()
     if image.ndim == 2:
         image = image[..., None]
@@ -321,10 +343,12 @@ def extract_line_images(image: np.ndarray, line_data: list[Line], default_k: flo
     if real:
         hw_h, off_h = hw.cpu().numpy(), off.cpu().numpy()
         total = int(off_h[-1] + ((int(hw_h[-1, 0]) * int(hw_h[-1, 1]) * C + 15) // 16) * 16)
-        buf = crops_dev[:max(total, 1)].cpu().numpy()
+        if download:
+            buf = crops_dev[:max(total, 1)].cpu().numpy()
         for p, i in enumerate(real):
             h, w = int(hw_h[p, 0]), int(hw_h[p, 1])
-            host[i] = buf[off_h[p]:off_h[p] + h * w * C].reshape(h, w, C).copy()
+            host[i] = (buf[off_h[p]:off_h[p] + h * w * C].reshape(h, w, C).copy() if download
+                       else DeviceCrop(crops_dev, int(off_h[p]), (h, w, C)))
         out.device_pack = (crops_dev, hw, off, real)
     for i in range(len(line_data)):
         if i in host:

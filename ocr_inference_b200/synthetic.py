@@ -68,3 +68,90 @@ def line_crop(seed: int, h: int | None = None, w: int | None = None) -> np.ndarr
 
 def line_crops(seed: int, n: int, fixed: tuple[int, int] | None = None) -> list[np.ndarray]:
     return [line_crop(seed * 100003 + i, *(fixed if fixed else (None, None))) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------
+# "glyph" lines: text-like line crops with a known transcription (76 fixed stroke glyphs, one per
+# charset symbol).  Used to fit the recogniser's output layer so that its logits are peaky like a
+# trained model's (tests/golden/make_heads.py) and as recognisable bench / parity inputs.
+# ------------------------------------------------------------------------------------------
+GLYPH_H, GLYPH_W = 44, 20
+_GLYPHS = None
+
+
+def glyph_bitmaps() -> np.ndarray:
+    """[76, GLYPH_H, GLYPH_W] u8 {0,1}: 1 = ink.  Fixed seed: part of the synthetic 'script'."""
+    global _GLYPHS
+    if _GLYPHS is None:
+        rng = np.random.default_rng(760076)
+        g = np.zeros((76, GLYPH_H, GLYPH_W), np.uint8)
+        for i in range(76):
+            c = np.zeros((GLYPH_H, GLYPH_W), np.uint8)
+            for _ in range(int(rng.integers(3, 6))):
+                p0 = (int(rng.integers(1, GLYPH_W - 1)), int(rng.integers(1, GLYPH_H - 1)))
+                p1 = (int(rng.integers(1, GLYPH_W - 1)), int(rng.integers(1, GLYPH_H - 1)))
+                if rng.random() < 0.65:
+                    cv2.line(c, p0, p1, 1, int(rng.integers(2, 4)))
+                else:
+                    cv2.ellipse(c, p0, (int(rng.integers(3, 8)), int(rng.integers(4, 12))), 0, 0, 360, 1, 2)
+            g[i] = c
+        _GLYPHS = g
+    return _GLYPHS
+
+
+def glyph_line(seed: int, n_chars: int | None = None, h: int | None = None):
+    """One line crop u8 [h,w,3] of glyphs + its transcription (indices into CHARSET_76)."""
+    rng = np.random.default_rng(seed)
+    glyphs = glyph_bitmaps()
+    h = int(rng.integers(64, 97)) if h is None else h
+    n = int(rng.integers(24, 61)) if n_chars is None else n_chars
+    ids = rng.integers(0, 76, n)
+    gaps = rng.integers(5, 12, n + 1)
+    w = int(gaps.sum() + n * GLYPH_W + 16)
+    ink = np.zeros((h, w), np.uint8)
+    x = 8 + int(gaps[0])
+    y0 = (h - GLYPH_H) // 2
+    for i, g in enumerate(ids):
+        dy = int(rng.integers(-3, 4))
+        ys = min(max(0, y0 + dy), h - GLYPH_H)
+        ink[ys:ys + GLYPH_H, x:x + GLYPH_W] |= glyphs[g]
+        x += GLYPH_W + int(gaps[i + 1])
+    bg = np.clip(rng.normal(225, 8, (h, w)), 0, 255)
+    fg = np.clip(rng.normal(40, 12, (h, w)), 0, 255)
+    img = np.where(ink > 0, fg, bg).astype(np.uint8)
+    img = cv2.GaussianBlur(img, (0, 0), 0.8)
+    return np.ascontiguousarray(np.stack([img, img, img], axis=-1)), [int(i) for i in ids]
+
+
+def glyph_lines(seed: int, n: int, **kw):
+    out = [glyph_line(seed * 100003 + i, **kw) for i in range(n)]
+    return [o[0] for o in out], [o[1] for o in out]
+
+
+def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (14, 22)):
+    """Synthetic page whose text bands are glyph lines with a known transcription (config C3/C5).
+    Returns (u8 [H,W,3], band boxes (x,y,w,h), transcriptions as CHARSET_76 index lists)."""
+    rng = np.random.default_rng(seed)
+    glyphs = glyph_bitmaps()
+    g = np.clip(rng.normal(215, 12, (H, W)), 0, 255).astype(np.uint8)
+    n = int(rng.integers(n_lines[0], n_lines[1] + 1))
+    pitch = H / (n + 1)
+    boxes, texts = [], []
+    for li in range(n):
+        y = int(pitch * (li + 0.5) + rng.integers(-4, 5))
+        x0 = int(rng.integers(W // 40, W // 10))
+        x1 = W - int(rng.integers(W // 40, W // 10))
+        x, ids = x0, []
+        while x + GLYPH_W < x1:
+            gid = int(rng.integers(0, 76))
+            dy = int(rng.integers(-2, 3))
+            ys = min(max(0, y + dy), H - GLYPH_H)
+            ink = glyphs[gid] > 0
+            patch = g[ys:ys + GLYPH_H, x:x + GLYPH_W]
+            patch[ink] = np.clip(rng.normal(40, 12, int(ink.sum())), 0, 255).astype(np.uint8)
+            ids.append(gid)
+            x += GLYPH_W + int(rng.integers(5, 12))
+        boxes.append((x0, y, x - x0, GLYPH_H))
+        texts.append(ids)
+    g = cv2.GaussianBlur(g, (3, 3), 0)
+    return np.ascontiguousarray(np.stack([g, g, g], axis=-1)), boxes, texts

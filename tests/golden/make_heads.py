@@ -1,0 +1,195 @@
+"""Trains the recogniser and fits the segmentation head on synthetic data, so that their logits look
+like a trained model's (peaky, temporally / spatially coherent) instead of 77-way near-ties.
+
+    python tests/golden/make_heads.py          # CPU, a few minutes; writes tests/golden/fitted_heads.npz
+
+Why: BASELINE.json's parity target is ">= 95 % identical decoded lines vs the reference CPU path".
+With a random-init recogniser the top-2 margin of most time steps is below the bf16 tolerance, so a
+whole-line comparison measures coin flips.  A real checkpoint cannot be shipped (no network), so the
+recogniser (6.2 M parameters, minutes on a CPU) is trained here on the "glyph" lines of
+ocr_inference_b200/synthetic.py, and the last two 1x1 layers of the segmentation network are fitted to
+the text-band mask of synthetic pages (its ResNet body stays the seeded random init).  The oracle (torch-CPU fp32) produces the
+features; the GPU path and the oracle then load the SAME fitted tensors
+(synthetic_weights.easter2_weights_fitted / seg_weights_fitted).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from ocr_inference_b200 import synthetic  # noqa: E402
+from oracle import hostops as ho  # noqa: E402
+from oracle import nets  # noqa: E402
+
+OUT = os.path.join(HERE, "fitted_heads.npz")
+OCR_SEED, SEG_SEED, V = 7, 11, 77
+
+
+def train_easter2(n_steps: int = 500):
+    """Easter2 trained from the seeded init on synthetic.glyph_line(): 60 % of the steps
+    with frame-wise cross-entropy (glyph centres are known), then CTC, at W = 512 / 1000, then a short
+    full-width (80 x 2000, real a-7 geometry) CTC fine-tune.  ~9 minutes on 8 cores."""
+    torch.manual_seed(0)
+    w0 = nets.easter2_weights(OCR_SEED, V, 80)
+    P = {k: torch.from_numpy(v.copy()).requires_grad_(True) for k, v in w0.items()}
+    with torch.no_grad():
+        P["head.weight"] *= 0.1
+
+    def c1d(name, x, stride=1, pad=0, dil=1):
+        return F.conv1d(x, P[name + ".weight"], P[name + ".bias"], stride=stride, padding=pad, dilation=dil)
+
+    def fwd(x):   # same graph as oracle/nets.py:easter2_forward, differentiable
+        x = F.relu(c1d("conv1", x, 2, 1))
+        x = F.relu(c1d("conv2", x, 2, 1))
+        old = data = x
+        for u, k in zip((1, 2, 3), (5, 7, 9)):
+            p = f"unit{u}"
+            res = c1d(p + ".res_old", old) + c1d(p + ".res_data", data)
+            d = F.relu(c1d(p + ".conv_a", data, pad=k // 2))
+            d = F.relu(c1d(p + ".conv_b", d, pad=k // 2))
+            d = c1d(p + ".conv_c", d, pad=k // 2)
+            z = F.relu(F.linear(d.mean(dim=2), P[p + ".se_fc1.weight"], P[p + ".se_fc1.bias"]))
+            g = torch.sigmoid(F.linear(z, P[p + ".se_fc2.weight"], P[p + ".se_fc2.bias"]))
+            data = F.relu(res + d * g.unsqueeze(-1))
+            old = res
+        x = F.relu(c1d("conv3", data, pad=10, dil=2))
+        return c1d("head", F.relu(c1d("conv4", x)))
+
+    def glyph_centres(seed, nch):   # replays the generator's draws (h and n_chars given -> two draws only)
+        r = np.random.default_rng(seed)
+        r.integers(0, 76, nch)
+        gaps = r.integers(5, 12, nch + 1)
+        cs, x = [], 8 + int(gaps[0])
+        for k in range(nch):
+            cs.append(x + synthetic.GLYPH_W / 2)
+            x += synthetic.GLYPH_W + int(gaps[k + 1])
+        return cs
+
+    def short_batch(seed, n, Wt):
+        xs, ts, labs = [], [], []
+        for i in range(n):
+            nch = int((Wt - 40) // 30)
+            img, ids = synthetic.glyph_line(seed * 1000 + i, n_chars=nch, h=80)
+            xs.append(ho.prepare_ocr_line(img, 80, Wt, pre_pad=False).reshape(80, Wt))
+            offx = (Wt - img.shape[1]) // 2
+            lab = np.zeros(Wt // 4, np.int64)
+            for c, k in zip(glyph_centres(seed * 1000 + i, nch), ids):
+                t = int((c + offx) // 4)
+                lab[t] = k + 1
+                if t + 1 < Wt // 4:
+                    lab[t + 1] = k + 1
+            ts.append([k + 1 for k in ids])
+            labs.append(lab)
+        return torch.from_numpy(np.stack(xs)), ts, torch.from_numpy(np.stack(labs))
+
+    opt = torch.optim.Adam(list(P.values()), lr=1e-3)
+
+    def apply(loss):
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(P.values()), 5.0)
+        opt.step()
+        return loss.item()
+
+    def step_frames(x, labs):
+        wts = torch.ones(V)
+        wts[0] = 0.3
+        return apply(F.cross_entropy(fwd(x), labs, weight=wts))
+
+    def step_ctc(x, ts):
+        lp = F.log_softmax(fwd(x), dim=1).permute(2, 0, 1)
+        tg = torch.cat([torch.tensor(t) for t in ts])
+        tl = torch.tensor([len(t) for t in ts])
+        return apply(F.ctc_loss(lp, tg, torch.full((x.shape[0],), lp.shape[0], dtype=torch.long), tl, blank=0,
+                                zero_infinity=True))
+
+    t0 = time.time()
+    for it in range(n_steps):
+        Wt = 512 if it < n_steps * 0.8 else 1000
+        x, ts, labs = short_batch(it + 1, 24 if Wt == 512 else 12, Wt)
+        loss = step_frames(x, labs) if it < n_steps * 0.6 else step_ctc(x, ts)
+        if it % 50 == 0:
+            print(f"  ocr it {it} W={Wt} loss {loss:.3f} {time.time() - t0:.0f}s", flush=True)
+    crops, texts = synthetic.glyph_lines(9001, 64)
+    Xf = torch.from_numpy(np.stack([ho.prepare_ocr_line(c, 80, 2000, pre_pad=False).reshape(80, 2000) for c in crops]))
+    for it in range(60):
+        idx = torch.randperm(48)[:8]
+        loss = step_ctc(Xf[idx], [[k + 1 for k in texts[j]] for j in idx.tolist()])
+    with torch.no_grad():
+        lo = fwd(Xf[48:]).numpy()
+    ok = sum(ho.ctc_greedy_ids(lo[j], V) == [k + 1 for k in texts[48 + j]] for j in range(16))
+    srt = np.sort(lo, axis=1)
+    m = srt[:, -1] - srt[:, -2]
+    print(f"ocr held-out exact lines {ok}/16; logit std {lo.std():.2f}; top-2 margin median {np.median(m):.2f}, "
+          f"1st pct {np.percentile(m, 1):.3f}")
+    return {"ocr." + k: v.detach().numpy().astype(np.float16) for k, v in P.items()}
+
+
+def seg_tiles_and_targets(seeds, H=1024, W=1536):
+    xs, ys = [], []
+    for s in seeds:
+        page, boxes = synthetic.page(s, H, W)
+        tiles, meta = ho.seg_preprocess(page, closed_form=False)
+        m = synthetic.band_mask(boxes, H, W)
+        for ty in range(H // 512):
+            for tx in range(W // 512):
+                t = m[ty * 512:(ty + 1) * 512, tx * 512:(tx + 1) * 512].astype(np.float32) / 255.0
+                ys.append(t.reshape(128, 4, 128, 4).mean(axis=(1, 3)))
+        xs.append(tiles)
+    return np.concatenate(xs), np.stack(ys)
+
+
+def fit_seg():
+    """decoder.block2.0.1 (1x1 304->256 + ReLU) and segmentation_head.0 (1x1 256->1) as a per-pixel MLP on
+    the (random-init) depthwise output, trained against the text-band mask at 128x128."""
+    torch.manual_seed(0)
+    w = nets.seg_weights(SEG_SEED, 1, 3)
+    tiles, tgt = seg_tiles_and_targets([501, 502, 503, 504, 505, 506])
+    t0 = time.time()
+    feats = np.concatenate([nets.seg_forward(w, np.repeat(tiles[i:i + 4, None].astype(np.float32), 3, axis=1),
+                                             return_features="block2_dw") for i in range(0, len(tiles), 4)])
+    print(f"seg features {feats.shape} in {time.time() - t0:.1f}s")
+    X = torch.from_numpy(feats).permute(0, 2, 3, 1).reshape(-1, 304)
+    y = torch.from_numpy((tgt > 0.5).astype(np.float32)).reshape(-1)
+    nva = 6 * 128 * 128
+    Xtr, ytr, Xva, yva = X[:-nva], y[:-nva], X[-nva:], y[-nva:]
+    w1 = torch.from_numpy(w["decoder.block2.0.1.weight"][:, :, 0, 0]).clone().requires_grad_(True)
+    b1 = torch.from_numpy(w["decoder.block2.0.1.bias"]).clone().requires_grad_(True)
+    w2 = torch.zeros(1, 256, requires_grad=True)
+    b2 = torch.zeros(1, requires_grad=True)
+    opt = torch.optim.Adam([w1, b1, w2, b2], lr=2e-3)
+    for it in range(1500):
+        idx = torch.randint(0, Xtr.shape[0], (8192,))
+        z = F.linear(F.relu(F.linear(Xtr[idx], w1, b1)), w2, b2)[:, 0]
+        loss = F.binary_cross_entropy_with_logits(z, ytr[idx])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if it % 250 == 0 or it == 1499:
+            print(f"  seg it {it} bce {loss.item():.4f}")
+    with torch.no_grad():
+        z = F.linear(F.relu(F.linear(Xva, w1, b1)), w2, b2)[:, 0]
+        acc = ((z > 0).float() == yva).float().mean().item()
+        print(f"seg head: held-out pixel accuracy {acc:.4f}, positives {yva.mean().item():.3f}, logit std {z.std().item():.2f}")
+    return {"seg.decoder.block2.0.1.weight": w1.detach().numpy().reshape(256, 304, 1, 1).astype(np.float16),
+            "seg.decoder.block2.0.1.bias": b1.detach().numpy().astype(np.float32),
+            "seg.segmentation_head.0.weight": w2.detach().numpy().reshape(1, 256, 1, 1).astype(np.float32),
+            "seg.segmentation_head.0.bias": b2.detach().numpy().reshape(1).astype(np.float32)}
+
+
+def main():
+    out = {}
+    out.update(fit_seg())
+    out.update(train_easter2())
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()
