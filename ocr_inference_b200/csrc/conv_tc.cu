@@ -76,6 +76,13 @@ __device__ __forceinline__ void decode_mtile(const TcParams& p, int mt, int& img
   oy0 = ht * p.BH;
 }
 
+// CTAS = 1: one CTA per SM works alone (cta_group::1, M = 128).
+// CTAS = 2: the two CTAs of a cluster form a pair (cta_group::2, M = 256).  Each CTA loads the A slabs of its
+//   own G pixel tiles and HALF of the B tile; the leader (cluster rank 0) issues one MMA for both, which reads
+//   A and the B half from each CTA's own shared memory -- 8 KB instead of 12 KB of operand reads per CTA per
+//   128-cycle MMA at N = 256, which is what the shared-memory operand path (~64 B/clk/SM, measured: the
+//   single-CTA kernel tops out at 67 % tensor-pipe activity with all loads and the epilogue disabled) can feed.
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
@@ -84,7 +91,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int G = p.G;
-  const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 2;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int unit_id = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // CTA or CTA pair
+  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t b_stage_bytes = (uint32_t)(p.BN / CTAS) * BK * 2;
   const uint32_t a_bytes = (uint32_t)G * A_STAGE_BYTES;
   const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
@@ -108,18 +118,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 8);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[i]), 8 * CTAS);  // one arrive per epilogue warp (of both CTAs on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -130,14 +147,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
+      // in a pair both CTAs signal the LEADER's full barrier; only the leader arms it (for both CTAs' bytes)
+      const uint32_t full0 = CTAS == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      for (int st = unit_id; st < p.total_tiles; st += n_units) {
         const int nt = st % p.tiles_n;
         const int mg = st / p.tiles_n;
-        const int n0 = nt * p.BN;
+        const int n0 = nt * p.BN + (int)cta_rank * (p.BN / CTAS);
         int img[MAX_G], oy0[MAX_G], ox0[MAX_G];
 #pragma unroll
         for (int g = 0; g < MAX_G; ++g)
-          if (g < G) decode_mtile(p, mg * G + g, img[g], oy0[g], ox0[g]);
+          if (g < G) decode_mtile(p, (mg * CTAS + (int)cta_rank) * G + g, img[g], oy0[g], ox0[g]);
         for (int r = 0; r < p.R; ++r) {
           const int th = r * p.dil_h - p.pad_h;
           const int par_h = ((th % p.stride_h) + p.stride_h) % p.stride_h;
@@ -148,20 +167,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const int off_w = floordiv(tw - par_w, p.stride_w);
             for (int kc = 0; kc < p.kchunks; ++kc) {
               mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.errflag, 1);
-              const uint32_t fb = smem_u32(&full_bar[stage]);
+              const uint32_t fb = full0 + (uint32_t)stage * 8u;
               const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-              const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : a_bytes) + ((p.dbg_skip & 2) ? 0u : b_stage_bytes);
-              if (elect_one()) {
-                if (bytes) mbar_arrive_expect_tx(fb, bytes); else mbar_arrive(fb);
-                if (!(p.dbg_skip & 1)) {
+              if (CTAS == 2) {
+                if (elect_one()) {
+                  if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2u * (a_bytes + b_stage_bytes));
 #pragma unroll
                   for (int g = 0; g < MAX_G; ++g)
                     if (g < G)
-                      tma_load_5d(a_dst + (uint32_t)g * A_STAGE_BYTES, &tmapA, fb, par_w * p.par_c + kc * BK,
-                                  ox0[g] + off_w, par_h, oy0[g] + off_h, img[g]);
+                      tma_load_5d_2sm(a_dst + (uint32_t)g * A_STAGE_BYTES, &tmapA, fb, par_w * p.par_c + kc * BK,
+                                      ox0[g] + off_w, par_h, oy0[g] + off_h, img[g]);
+                  tma_load_2d_2sm(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
                 }
-                if (!(p.dbg_skip & 2))
-                  tma_load_2d(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
+              } else {
+                const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : a_bytes) + ((p.dbg_skip & 2) ? 0u : b_stage_bytes);
+                if (elect_one()) {
+                  if (bytes) mbar_arrive_expect_tx(fb, bytes); else mbar_arrive(fb);
+                  if (!(p.dbg_skip & 1)) {
+#pragma unroll
+                    for (int g = 0; g < MAX_G; ++g)
+                      if (g < G)
+                        tma_load_5d(a_dst + (uint32_t)g * A_STAGE_BYTES, &tmapA, fb, par_w * p.par_c + kc * BK,
+                                    ox0[g] + off_w, par_h, oy0[g] + off_h, img[g]);
+                  }
+                  if (!(p.dbg_skip & 2))
+                    tma_load_2d(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
+                }
               }
               __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -172,12 +203,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) ============
-    {
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
+      for (int st = unit_id; st < p.total_tiles; st += n_units) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G * p.BN);
@@ -192,17 +223,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               // advance 16 bf16 = 32 B along K inside the 128-byte swizzle row: +2 in 16-B units
 #pragma unroll
               for (int g = 0; g < MAX_G; ++g)
-                if (g < G)
-                  tc_mma_bf16(d_tmem + (uint32_t)(g * p.BN),
-                              make_sdesc(a_addr + (uint32_t)g * A_STAGE_BYTES) + (uint64_t)(2 * k),
-                              bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                if (g < G) {
+                  if (CTAS == 2)
+                    tc_mma_bf16_2sm(d_tmem + (uint32_t)(g * p.BN),
+                                    make_sdesc(a_addr + (uint32_t)g * A_STAGE_BYTES) + (uint64_t)(2 * k),
+                                    bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                  else
+                    tc_mma_bf16(d_tmem + (uint32_t)(g * p.BN),
+                                make_sdesc(a_addr + (uint32_t)g * A_STAGE_BYTES) + (uint64_t)(2 * k),
+                                bdesc + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
             }
-            tc_commit(smem_u32(&empty_bar[stage]));   // frees the smem slot when the MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+            if (CTAS == 2) tc_commit_2sm(smem_u32(&empty_bar[stage])); else tc_commit(smem_u32(&empty_bar[stage]));
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));   // accumulators complete -> epilogue
+        if (elect_one()) {   // accumulators complete -> epilogue (of both CTAs)
+          if (CTAS == 2) tc_commit_2sm(smem_u32(&tfull_bar[acc])); else tc_commit(smem_u32(&tfull_bar[acc]));
+        }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -227,9 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t use = 0;                          // staging buffer toggle
-    for (int st = blockIdx.x; st < p.total_tiles; st += gridDim.x) {
+    const uint32_t tempty0 = CTAS == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
+    for (int st = unit_id; st < p.total_tiles; st += n_units) {
       const int nt = st % p.tiles_n;
-      const int mg = st / p.tiles_n;
+      const int mg = (st / p.tiles_n) * CTAS + (int)cta_rank;
       const int n0 = nt * p.BN;
       // this group's units: u = egrp, egrp + 2  ->  local index ul = 0, 1
       size_t pix[2];
@@ -368,19 +409,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u); else mbar_arrive(tempty0 + (uint32_t)acc * 8u);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal barriers in this CTA
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(p.tmem_cols)
-                 : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -391,7 +435,7 @@ typedef BdrcEncodeTiledFn EncodeTiledFn;
 EncodeTiledFn get_encode_fn() { return bdrc_tma_encode_fn(); }
 
 struct TcPlan {
-  int BW, BH, BN, tiles_w, tiles_h, tiles_n, stages, G;
+  int BW, BH, BN, tiles_w, tiles_h, tiles_n, stages, G, ctas;
   uint32_t tmem_cols;
   size_t smem_bytes;
 };
@@ -433,10 +477,18 @@ bool make_plan(const ConvWeights& w, const ConvArgs& a, TcPlan* pl) {
     if (want >= 1 && want <= G && m_tiles % want == 0) G = want;
   }
   pl->G = G;
+  // CTA pairs (cta_group::2) whenever the pixel tiles split evenly over the two CTAs
+  // and the K loop is long enough to amortise the pair's coupled accumulator hand-off (measured: pairs win
+  // on the 3x3 / k-tap layers with N >= 128, lose on 1x1 layers whose tiles are epilogue-bound)
+  const int k_iters = w.R * w.S * (w.Cin_pad / BK);
+  pl->ctas = (pl->BN >= 128 && pl->BN % 16 == 0 && k_iters >= 16 && m_tiles % (2 * G) == 0) ? 2 : 1;
+  if (const char* e = getenv("BDRC_TC_CTAS"))
+    if (atoi(e) == 1) pl->ctas = 1;
+    else if (atoi(e) == 2 && pl->BN >= 64 && pl->BN % 16 == 0 && m_tiles % (2 * G) == 0) pl->ctas = 2;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * G * pl->BN)) cols <<= 1;
   pl->tmem_cols = cols;
-  const size_t stage_bytes = (size_t)G * A_STAGE_BYTES + (size_t)pl->BN * BK * 2;
+  const size_t stage_bytes = (size_t)G * A_STAGE_BYTES + (size_t)(pl->BN / pl->ctas) * BK * 2;
   const size_t out_stage = a.out_fp32 ? 0 : 4 * (size_t)OUT_STAGE_BYTES;   // 2 groups x 2 buffers
   int stages = (int)((224 * 1024 - out_stage) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -492,7 +544,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
     cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
     cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)pl.BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(pl.BN / pl.ctas)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -519,7 +571,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
 
   TcParams p;
   p.tiles_n = pl.tiles_n; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_img = a.N;
-  p.total_tiles = pl.tiles_n * ((pl.tiles_w * pl.tiles_h * a.N) / pl.G);   // super tiles
+  p.total_tiles = pl.tiles_n * ((pl.tiles_w * pl.tiles_h * a.N) / (pl.G * pl.ctas));   // super tiles (per CTA / pair)
   p.BW = pl.BW; p.BH = pl.BH; p.BN = pl.BN; p.stages = pl.stages; p.G = pl.G;
   p.R = w.R; p.S = w.S; p.kchunks = w.Cin_pad / BK;
   p.stride_h = sh; p.stride_w = sw; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
@@ -527,8 +579,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
   p.par_c = a.in_ld;
   p.Hout = a.Hout; p.Wout = a.Wout; p.Cout = w.Cout;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.BN >> 3) << 17) |
-            ((uint32_t)(BM >> 4) << 24);
+  p.idesc = make_idesc_bf16(BM * pl.ctas, pl.BN);
   p.tmem_cols = pl.tmem_cols;
   p.bias = a.bias_override ? a.bias_override : w.b;
   p.bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
@@ -544,12 +595,30 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
 
   static bool attr_set = false;
   if (!attr_set) {
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        226 * 1024));
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-  conv_tc_kernel<<<grid, NUM_THREADS, pl.smem_bytes, s>>>(mapA, mapB, mapO, p);
+  if (pl.ctas == 2) {
+    const int pairs = ctx->sm_count / 2;
+    const int units = p.total_tiles < pairs ? p.total_tiles : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, mapA, mapB, mapO, p));
+  } else {
+    int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+    conv_tc_kernel<1><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(mapA, mapB, mapO, p);
+  }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

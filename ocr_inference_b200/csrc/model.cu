@@ -3,6 +3,7 @@
 //
 //   SEG : DeepLabV3+/ResNet-34, node list PyTorch-LineInference.ipynb:L233-L469 (BN folded)
 //   OCR : Easter2 as declared in SURVEY.md 8(a)-8 (oracle/nets.py:easter2_forward is the twin)
+#include <cstdlib>
 #include <map>
 
 #include "nn_kernels.cuh"
@@ -312,7 +313,7 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   if (!A.ok) return bdrc_fail(ctx, BDRC_ERR_ARG, "seg_forward: workspace too small");
 
   // stem + maxpool (ipynb:L233-L238)
-  if (cin == 1 && ctx->conv_engine == 0) {
+  if (cin == 1 && ctx->conv_engine == 0 && !getenv("BDRC_NO_STEM_TC")) {
     // binarised tiles: tcgen05 stem fused with the max-pool, the 256x256x64 activation stays on chip
     bdrc_prof_begin(ctx, "stem7x7+maxpool", 2.0 * n * 256 * 256 * 64 * 49 * 3, s);
     BDRC_TRY(stem_tc_pool_launch(ctx, reinterpret_cast<const uint8_t*>(tiles), n, m->stem_wb, m->stem_b, buf[0], s));
@@ -379,7 +380,13 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
       dwo[i] = dws + i * br;
     }
     bdrc_prof_begin(ctx, "aspp.dw3x3", 2.0 * n * 32 * 32 * 512 * 9 * 3, s);
-    BDRC_TRY(aspp_dw3_launch(ctx, x, n, 512, rates, dww, dwo, gmean, s));
+    if (getenv("BDRC_NO_ASPP_FUSED")) {
+      for (int i = 0; i < 3; ++i)
+        BDRC_TRY(depthwise3x3_launch(ctx, x, 512, 0, n, 32, 32, 512, rates[i], dww[i], dwo[i], 512, 0, s));
+      gmean = nullptr;
+    } else {
+      BDRC_TRY(aspp_dw3_launch(ctx, x, n, 512, rates, dww, dwo, gmean, s));
+    }
     bdrc_prof_end(ctx, s);
     for (int i = 0; i < 3; ++i)
       BDRC_TRY(conv_launch(ctx, "aspp.1x1", m->conv["decoder.aspp.0.convs." + std::to_string(i + 1) + ".0.1"],

@@ -1,5 +1,7 @@
 // Memory-bound network kernels between the implicit-GEMM convolutions (see nn_kernels.cuh).
 // All activations are bf16 NHWC; arithmetic is fp32.
+#include <cstdlib>
+
 #include "nn_kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -277,7 +279,14 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
     uint4 v[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) v[s] = *reinterpret_cast<const uint4*>(row + s * 128);
-    __syncthreads();                           // every thread holds its 3 pixels: the slot can be refilled
+    // The slot is refilled by TMA (async proxy) right after the barrier.  Arriving at a barrier does not
+    // wait for this thread's outstanding shared-memory LOADS, and an async-proxy write is not ordered
+    // behind them: pin the loaded registers (forces the loads to have returned) and fence the proxies
+    // before the barrier.  (Without this a few output pixels per launch were wrong, run to run.)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) asm volatile("" ::"r"(v[s].x), "r"(v[s].y), "r"(v[s].z), "r"(v[s].w) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
     if (tid == 0 && k + DWR_SLOTS < rows_in) issue(k + DWR_SLOTS);
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
@@ -661,7 +670,7 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                         cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
                "depthwise: channel counts must be multiples of 8");
-  if (dil == 1 && W % DWR_PX == 0 && bdrc_tma_encode_fn() != nullptr) {
+  if (dil == 1 && W % DWR_PX == 0 && bdrc_tma_encode_fn() != nullptr && !getenv("BDRC_NO_DW_RING")) {
     CUtensorMap map;
     const cuuint64_t ld = (cuuint64_t)in_ld;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};

@@ -47,11 +47,14 @@ def page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (14
     return np.ascontiguousarray(img), boxes
 
 
-def band_mask(boxes, H: int, W: int, grow: int = 4) -> np.ndarray:
-    """u8 {0,255} mask with one rounded blob per text band (a trained line model's output shape)."""
+def band_mask(boxes, H: int, W: int, grow: int = 4, thin: float = 1.0) -> np.ndarray:
+    """u8 {0,255} mask with one blob per text band (a trained line model's output shape).  thin < 1 keeps
+    only the central fraction of each band's height: line models mark the core of a text line, and the
+    reference's extraction (dilate by ~2.4x the blob height) expects that."""
     m = np.zeros((H, W), np.uint8)
     for (x, y, w, h) in boxes:
-        cv2.rectangle(m, (x, max(0, y - grow)), (x + w, min(H - 1, y + h + grow)), 255, -1)
+        cut = int(round(h * (1.0 - thin) / 2))
+        cv2.rectangle(m, (x, max(0, y + cut - grow)), (x + w, min(H - 1, y + h - cut + grow)), 255, -1)
     return m
 
 
@@ -128,11 +131,15 @@ def glyph_lines(seed: int, n: int, **kw):
     return [o[0] for o in out], [o[1] for o in out]
 
 
-def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (14, 22)):
+def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (9, 12), glyph_scale: float = 1.5):
     """Synthetic page whose text bands are glyph lines with a known transcription (config C3/C5).
+    Glyphs are drawn `glyph_scale` x larger than in glyph_line(): the reference's line extraction returns
+    crops about twice as tall as the text (dilated contour, BDRC/line_detection.py:267-288), so after the
+    resize to 80 px the glyphs arrive at the size the recogniser was trained on.
     Returns (u8 [H,W,3], band boxes (x,y,w,h), transcriptions as CHARSET_76 index lists)."""
     rng = np.random.default_rng(seed)
-    glyphs = glyph_bitmaps()
+    gh, gw = int(round(GLYPH_H * glyph_scale)), int(round(GLYPH_W * glyph_scale))
+    glyphs = [cv2.resize(b * 255, (gw, gh), interpolation=cv2.INTER_LINEAR) > 127 for b in glyph_bitmaps()]
     g = np.clip(rng.normal(215, 12, (H, W)), 0, 255).astype(np.uint8)
     n = int(rng.integers(n_lines[0], n_lines[1] + 1))
     pitch = H / (n + 1)
@@ -142,16 +149,16 @@ def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] 
         x0 = int(rng.integers(W // 40, W // 10))
         x1 = W - int(rng.integers(W // 40, W // 10))
         x, ids = x0, []
-        while x + GLYPH_W < x1:
+        while x + gw < x1:
             gid = int(rng.integers(0, 76))
             dy = int(rng.integers(-2, 3))
-            ys = min(max(0, y + dy), H - GLYPH_H)
-            ink = glyphs[gid] > 0
-            patch = g[ys:ys + GLYPH_H, x:x + GLYPH_W]
+            ys = min(max(0, y + dy), H - gh)
+            ink = glyphs[gid]
+            patch = g[ys:ys + gh, x:x + gw]
             patch[ink] = np.clip(rng.normal(40, 12, int(ink.sum())), 0, 255).astype(np.uint8)
             ids.append(gid)
-            x += GLYPH_W + int(rng.integers(5, 12))
-        boxes.append((x0, y, x - x0, GLYPH_H))
+            x += gw + int(rng.integers(int(5 * glyph_scale), int(12 * glyph_scale)))
+        boxes.append((x0, y, x - x0, gh))
         texts.append(ids)
     g = cv2.GaussianBlur(g, (3, 3), 0)
     return np.ascontiguousarray(np.stack([g, g, g], axis=-1)), boxes, texts
