@@ -131,7 +131,7 @@ def glyph_lines(seed: int, n: int, **kw):
     return [o[0] for o in out], [o[1] for o in out]
 
 
-def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (9, 12), glyph_scale: float = 1.5):
+def text_page(seed: int, H: int = 2048, W: int = 3072, n_lines: tuple[int, int] = (6, 7), glyph_scale: float = 1.5):
     """Synthetic page whose text bands are glyph lines with a known transcription (config C3/C5).
     Glyphs are drawn `glyph_scale` x larger than in glyph_line(): the reference's line extraction returns
     crops about twice as tall as the text (dilated contour, BDRC/line_detection.py:267-288), so after the

@@ -55,7 +55,7 @@ def test_fitted_segmentation_mask_matches_oracle(engine):
 
     ws = seg_weights_fitted(11)
     det = LineDetection(LineDetectionConfig("", ws, "deeplabv3plus-r34", 512, ["line"]), engine=engine)
-    page, boxes, _ = synth.text_page(77, 1024, 1536, n_lines=(8, 10))
+    page, boxes, _ = synth.text_page(77, 1024, 1536, n_lines=(3, 3))
     mask = det.predict(page)
     tiles, meta = ho.seg_preprocess(page, closed_form=False)
     ref_logits = nets.seg_forward(ws, np.repeat(tiles[:, None].astype(np.float32), 3, axis=1))
@@ -69,7 +69,7 @@ def test_fitted_segmentation_mask_matches_oracle(engine):
     assert np.array_equal(mask[dec_full], ref_mask[dec_full])
     assert agree >= 0.995
     # the fitted head must give line-shaped output on these pages, or the pipeline tests exercise nothing
-    band = synth.band_mask(boxes, 1024, 1536) > 0
+    band = synth.band_mask(boxes, 1024, 1536, grow=2, thin=0.45) > 0      # what make_heads.py fitted
     iou = float(((mask > 0) & band).sum() / max(1, ((mask > 0) | band).sum()))
     assert iou > 0.4, iou
 
@@ -84,15 +84,15 @@ def test_pipeline_page_to_text_trained_recogniser(engine, monkeypatch):
     pipe = OCRPipeline(OCRModelConfig(we, "Easter2", 2000, 80, "input", "output", True, False, CharsetEncoder.STACK,
                                       synth.CHARSET_76, True, "fitted"),
                        LineDetectionConfig("", ws, "deeplabv3plus-r34", 512, ["line"]), None, engine=engine)
-    page, _, _ = synth.text_page(78, 1024, 1536, n_lines=(8, 10))
+    page, _, truth = synth.text_page(78, 1024, 1536, n_lines=(3, 3))
     tiles, meta = ho.seg_preprocess(page, closed_form=False)
     ref_mask = ho.line_postprocess(nets.seg_forward(ws, np.repeat(tiles[:, None].astype(np.float32), 3, axis=1)), meta,
                                    0.9, closed_form=False)
     monkeypatch.setattr(pipe.line_inference, "predict", lambda image, class_threshold=None: ref_mask)
-    status, result = pipe.run_ocr(page)
+    status, result = pipe.run_ocr(page, k_factor=2.0, bbox_tolerance=2.5)     # Demo-OCR.ipynb parameters
     assert status == OpStatus.SUCCESS, result
     rot_mask, sorted_lines, ocr_lines, angle = result
-    o = og.page_to_lines(page, ref_mask, 2.5, 4.0)
+    o = og.page_to_lines(page, ref_mask, 2.0, 2.5)
     assert not isinstance(o, str)
     o_mask, o_lines, o_imgs, o_angle = o
     assert angle == o_angle and np.array_equal(rot_mask, o_mask)
@@ -100,10 +100,12 @@ def test_pipeline_page_to_text_trained_recogniser(engine, monkeypatch):
     texts, _ = og.recognise(o_imgs, we, synth.CHARSET_76)
     assert len(ocr_lines) == len(texts)
     same = sum(a.text == b.strip().replace("§", " ") for a, b in zip(ocr_lines, texts))
-    print(f"pipeline (trained recogniser): identical decoded lines {same}/{len(texts)}")
+    want = {"".join(synth.CHARSET_76[i] for i in t).strip().replace("§", " ") for t in truth}
+    print(f"pipeline (trained recogniser): identical decoded lines {same}/{len(texts)}; "
+          f"equal to the page's transcription: {sum(l.text in want for l in ocr_lines)}/{len(truth)}")
     assert same >= int(np.ceil(0.95 * len(texts)))
     # the threaded batch entry point returns exactly what the single-page call returns
-    batch = pipe.run_ocr_batch([page, page, page], workers=3)
+    batch = pipe.run_ocr_batch([page, page, page], workers=3, k_factor=2.0, bbox_tolerance=2.5)
     for st, res in batch:
         assert st == OpStatus.SUCCESS
         assert [l.text for l in res[2]] == [l.text for l in ocr_lines] and res[3] == angle
