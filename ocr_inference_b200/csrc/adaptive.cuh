@@ -5,11 +5,14 @@
 // Arithmetic is pinned to oracle/hostops.py:adaptive_threshold: row pass k = 0..50 sequential
 // FMA, column pass centre tap then symmetric pairs (x[-k] + x[k]) * w[k] by FMA.
 //
-// Work decomposition: one CTA produces a 64x64 output region of one image.  The gray halo
-// (114x114, clamped to the image) is staged in shared memory as fp32, the row pass writes a
-// 114x64 fp32 buffer, the column pass reads it.  Both passes keep a sliding register window so
-// shared-memory traffic is ~1 load per 4 FMAs.  The kernel is fp32-FMA bound, not HBM bound:
-// ~142 FMA per output pixel against 4 bytes of DRAM traffic.
+// Work decomposition: one CTA owns a 32-column strip of one image and STREAMS down its rows in
+// blocks of 32.  Per block the gray halo (32 rows x 82 columns, replicate-clamped at the image edge)
+// is staged as fp32, the row pass writes 32 rows of a 128-row shared-memory ring, and -- two blocks
+// behind, when its 51-row window is complete -- the column pass + threshold emits 32 output rows.
+// Nothing is recomputed vertically (the first version recomputed the row pass for a 114-row halo of
+// every 64-row region: 142 flop per pixel; now 102), both passes keep sliding register windows
+// (~1 shared load per 4 FMAs) and ~40 KB of shared memory allows 4 CTAs per SM.
+// The kernel is fp32-FMA bound, not HBM bound: 102 flop per pixel against 4 bytes of DRAM traffic.
 #pragma once
 #include <cmath>
 
@@ -18,11 +21,13 @@
 namespace adaptive {
 
 constexpr int KS = 51, KR = 25;
-constexpr int RT = 64;                 // output region edge
-constexpr int HALO = RT + 2 * KR;      // 114
-constexpr int GSTRIDE = 116;           // padded row stride of the gray tile (float4-aligned)
+constexpr int SW = 32;                 // strip width (output columns per CTA)
+constexpr int RB = 32;                 // rows per block
+constexpr int GW = SW + 2 * KR;        // 82 staged columns
+constexpr int GSTRIDE = 84;            // padded row stride of the staged gray block (float4-aligned)
+constexpr int RING = 128;              // row-pass ring (rows), power of two
 constexpr int THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t)(HALO * GSTRIDE + HALO * RT) * sizeof(float) + RT * RT;
+constexpr size_t SMEM_BYTES = (size_t)(RB * GSTRIDE + RING * SW) * sizeof(float) + RING * SW + RB * SW;
 
 __constant__ float c_gauss[KS];
 
@@ -55,22 +60,21 @@ struct SrcGrayBatch {
 };
 
 // Sink policies --------------------------------------------------------------------------------
+// `res` is a block of RB rows x SW columns of bytes (1 = white) whose top-left output pixel is (y0, x0).
 // u8 {0,1} tiles [n][H][W]
 struct SinkTiles01 {
   uint8_t* out;
   int H, W;
-  __device__ __forceinline__ void store(const uint8_t* res, int img, int y0, int x0, int IH,
-                                        int IW) const {
-    // res: RT x RT bytes (1 = white). 4 consecutive x per thread -> 32-bit stores when aligned.
-    for (int i = threadIdx.x; i < RT * RT / 4; i += THREADS) {
-      const int r = i / (RT / 4), c4 = (i % (RT / 4)) * 4;
+  __device__ __forceinline__ void store(const uint8_t* res, int img, int y0, int x0, int IH, int IW) const {
+    for (int i = threadIdx.x; i < RB * SW / 4; i += THREADS) {
+      const int r = i / (SW / 4), c4 = (i % (SW / 4)) * 4;
       const int y = y0 + r, x = x0 + c4;
       if (y >= IH || x >= IW) continue;
       uint8_t* o = out + ((size_t)img * H + y) * W + x;
       if (x + 3 < IW && (W & 3) == 0) {
-        *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(res + r * RT + c4);
+        *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(res + r * SW + c4);
       } else {
-        for (int j = 0; j < 4 && x + j < IW; ++j) o[j] = res[r * RT + c4 + j];
+        for (int j = 0; j < 4 && x + j < IW; ++j) o[j] = res[r * SW + c4 + j];
       }
     }
   }
@@ -82,23 +86,22 @@ struct SinkOcrLines {
   bf16* lines;      // may be null
   float* lines_f32; // may be null
   int H, W, Cpad;
-  __device__ __forceinline__ void store(const uint8_t* res, int img, int y0, int x0, int IH,
-                                        int IW) const {
+  __device__ __forceinline__ void store(const uint8_t* res, int img, int y0, int x0, int IH, int IW) const {
     if (lines) {
       // lanes run along y (the channel axis of the output) so stores are contiguous
-      for (int i = threadIdx.x; i < RT * RT; i += THREADS) {
-        const int c = i / RT, r = i % RT;   // c = x offset, r = y offset
+      for (int i = threadIdx.x; i < RB * SW; i += THREADS) {
+        const int c = i / RB, r = i % RB;   // c = x offset, r = y offset
         const int y = y0 + r, x = x0 + c;
         if (y >= IH || x >= IW) continue;
-        lines[((size_t)img * W + x) * Cpad + y] = __float2bfloat16(res[r * RT + c] ? 1.f : -1.f);
+        lines[((size_t)img * W + x) * Cpad + y] = __float2bfloat16(res[r * SW + c] ? 1.f : -1.f);
       }
     }
     if (lines_f32) {
-      for (int i = threadIdx.x; i < RT * RT; i += THREADS) {
-        const int r = i / RT, c = i % RT;
+      for (int i = threadIdx.x; i < RB * SW; i += THREADS) {
+        const int r = i / SW, c = i % SW;
         const int y = y0 + r, x = x0 + c;
         if (y >= IH || x >= IW) continue;
-        lines_f32[((size_t)img * H + y) * W + x] = res[r * RT + c] ? 1.f : -1.f;
+        lines_f32[((size_t)img * H + y) * W + x] = res[r * SW + c] ? 1.f : -1.f;
       }
     }
   }
@@ -106,92 +109,106 @@ struct SinkOcrLines {
 
 template <class Src, class Sink>
 __global__ void __launch_bounds__(THREADS)
-adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int regions_x,
-                          int regions_y) {
+adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int strips_x) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* g = reinterpret_cast<float*>(smem_raw);       // [HALO][GSTRIDE]
-  float* rowb = g + HALO * GSTRIDE;                     // [HALO][RT]
-  uint8_t* res = reinterpret_cast<uint8_t*>(rowb + HALO * RT);  // [RT][RT]
+  float* g = reinterpret_cast<float*>(smem_raw);                 // [RB][GSTRIDE]  staged gray block
+  float* ring = g + RB * GSTRIDE;                                // [RING][SW]     row-pass results
+  uint8_t* gc = reinterpret_cast<uint8_t*>(ring + RING * SW);    // [RING][SW]     gray of the strip itself
+  uint8_t* res = gc + RING * SW;                                 // [RB][SW]
 
-  int b = blockIdx.x;
-  const int rx = b % regions_x; b /= regions_x;
-  const int ry = b % regions_y;
-  const int img = b / regions_y;
-  const int x0 = rx * RT, y0 = ry * RT;
+  const int sx = blockIdx.x % strips_x;
+  const int img = blockIdx.x / strips_x;
+  const int x0 = sx * SW;
+  const int n_blocks = (IH + RB - 1) / RB;
 
-  // ---- stage gray halo (replicate border at the image edge) ----
-  for (int i = threadIdx.x; i < HALO * HALO; i += THREADS) {
-    const int r = i / HALO, c = i - r * HALO;
-    const int y = min(max(y0 + r - KR, 0), IH - 1);
-    const int x = min(max(x0 + c - KR, 0), IW - 1);
-    g[r * GSTRIDE + c] = src.gray(img, y, x);
-  }
-  __syncthreads();
-
-  // ---- row pass: rowb[r][c] = sum_k g[r][c + k] * w[k], k ascending, FMA ----
-  for (int it = threadIdx.x; it < HALO * (RT / 4); it += THREADS) {
-    const int r = it / (RT / 4), c = (it - r * (RT / 4)) * 4;
-    const float* gp = g + r * GSTRIDE + c;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    float4 v = *reinterpret_cast<const float4*>(gp);
-    float w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;   // sliding window g[c+k .. c+k+3]
-#pragma unroll
-    for (int k4 = 0; k4 < 52; k4 += 4) {
-      const float4 n = *reinterpret_cast<const float4*>(gp + k4 + 4);
-      // taps k4 .. k4+3 (k = 51 does not exist: guarded at compile time)
-      {
-        const float wk = c_gauss[k4];
-        a0 = __fmaf_rn(w0, wk, a0); a1 = __fmaf_rn(w1, wk, a1);
-        a2 = __fmaf_rn(w2, wk, a2); a3 = __fmaf_rn(w3, wk, a3);
+  for (int b = 0; b < n_blocks + 2; ++b) {
+    // ---- stage gray rows [RB*b, RB*b + RB) x columns [x0 - KR, x0 + SW + KR), clamped to the image ----
+    // (prefetching the next block into registers during the filter passes was tried: 128 registers, 2 CTAs
+    //  per SM, 0.197 ms per page against 0.130 ms for this version -- the kernel is bound by shared-memory
+    //  load latency at 3 CTAs per SM, ncu: 58 % of stalls are short-scoreboard, issue slots 36 % busy)
+    if (b < n_blocks) {
+      for (int i = threadIdx.x; i < RB * GW; i += THREADS) {
+        const int r = i / GW, c = i - r * GW;
+        const int y = min(RB * b + r, IH - 1);
+        const int x = min(max(x0 + c - KR, 0), IW - 1);
+        const float v = src.gray(img, y, x);
+        g[r * GSTRIDE + c] = v;
+        if (c >= KR && c < KR + SW) gc[((RB * b + r) & (RING - 1)) * SW + c - KR] = (uint8_t)v;
       }
-      if (k4 + 1 < KS) {
-        const float wk = c_gauss[k4 + 1];
-        a0 = __fmaf_rn(w1, wk, a0); a1 = __fmaf_rn(w2, wk, a1);
-        a2 = __fmaf_rn(w3, wk, a2); a3 = __fmaf_rn(n.x, wk, a3);
-      }
-      if (k4 + 2 < KS) {
-        const float wk = c_gauss[k4 + 2];
-        a0 = __fmaf_rn(w2, wk, a0); a1 = __fmaf_rn(w3, wk, a1);
-        a2 = __fmaf_rn(n.x, wk, a2); a3 = __fmaf_rn(n.y, wk, a3);
-      }
-      if (k4 + 3 < KS) {
-        const float wk = c_gauss[k4 + 3];
-        a0 = __fmaf_rn(w3, wk, a0); a1 = __fmaf_rn(n.x, wk, a1);
-        a2 = __fmaf_rn(n.y, wk, a2); a3 = __fmaf_rn(n.z, wk, a3);
-      }
-      w0 = n.x; w1 = n.y; w2 = n.z; w3 = n.w;
     }
-    *reinterpret_cast<float4*>(rowb + r * RT + c) = make_float4(a0, a1, a2, a3);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- column pass + threshold: 4 consecutive rows per thread, lanes along x ----
-  for (int it = threadIdx.x; it < (RT / 4) * RT; it += THREADS) {
-    const int c = it % RT, r4 = (it / RT) * 4;   // output rows r4 .. r4+3 (region coords)
-    // output row r uses rowb rows (r + KR - k) and (r + KR + k): 54-row register window
-    const float* rp = rowb + r4 * RT + c;
-    float v[2 * KR + 4];
+    // ---- row pass of block b: ring[row][c] = sum_k g[row][c + k] * w[k], k ascending, FMA ----
+    if (b < n_blocks) {
+      const int r = threadIdx.x / (SW / 4), c = (threadIdx.x % (SW / 4)) * 4;
+      const float* gp = g + r * GSTRIDE + c;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      float4 v = *reinterpret_cast<const float4*>(gp);
+      float w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;   // sliding window g[c+k .. c+k+3]
 #pragma unroll
-    for (int i = 0; i < 2 * KR + 4; ++i) v[i] = rp[i * RT];
-    float s[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[j] = __fmul_rn(v[j + KR], c_gauss[KR]);
-#pragma unroll
-    for (int k = 1; k <= KR; ++k) {
-      const float wk = c_gauss[KR + k];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] = __fmaf_rn(__fadd_rn(v[j + KR - k], v[j + KR + k]), wk, s[j]);
+      for (int k4 = 0; k4 < 52; k4 += 4) {
+        const float4 n = *reinterpret_cast<const float4*>(gp + k4 + 4);
+        // taps k4 .. k4+3 (k = 51 does not exist: guarded at compile time)
+        {
+          const float wk = c_gauss[k4];
+          a0 = __fmaf_rn(w0, wk, a0); a1 = __fmaf_rn(w1, wk, a1);
+          a2 = __fmaf_rn(w2, wk, a2); a3 = __fmaf_rn(w3, wk, a3);
+        }
+        if (k4 + 1 < KS) {
+          const float wk = c_gauss[k4 + 1];
+          a0 = __fmaf_rn(w1, wk, a0); a1 = __fmaf_rn(w2, wk, a1);
+          a2 = __fmaf_rn(w3, wk, a2); a3 = __fmaf_rn(n.x, wk, a3);
+        }
+        if (k4 + 2 < KS) {
+          const float wk = c_gauss[k4 + 2];
+          a0 = __fmaf_rn(w2, wk, a0); a1 = __fmaf_rn(w3, wk, a1);
+          a2 = __fmaf_rn(n.x, wk, a2); a3 = __fmaf_rn(n.y, wk, a3);
+        }
+        if (k4 + 3 < KS) {
+          const float wk = c_gauss[k4 + 3];
+          a0 = __fmaf_rn(w3, wk, a0); a1 = __fmaf_rn(n.x, wk, a1);
+          a2 = __fmaf_rn(n.y, wk, a2); a3 = __fmaf_rn(n.z, wk, a3);
+        }
+        w0 = n.x; w1 = n.y; w2 = n.z; w3 = n.w;
+      }
+      if (RB * b + r < IH)
+        *reinterpret_cast<float4*>(ring + ((RB * b + r) & (RING - 1)) * SW + c) = make_float4(a0, a1, a2, a3);
     }
+
+    // ---- column pass + threshold of block b - 2 (its 51-row window was complete one barrier ago) ----
+    const int ob = b - 2;
+    if (ob >= 0 && ob < n_blocks) {
+      const int c = threadIdx.x % SW, r4 = RB * ob + (threadIdx.x / SW) * 4;   // output rows r4 .. r4+3
+      float v[2 * KR + 4];
+      if (r4 - KR >= 0 && r4 + 3 + KR < IH) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int mean = __float2int_rn(s[j]);
-      mean = min(max(mean, 0), 255);
-      const int gv = (int)g[(r4 + j + KR) * GSTRIDE + c + KR];
-      res[(r4 + j) * RT + c] = (gv - mean > -13) ? 1 : 0;
+        for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[((r4 - KR + i) & (RING - 1)) * SW + c];
+      } else {   // replicate border at the top / bottom of the image
+#pragma unroll
+        for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[(min(max(r4 - KR + i, 0), IH - 1) & (RING - 1)) * SW + c];
+      }
+      float s[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = __fmul_rn(v[j + KR], c_gauss[KR]);
+#pragma unroll
+      for (int k = 1; k <= KR; ++k) {
+        const float wk = c_gauss[KR + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = __fmaf_rn(__fadd_rn(v[j + KR - k], v[j + KR + k]), wk, s[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int mean = __float2int_rn(s[j]);
+        mean = min(max(mean, 0), 255);
+        const int gv = (int)gc[((r4 + j) & (RING - 1)) * SW + c];
+        res[(r4 - RB * ob + j) * SW + c] = (r4 + j < IH && gv - mean > -13) ? 1 : 0;
+      }
     }
+    __syncthreads();
+    if (ob >= 0 && ob < n_blocks) sink.store(res, img, RB * ob, x0, IH, IW);
+    // res is rewritten only after the next iteration's first barrier; the ring rows block b + 1 will
+    // overwrite (two blocks ahead of the oldest row any pending window needs) are dead by then
   }
-  __syncthreads();
-  sink.store(res, img, y0, x0, IH, IW);
 }
 
 // Gaussian taps exactly as cv2.getGaussianKernel(51, 0, CV_32F): double exp, double
@@ -218,12 +235,15 @@ int launch(bdrc_ctx* ctx, const Src& src, const Sink& sink, int n_img, int IH, i
            cudaStream_t s) {
   BDRC_CUDA(ctx, upload_gauss());
   auto kern = adaptive_threshold_kernel<Src, Sink>;
-  BDRC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)SMEM_BYTES));
-  const int rx = ceil_div(IW, RT), ry = ceil_div(IH, RT);
-  const long long blocks = (long long)rx * ry * n_img;
-  if (blocks == 0) return 0;
-  kern<<<(unsigned)blocks, THREADS, SMEM_BYTES, s>>>(src, sink, IH, IW, rx, ry);
+  static bool attr_set = false;   // one flag per <Src, Sink> instantiation
+  if (!attr_set) {
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  const int rx = ceil_div(IW, SW);
+  const long long blocks = (long long)rx * n_img;
+  if (blocks == 0 || IH <= 0) return 0;
+  kern<<<(unsigned)blocks, THREADS, SMEM_BYTES, s>>>(src, sink, IH, IW, rx);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

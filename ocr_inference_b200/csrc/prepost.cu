@@ -444,7 +444,10 @@ int bdrc_seg_preprocess(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int pa
   const int nty = ceil_div(H, patch), ntx = ceil_div(W, patch);
   adaptive::SrcPageTiles src{page, H, W, ntx, patch};
   adaptive::SinkTiles01 sink{tiles, patch, patch};
-  return adaptive::launch(ctx, src, sink, nty * ntx, patch, patch, (cudaStream_t)stream);
+  bdrc_prof_begin(ctx, "a-1.adaptive_threshold", 0, (cudaStream_t)stream);
+  const int rc = adaptive::launch(ctx, src, sink, nty * ntx, patch, patch, (cudaStream_t)stream);
+  bdrc_prof_end(ctx, (cudaStream_t)stream);
+  return rc;
 }
 
 int bdrc_seg_tile_rgb(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int Hc, int Wc, int patch,
@@ -474,6 +477,7 @@ static int seg_post_common(bdrc_ctx* ctx, const float* logits, int nty, int ntx,
   p.thr_logit = sigmoid_logit_threshold(thr);
   p.mask = mask;
   cudaStream_t s = (cudaStream_t)stream;
+  bdrc_prof_begin(ctx, "a-3.seg_post", 0, s);
   if (torch_path) {
     dim3 grid(ceil_div(W0, 128), H0);
     seg_post_torch_kernel<<<grid, 128, 0, s>>>(p);
@@ -485,6 +489,7 @@ static int seg_post_common(bdrc_ctx* ctx, const float* logits, int nty, int ntx,
     dim3 grid(ceil_div(W0, 128), H0);
     seg_post_kernel<<<grid, 128, 0, s>>>(p);
   }
+  bdrc_prof_end(ctx, s);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

@@ -70,6 +70,14 @@ def main():
     tiles_buf = torch.empty((24, 512, 512), dtype=torch.uint8, device=dev)
     ms = timeit(lambda p: eng.seg_preprocess(p, out=tiles_buf), pages)
     add("a-1", "gray + adaptive threshold + tile, 2048x3072x3 page -> 24 u8 tiles", ms, bytes_=5 * H * W)
+    eng.profile(True)
+    for p in pages:
+        eng.seg_preprocess(p, out=tiles_buf)
+    torch.cuda.synchronize()
+    ev = [t for (n, t, f) in eng.profile_results() if n.startswith("a-1")]
+    eng.profile(False)
+    add("a-1", "  same, kernel only (CUDA events around the launch, no host call overhead)", sum(ev) / len(ev),
+        bytes_=5 * H * W)
 
     # a-2 ------------------------------------------------------------------------------------------
     seg = eng.load_model(1, seg_weights_fitted(11), 1)
