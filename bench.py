@@ -331,6 +331,82 @@ def bench_c3(eng, steps: int, pages_per_step: int = 16, workers: int = 4):
     }
 
 
+def _c3_worker(rank, n_workers, device, pages_per_worker, steps, threads, barrier, q):
+    """One host process of the C3 page->text run: owns a shard of the pages and its own OCRPipeline (CUDA
+    context, weights, workspaces) on `device`.  Pages are independent units: no exchange."""
+    try:
+        import torch
+
+        from ocr_inference_b200 import synthetic
+        from ocr_inference_b200.data import LineDetectionConfig, OpStatus
+        from ocr_inference_b200.inference import OCRPipeline, get_engine
+        from ocr_inference_b200.synthetic_weights import seg_weights_fitted
+        from ocr_inference_b200.weights import write_blob
+
+        torch.cuda.set_device(device)
+        eng = get_engine(device)
+        pipe = OCRPipeline(_ocr_config(), LineDetectionConfig("", write_blob(seg_weights_fitted(11)),
+                                                              "deeplabv3plus-r34", 512, ["line"]), None, engine=eng)
+        base = [synthetic.text_page(3003 + (rank * 2 + i) % 4) for i in range(2)]
+        pages = [base[i % 2][0] for i in range(pages_per_worker)]
+        kw = dict(k_factor=2.0, bbox_tolerance=2.5)
+        pipe.run_ocr_batch(pages[:max(2, threads)], workers=threads, **kw)
+        torch.cuda.synchronize()
+        barrier.wait()
+        t0 = time.perf_counter()
+        n_lines = n_ok = 0
+        for _ in range(steps):
+            for st, res in pipe.run_ocr_batch(pages, workers=threads, **kw):
+                if st == OpStatus.SUCCESS:
+                    n_ok += 1
+                    n_lines += len(res[2])
+        torch.cuda.synchronize()
+        q.put((rank, t0, time.perf_counter(), n_ok, n_lines, None))
+    except Exception as e:  # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:  # noqa: BLE001
+            pass
+        q.put((rank, 0.0, 0.0, 0, 0, repr(e)))
+
+
+def bench_c3_procs(device: int, n_workers: int, pages_per_worker: int = 8, steps: int = 2, threads: int = 2):
+    """C3 with several host processes per GPU: the cv2 / Python geometry of SURVEY 8(a)-10 is the per-page
+    critical path (~25 ms per page per core, GIL-bound inside one process), the GPU stages take ~3-7 ms."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    barrier, q = ctx.Barrier(n_workers), ctx.Queue()
+    procs = [ctx.Process(target=_c3_worker, args=(r, n_workers, device, pages_per_worker, steps, threads, barrier, q))
+             for r in range(n_workers)]
+    for p in procs:
+        p.start()
+    out, deadline = [], time.time() + 240
+    while len(out) < n_workers:
+        try:
+            out.append(q.get(timeout=2))
+        except Exception:  # noqa: BLE001  (queue.Empty)
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() > deadline:
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                return {"error": f"{len(dead)} worker(s) died" if dead else "timeout waiting for the workers"}
+    for p in procs:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    errs = [o[5] for o in out if o[5]]
+    if errs:
+        return {"error": errs[0]}
+    t0, t1 = min(o[1] for o in out), max(o[2] for o in out)
+    pages = sum(o[3] for o in out)
+    lines = sum(o[4] for o in out)
+    return {"host_processes": n_workers, "threads_per_process": threads, "pages": pages,
+            "e2e_pages_per_sec": pages / (t1 - t0), "e2e_lines_per_sec": lines / (t1 - t0),
+            "note": "perf_counter is CLOCK_MONOTONIC (system-wide): first worker start to last worker end"}
+
+
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
@@ -460,6 +536,8 @@ def run_ours(args, rank, world, local_rank):
         try:
             extras["c1"] = bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline)
             extras["c3"] = bench_c3(eng, 2)
+            nproc = max(2, min(8, len(os.sched_getaffinity(0)) // 2))
+            extras["c3"]["multi_process"] = bench_c3_procs(local_rank, nproc)
         except Exception as e:  # noqa: BLE001  (the headline must still print)
             extras["error"] = repr(e)
     h2d = sum(p.nbytes for p in pages)
