@@ -76,6 +76,198 @@ __device__ __forceinline__ void decode_mtile(const TcParams& p, int mt, int& img
   oy0 = ht * p.BH;
 }
 
+// ---------------------------------------------------------------------------------------
+// epilogue (warps 4..11), shared by the kernels of this file
+// ---------------------------------------------------------------------------------------
+// 8 warps in two groups of 4 (warp % 4 = TMEM lane quarter, hardware rule).  The work of one
+// super tile is a list of units (pixel tile g, 64-column group j), dealt round-robin to the two
+// groups.  bf16 outputs are staged in shared memory in the SWIZZLE_128B layout and written with
+// one TMA tensor store per unit (full 128-byte lines; a 16-bytes-per-thread direct store pattern
+// cost 2x the MMA time: measured).  The residual of this thread's rows is prefetched into
+// registers BEFORE waiting for the accumulators.
+// Super tiles st_begin, st_begin + st_step, ... < st_end; `stage_out` = 2 groups x 2 staging buffers.
+template <int CTAS, int NBUF>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* tmapO_ptr, uint8_t* stage_out_base,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                              uint32_t cta_rank, int st_begin, int st_end, int st_step) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = p.G;
+  const CUtensorMap& tmapO = *tmapO_ptr;
+  {
+    // ===================== epilogue =====================
+    // 8 warps in two groups of 4 (warp % 4 = TMEM lane quarter, hardware rule).  The work of one
+    // super tile is a list of units (pixel tile g, 64-column group j), dealt round-robin to the two
+    // groups.  bf16 outputs are staged in shared memory in the SWIZZLE_128B layout and written with
+    // one TMA tensor store per unit (full 128-byte lines; a 16-bytes-per-thread direct store pattern
+    // cost 2x the MMA time: measured).  The residual of this thread's rows is prefetched into
+    // registers BEFORE waiting for the accumulators.
+    const int wrank = warp & 3;
+    const int egrp = (warp - 4) >> 2;
+    const int ngrp64 = (p.BN + 63) / 64;
+    const int units = G * ngrp64;              // <= 4 by construction (host)
+    const int m = wrank * 32 + lane;           // row of the tile = pixel
+    const int hl = m / p.BW, wl = m % p.BW;
+    const bool res_vec = p.residual != nullptr && (p.res_ld & 7) == 0;
+    const bool issuer = (threadIdx.x == 128 + 128 * egrp);
+    uint8_t* stage_out = stage_out_base + (size_t)egrp * NBUF * OUT_STAGE_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t use = 0;                          // staging buffer toggle
+    const uint32_t tempty0 = CTAS == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
+    for (int st = st_begin; st < st_end; st += st_step) {
+      const int nt = st % p.tiles_n;
+      const int mg = (st / p.tiles_n) * CTAS + (int)cta_rank;
+      const int n0 = nt * p.BN;
+      // this group's units: u = egrp, egrp + 2  ->  local index ul = 0, 1
+      size_t pix[2];
+      bool valid[2];
+      int imgs[2], oxs[2], oys[2], cg0[2];
+#pragma unroll
+      for (int ul = 0; ul < 2; ++ul) {
+        const int u = egrp + 2 * ul;
+        pix[ul] = 0; valid[ul] = false; imgs[ul] = 0; oxs[ul] = 0; oys[ul] = 0; cg0[ul] = 0;
+        if (u < units) {
+          const int g = u / ngrp64;
+          cg0[ul] = (u - g * ngrp64) * 64;
+          int img, oy0, ox0;
+          decode_mtile(p, mg * G + g, img, oy0, ox0);
+          const int ox = ox0 + wl, oy = oy0 + hl;
+          valid[ul] = (ox < p.Wout) && (oy < p.Hout);
+          pix[ul] = ((size_t)img * p.Hout + oy) * p.Wout + ox;
+          imgs[ul] = img; oxs[ul] = ox0; oys[ul] = oy0;
+        }
+      }
+      uint4 rres[16];
+      if (res_vec && !(p.dbg_skip & (4 | 16))) {
+#pragma unroll
+        for (int ul = 0; ul < 2; ++ul) {
+          if (egrp + 2 * ul < units && valid[ul]) {
+            const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + cg0[ul];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (n0 + cg0[ul] + q * 8 + 8 <= p.Cout)
+                rres[ul * 8 + q] = *reinterpret_cast<const uint4*>(rp + q * 8);   // plain load: may alias out
+          }
+        }
+      }
+
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * G * p.BN);
+#pragma unroll
+      for (int ul = 0; ul < 2; ++ul) {
+        const int u = egrp + 2 * ul;
+        if (u >= units) break;
+        const int g = u / ngrp64;
+        uint8_t* sbuf = stage_out + (size_t)(use & (NBUF - 1)) * OUT_STAGE_BYTES;
+        if (p.out_tma) {
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (issuer) {
+            if (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+        }
+        const float* bias = p.bias + (size_t)imgs[ul] * p.bias_img_stride + n0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = cg0[ul] + q * 16;
+          if (c0 >= p.BN) break;
+          uint32_t v[16];
+          tc_ld16(tbase + (uint32_t)(g * p.BN + c0), v);
+          tc_wait_ld();
+          if (p.dbg_skip & 4) continue;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+            f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (p.residual && valid[ul]) {
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              if (res_vec && n0 + c0 + hq * 8 + 8 <= p.Cout) {
+                const uint4 rv = rres[ul * 8 + q * 2 + hq];
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                  f[hq * 8 + 2 * j] += __low2float(h);
+                  f[hq * 8 + 2 * j + 1] += __high2float(h);
+                }
+              } else {
+                const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + c0 + hq * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)   // static indices only: keeps f[] in registers
+                  if (n0 + c0 + hq * 8 + j < p.Cout) f[hq * 8 + j] += __bfloat162float(rp[j]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.out_tma) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            // row m, 16-byte chunks 2q and 2q+1 of the 128-byte row, XOR-swizzled with (m & 7)
+            uint8_t* rowp = sbuf + (size_t)m * 128;
+            *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else if (valid[ul] && n0 + c0 < p.Cout) {
+            const bool full16 = (n0 + c0 + 16 <= p.Cout);
+            if (p.out_fp32) {
+              float* op = reinterpret_cast<float*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
+              if (full16 && ((p.out_ld | p.out_coff) & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c0 + j < p.Cout) op[j] = f[j];
+              }
+            } else {
+              bf16* op = reinterpret_cast<bf16*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < p.Cout) op[j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+        if (p.out_tma) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
+          if (issuer && !(p.dbg_skip & (4 | 8))) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tmapO)), "r"(smem_u32(sbuf)), "r"(n0 + cg0[ul]), "r"(oxs[ul]),
+                "r"(oys[ul]), "r"(imgs[ul])
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++use;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u); else mbar_arrive(tempty0 + (uint32_t)acc * 8u);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 // CTAS = 1: one CTA per SM works alone (cta_group::1, M = 128).
 // CTAS = 2: the two CTAs of a cluster form a pair (cta_group::2, M = 256).  Each CTA loads the A slabs of its
 //   own G pixel tiles and HALF of the B tile; the leader (cluster rank 0) issues one MMA for both, which reads
@@ -248,173 +440,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    // 8 warps in two groups of 4 (warp % 4 = TMEM lane quarter, hardware rule).  The work of one
-    // super tile is a list of units (pixel tile g, 64-column group j), dealt round-robin to the two
-    // groups.  bf16 outputs are staged in shared memory in the SWIZZLE_128B layout and written with
-    // one TMA tensor store per unit (full 128-byte lines; a 16-bytes-per-thread direct store pattern
-    // cost 2x the MMA time: measured).  The residual of this thread's rows is prefetched into
-    // registers BEFORE waiting for the accumulators.
-    const int wrank = warp & 3;
-    const int egrp = (warp - 4) >> 2;
-    const int ngrp64 = (p.BN + 63) / 64;
-    const int units = G * ngrp64;              // <= 4 by construction (host)
-    const int m = wrank * 32 + lane;           // row of the tile = pixel
-    const int hl = m / p.BW, wl = m % p.BW;
-    const bool res_vec = p.residual != nullptr && (p.res_ld & 7) == 0;
-    const bool issuer = (threadIdx.x == 128 + 128 * egrp);
-    uint8_t* stage_out = smem + (size_t)p.stages * stage_bytes + 1024 + (size_t)egrp * 2 * OUT_STAGE_BYTES;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t use = 0;                          // staging buffer toggle
-    const uint32_t tempty0 = CTAS == 2 ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
-    for (int st = unit_id; st < p.total_tiles; st += n_units) {
-      const int nt = st % p.tiles_n;
-      const int mg = (st / p.tiles_n) * CTAS + (int)cta_rank;
-      const int n0 = nt * p.BN;
-      // this group's units: u = egrp, egrp + 2  ->  local index ul = 0, 1
-      size_t pix[2];
-      bool valid[2];
-      int imgs[2], oxs[2], oys[2], cg0[2];
-#pragma unroll
-      for (int ul = 0; ul < 2; ++ul) {
-        const int u = egrp + 2 * ul;
-        pix[ul] = 0; valid[ul] = false; imgs[ul] = 0; oxs[ul] = 0; oys[ul] = 0; cg0[ul] = 0;
-        if (u < units) {
-          const int g = u / ngrp64;
-          cg0[ul] = (u - g * ngrp64) * 64;
-          int img, oy0, ox0;
-          decode_mtile(p, mg * G + g, img, oy0, ox0);
-          const int ox = ox0 + wl, oy = oy0 + hl;
-          valid[ul] = (ox < p.Wout) && (oy < p.Hout);
-          pix[ul] = ((size_t)img * p.Hout + oy) * p.Wout + ox;
-          imgs[ul] = img; oxs[ul] = ox0; oys[ul] = oy0;
-        }
-      }
-      uint4 rres[16];
-      if (res_vec && !(p.dbg_skip & (4 | 16))) {
-#pragma unroll
-        for (int ul = 0; ul < 2; ++ul) {
-          if (egrp + 2 * ul < units && valid[ul]) {
-            const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + cg0[ul];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (n0 + cg0[ul] + q * 8 + 8 <= p.Cout)
-                rres[ul * 8 + q] = *reinterpret_cast<const uint4*>(rp + q * 8);   // plain load: may alias out
-          }
-        }
-      }
-
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * G * p.BN);
-#pragma unroll
-      for (int ul = 0; ul < 2; ++ul) {
-        const int u = egrp + 2 * ul;
-        if (u >= units) break;
-        const int g = u / ngrp64;
-        uint8_t* sbuf = stage_out + (size_t)(use & 1) * OUT_STAGE_BYTES;
-        if (p.out_tma) {
-          // the TMA store that last read this staging buffer must have finished reading it
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
-        }
-        const float* bias = p.bias + (size_t)imgs[ul] * p.bias_img_stride + n0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = cg0[ul] + q * 16;
-          if (c0 >= p.BN) break;
-          uint32_t v[16];
-          tc_ld16(tbase + (uint32_t)(g * p.BN + c0), v);
-          tc_wait_ld();
-          if (p.dbg_skip & 4) continue;
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-            f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (p.residual && valid[ul]) {
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              if (res_vec && n0 + c0 + hq * 8 + 8 <= p.Cout) {
-                const uint4 rv = rres[ul * 8 + q * 2 + hq];
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-                  f[hq * 8 + 2 * j] += __low2float(h);
-                  f[hq * 8 + 2 * j + 1] += __high2float(h);
-                }
-              } else {
-                const bf16* rp = p.residual + pix[ul] * p.res_ld + n0 + c0 + hq * 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)   // static indices only: keeps f[] in registers
-                  if (n0 + c0 + hq * 8 + j < p.Cout) f[hq * 8 + j] += __bfloat162float(rp[j]);
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (p.out_tma) {
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              w[j] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            // row m, 16-byte chunks 2q and 2q+1 of the 128-byte row, XOR-swizzled with (m & 7)
-            uint8_t* rowp = sbuf + (size_t)m * 128;
-            *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else if (valid[ul] && n0 + c0 < p.Cout) {
-            const bool full16 = (n0 + c0 + 16 <= p.Cout);
-            if (p.out_fp32) {
-              float* op = reinterpret_cast<float*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
-              if (full16 && ((p.out_ld | p.out_coff) & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (n0 + c0 + j < p.Cout) op[j] = f[j];
-              }
-            } else {
-              bf16* op = reinterpret_cast<bf16*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < p.Cout) op[j] = __float2bfloat16(f[j]);
-            }
-          }
-        }
-        if (p.out_tma) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
-          if (issuer && !(p.dbg_skip & (4 | 8))) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                ::"l"(reinterpret_cast<uint64_t>(&tmapO)), "r"(smem_u32(sbuf)), "r"(n0 + cg0[ul]), "r"(oxs[ul]),
-                "r"(oys[ul]), "r"(imgs[ul])
-                : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          ++use;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u); else mbar_arrive(tempty0 + (uint32_t)acc * 8u);
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epilogue_loop<CTAS, 2>(p, &tmapO, smem + (size_t)p.stages * stage_bytes + 1024, tfull_bar, tempty_bar, tmem_base,
+                        cta_rank, unit_id, p.total_tiles, n_units);
   }
 
   tc_fence_before();
@@ -425,6 +452,163 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// "slab" kernel: 3x3 stride-1 convolutions on 128-pixel-wide maps with Cin = Cout = 64 (ResNet layer 1)
+// ---------------------------------------------------------------------------------------
+// The generic kernel re-loads the 128 x 64 A slab of a pixel tile for each of the 9 filter taps and, at
+// N = 64, spends 72 KB of L2 -> SMEM traffic per 512 MMA clocks (~140 B/clk/SM against the ~50 the L2 can
+// deliver): these layers ran at 539 TFLOP/s.  Here an M tile is one full image row, the input rows are
+// streamed ONCE through a ring of shared-memory slots (130 pixels x 128 B: left/right halo by TMA
+// out-of-bounds fill), and the A operand of tap (r, s) is simply the slot of input row y + r - 1 with its
+// start address advanced by s pixels (s x 128 B).  The 128-byte swizzle is a function of the absolute
+// shared-memory address bits (measured: the descriptor's base-offset field must stay 0 for such a start; with
+// base offset = s the results are wrong), so a window that starts at any 128-byte row reads what TMA wrote.  All 9 weight tiles stay resident (72 KB).  A CTA owns a contiguous range
+// of "super rows" (4 output rows = 4 interleaved accumulators); consecutive super rows reuse 2 of their 6
+// input rows, slots are released tap-row by tap-row with tcgen05.commit so the ring (7 slots) never stalls.
+constexpr int SLAB_SLOTS = 7;
+constexpr uint32_t SLAB_ROW_BYTES = 17 * 1024;        // 130 px x 128 B = 16640, padded to 1024
+constexpr uint32_t SLAB_ROW_TX = 130 * 128;
+constexpr uint32_t SLAB_B_TAP_BYTES = 64 * 128;       // 8 KB per filter tap
+constexpr uint32_t SLAB_B_BYTES = 9 * SLAB_B_TAP_BYTES;
+constexpr size_t SLAB_SMEM = 1024 + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES + SLAB_B_BYTES + 1024 + 2 * OUT_STAGE_BYTES;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* rows = smem;
+  uint8_t* bmat = rows + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES;
+  uint8_t* bar_base = bmat + SLAB_B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + SLAB_SLOTS;
+  uint64_t* bfull_bar = empty_bar + SLAB_SLOTS;
+  uint64_t* tfull_bar = bfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* stage_out = bar_base + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_img = p.Hout / 4;
+  // contiguous range of super rows for this CTA
+  const int st_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int st_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SLAB_SLOTS; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(bfull_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(smem_u32(bfull_bar), SLAB_B_BYTES);
+      for (int t = 0; t < 9; ++t)
+        tma_load_2d(smem_u32(bmat) + (uint32_t)t * SLAB_B_TAP_BYTES, &tmapB, smem_u32(bfull_bar), t * BK, 0);
+    }
+    __syncwarp();
+    uint32_t L = 0;   // row-load counter: load L goes to slot L % SLOTS, use (L / SLOTS)
+    for (int st = st_begin; st < st_end; ++st) {
+      const int img = st / tiles_per_img, y0 = (st - img * tiles_per_img) * 4;
+      const bool carry = (st > st_begin) && (y0 != 0);    // rows y0-1, y0 are the previous super row's last two
+      for (int q = carry ? 2 : 0; q < 6; ++q) {
+        const uint32_t slot = L % SLAB_SLOTS, use = L / SLAB_SLOTS;
+        mbar_wait(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[slot]);
+          mbar_arrive_expect_tx(fb, SLAB_ROW_TX);
+          tma_load_4d(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
+        }
+        __syncwarp();
+        ++L;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
+    uint32_t base = 0, waited = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int st = st_begin; st < st_end; ++st) {
+      const int y0 = (st % tiles_per_img) * 4;
+      const bool next_carry = (st + 1 < st_end) && (y0 + 4 < p.Hout);
+      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 4 * 64);
+      for (int r = 0; r < 3; ++r) {
+        while (waited <= base + (uint32_t)r + 3u) {
+          mbar_wait(smem_u32(&full_bar[waited % SLAB_SLOTS]), (waited / SLAB_SLOTS) & 1, p.errflag, 3);
+          ++waited;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3 + s) * SLAB_B_TAP_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t slot = (base + (uint32_t)(r + g)) % SLAB_SLOTS;
+                const uint32_t a_addr = smem_u32(rows) + slot * SLAB_ROW_BYTES + (uint32_t)s * 128u;
+                tc_mma_bf16(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
+                            bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
+              }
+            }
+          }
+          // release the rows whose last use was this tap row
+          if (r < 2) {
+            tc_commit(smem_u32(&empty_bar[(base + (uint32_t)r) % SLAB_SLOTS]));
+          } else {
+            tc_commit(smem_u32(&empty_bar[(base + 2u) % SLAB_SLOTS]));
+            tc_commit(smem_u32(&empty_bar[(base + 3u) % SLAB_SLOTS]));
+            if (!next_carry) {
+              tc_commit(smem_u32(&empty_bar[(base + 4u) % SLAB_SLOTS]));
+              tc_commit(smem_u32(&empty_bar[(base + 5u) % SLAB_SLOTS]));
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      base += next_carry ? 4u : 6u;
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<1, 1>(p, &tmapO, stage_out, tfull_bar, tempty_bar, tmem_base, 0u, st_begin, st_end, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -517,7 +701,87 @@ int conv_tc_supported(const ConvWeights& w, const ConvArgs& a) {
   return make_plan(w, a, &pl) && get_encode_fn() != nullptr;
 }
 
+namespace {
+
+bool slab_eligible(const ConvWeights& w, const ConvArgs& a) {
+  if (const char* e = getenv("BDRC_TC_SLAB"))
+    if (atoi(e) == 0) return false;
+  return w.R == 3 && w.S == 3 && a.stride_h == 1 && a.stride_w == 1 && a.dil_h == 1 && a.dil_w == 1 && a.pad_h == 1 &&
+         a.pad_w == 1 && w.Cin == 64 && w.Cin_pad == 64 && w.Cout_pad == 64 && a.Win == 128 && a.Wout == 128 &&
+         a.Hin == a.Hout && a.Hout % 4 == 0 && !a.out_fp32 && a.out_ld % 8 == 0 && a.out_coff % 8 == 0 &&
+         a.in_ld % 8 == 0 && a.in_coff % 8 == 0 && a.N >= 1;
+}
+
+int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  CUtensorMap mapA, mapB, mapO;
+  {
+    const cuuint64_t ld = (cuuint64_t)a.in_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)w.Cin, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Win * ld * 2, (cuuint64_t)a.Hin * a.Win * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 130, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(a.in) + a.in_coff, dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab A) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
+    cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, 64};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab B) failed: %d", (int)r);
+  }
+  {
+    const cuuint64_t ld = (cuuint64_t)a.out_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)w.Cout, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<bf16*>(a.out) + a.out_coff, dims,
+                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab out) failed: %d", (int)r);
+  }
+  TcParams p;
+  p.tiles_n = 1; p.tiles_w = 1; p.tiles_h = a.Hout; p.n_img = a.N;
+  p.total_tiles = a.N * (a.Hout / 4);
+  p.BW = 128; p.BH = 1; p.BN = 64; p.stages = 0; p.G = 4;
+  p.R = 3; p.S = 3; p.kchunks = 1;
+  p.stride_h = p.stride_w = 1; p.pad_h = p.pad_w = 1; p.dil_h = p.dil_w = 1;
+  p.par_c = a.in_ld;
+  p.Hout = a.Hout; p.Wout = a.Wout; p.Cout = w.Cout;
+  p.idesc = make_idesc_bf16(BM, 64);
+  p.tmem_cols = 512;
+  p.bias = a.bias_override ? a.bias_override : w.b;
+  p.bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
+  p.residual = a.residual; p.res_ld = a.res_ld;
+  p.out = a.out; p.out_ld = a.out_ld; p.out_coff = a.out_coff; p.out_fp32 = 0;
+  p.relu = a.relu;
+  p.out_tma = 1;
+  p.errflag = ctx->d_errflag;
+  p.dbg_skip = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+  conv_tc_slab_kernel<<<grid, NUM_THREADS, SLAB_SMEM, s>>>(mapA, mapB, mapO, p);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+}  // namespace
+
 int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
+  if (slab_eligible(w, a)) return conv_tc_slab_launch(ctx, w, a, s);
   TcPlan pl;
   if (!make_plan(w, a, &pl)) return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED, "conv_tc: unsupported shape");
   EncodeTiledFn enc = get_encode_fn();

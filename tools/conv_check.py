@@ -74,6 +74,8 @@ CASES = [
     ("gemm_1x1_n256", 2, 1, 384, 512, 256, 1, 1, (1, 1), (0, 0), (1, 1), False, True, False),
     ("gemm_1x1_n512", 1, 32, 32, 512, 512, 1, 1, (1, 1), (0, 0), (1, 1), True, True, False),
     ("c3x3_64_128sq", 2, 128, 128, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1), True, True, False),
+    ("c3x3_64_128sq_n5", 5, 128, 128, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1), False, False, False),
+    ("c3x3_64_128x8", 3, 8, 128, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1), True, False, False),
     ("c3x3_128_64sq", 2, 64, 64, 128, 128, 3, 3, (1, 1), (1, 1), (1, 1), True, True, False),
     ("c3x3_256_32sq", 3, 32, 32, 256, 256, 3, 3, (1, 1), (1, 1), (1, 1), False, True, False),
     ("c3x3_d2_512", 2, 32, 32, 512, 512, 3, 3, (1, 1), (2, 2), (2, 2), True, True, False),
