@@ -331,6 +331,36 @@ def bench_c3(eng, steps: int, pages_per_step: int = 16, workers: int = 4):
     }
 
 
+def bench_c4(eng, steps: int = 2):
+    """Modern-layout path (torch-path semantics: float-bilinear resize_clamp, pad 255, RGB tiles, /255 in the
+    stem, softmax over 5 classes, stitch, crop, resize back, > 0.8) on mixed page sizes."""
+    import torch
+
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.data import LayoutDetectionConfig
+    from ocr_inference_b200.inference import ModernBookFormatLayoutDetection
+    from ocr_inference_b200.synthetic_weights import seg_weights
+    from ocr_inference_b200.weights import write_blob
+
+    classes = ["background", "image", "line", "caption", "margin"]
+    det = ModernBookFormatLayoutDetection(LayoutDetectionConfig(write_blob(seg_weights(13, 5, 3)), "", "deeplabv3plus", 512,
+                                                                classes), engine=eng)
+    sizes = [(472, 2550), (1200, 1800), (2048, 3072), (3300, 2550), (700, 4600), (400, 1500)]
+    pages = [synthetic.page(4004 + i, h, w, rgb=True)[0] for i, (h, w) in enumerate(sizes)]
+    for p in pages:
+        det.predict_masks(p, 0.8)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for p in pages:
+            m = det.predict_masks(p, 0.8)
+    dt = (time.perf_counter() - t0) / steps
+    return {"workload": "C4: ModernBookFormatLayoutDetection.predict_masks on 6 page sizes "
+                        f"{sizes} (5 classes, random-init), host page in -> host [5,H,W] masks out",
+            "e2e_pages_per_sec": len(pages) / dt, "ms_per_page": dt * 1e3 / len(pages),
+            "megapixels_per_sec": sum(h * w for h, w in sizes) / dt / 1e6, "last_mask_shape": list(m.shape)}
+
+
 def _c3_worker(rank, n_workers, device, pages_per_worker, steps, threads, barrier, q):
     """One host process of the C3 page->text run: owns a shard of the pages and its own OCRPipeline (CUDA
     context, weights, workspaces) on `device`.  Pages are independent units: no exchange."""
@@ -536,6 +566,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             extras["c1"] = bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline)
             extras["c3"] = bench_c3(eng, 2)
+            extras["c4"] = bench_c4(eng)
             nproc = max(2, min(8, len(os.sched_getaffinity(0)) // 2))
             extras["c3"]["multi_process"] = bench_c3_procs(local_rank, nproc)
         except Exception as e:  # noqa: BLE001  (the headline must still print)

@@ -88,6 +88,11 @@ struct ConvArgs {
   int out_ld = 0, out_coff = 0;
   int out_fp32 = 0;
   int relu = 0;
+  // optional fused 1x1 head (tcgen05 engine only): out is not written, head_out [N,Hout,Wout,head_C] fp32 is
+  const float* head_w = nullptr;          // [head_C][Cout_pad] fp32
+  const float* head_b = nullptr;
+  float* head_out = nullptr;
+  int head_C = 0;
 };
 
 int conv_tc_supported(const ConvWeights& w, const ConvArgs& a);

@@ -47,6 +47,12 @@ struct TcParams {
   int res_ld;
   void* out;
   int out_ld, out_coff, out_fp32, relu, out_tma;
+  // optional fused 1x1 "head" over the (ReLU'd, bf16-rounded) outputs of this layer: head_out[pix][c] =
+  // head_b[c] + sum_n out[pix][n] * head_w[c][n]; the layer's own output is then not stored at all
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int head_C, head_ld;
   int* errflag;
   int dbg_skip;   // timing experiments only -- bit 0: skip A loads, 1: skip B loads, 2: skip epilogue math + I/O,
                   // 3: skip the TMA stores, 4: skip the residual loads
@@ -152,6 +158,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
       }
 
+      float hacc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) hacc[c] = 0.f;
+
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * G * p.BN);
@@ -211,7 +221,25 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (p.out_tma) {
+          if (p.head_w) {
+            // the head consumes this layer's output as the unfused path stores it: rounded to bf16
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c < p.head_C) {
+                const float* hw = p.head_w + (size_t)c * p.BN + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(hw + j));
+                  hacc[c] = fmaf(f[j + 0], w4.x, hacc[c]);
+                  hacc[c] = fmaf(f[j + 1], w4.y, hacc[c]);
+                  hacc[c] = fmaf(f[j + 2], w4.z, hacc[c]);
+                  hacc[c] = fmaf(f[j + 3], w4.w, hacc[c]);
+                }
+              }
+            }
+          } else if (p.out_tma) {
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -222,7 +250,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
             uint8_t* rowp = sbuf + (size_t)m * 128;
             *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else if (valid[ul] && n0 + c0 < p.Cout) {
+          } else if (valid[ul] && n0 + c0 < p.Cout) {   // (never reached with a fused head: handled above)
             const bool full16 = (n0 + c0 + 16 <= p.Cout);
             if (p.out_fp32) {
               float* op = reinterpret_cast<float*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
@@ -263,6 +291,21 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         if (CTAS == 2) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u); else mbar_arrive(tempty0 + (uint32_t)acc * 8u);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.head_w) {
+        // the two epilogue groups hold the partial dot products of their column groups: combine through
+        // shared memory (two buffers alternate, so one 256-thread barrier per tile is enough)
+        float* hbuf = reinterpret_cast<float*>(stage_out_base) + (size_t)(use & 1) * (2 * 128 * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hbuf[((size_t)egrp * 128 + m) * 8 + c] = hacc[c];
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (egrp == 0 && valid[0]) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < p.head_C)
+              p.head_out[pix[0] * p.head_ld + c] = hbuf[(size_t)m * 8 + c] + hbuf[((size_t)128 + m) * 8 + c] + __ldg(p.head_b + c);
+        }
+        ++use;
+      }
     }
     if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -704,6 +747,7 @@ int conv_tc_supported(const ConvWeights& w, const ConvArgs& a) {
 namespace {
 
 bool slab_eligible(const ConvWeights& w, const ConvArgs& a) {
+  if (a.head_w) return false;
   if (const char* e = getenv("BDRC_TC_SLAB"))
     if (atoi(e) == 0) return false;
   return w.R == 3 && w.S == 3 && a.stride_h == 1 && a.stride_w == 1 && a.dil_h == 1 && a.dil_w == 1 && a.pad_h == 1 &&
@@ -767,6 +811,7 @@ int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, 
   p.out_tma = 1;
   p.errflag = ctx->d_errflag;
   p.dbg_skip = 0;
+  p.head_w = nullptr; p.head_b = nullptr; p.head_out = nullptr; p.head_C = 0; p.head_ld = 0;
   static bool attr_set = false;
   if (!attr_set) {
     BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM));
@@ -855,6 +900,12 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
   {
     const char* e = getenv("BDRC_DBG_SKIP");
     p.dbg_skip = e ? atoi(e) : 0;
+  }
+  p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.head_C = a.head_C; p.head_ld = a.head_C;
+  if (a.head_w) {
+    if (pl.tiles_n != 1 || pl.G != 1 || pl.ctas != 1 || a.head_C < 1 || a.head_C > 8 || pl.BN % 64 != 0)
+      return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED, "conv_tc: fused head needs one column tile, G = 1 and <= 8 classes");
+    p.out_tma = 0;
   }
 
   static bool attr_set = false;
