@@ -265,6 +265,9 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     eng.profile(False)
     tc = [(n, t, f) for (n, t, f) in prof if f > 0]
     tc_ms, tc_fl = sum(x[1] for x in tc), sum(x[2] for x in tc)
+    by = {}
+    for n, t, f in prof:
+        by[n] = by.get(n, 0.0) + t / steps
     for _ in range(2):
         texts = ocr.run_batch(crops, pre_pad=False)
     t0 = time.perf_counter()
@@ -286,6 +289,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
                      "frac": (tc_fl / (tc_ms / 1e3) / 1e12) / peak_tf if tc_ms else 0.0, "peak_source": peak_src,
                      "share_of_step": tc_ms / steps / ms if ms else None},
         "lines_equal_to_truth": sum(a == b for a, b in zip(texts, want)) / C1_LINES,
+        "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1])},
     }
     if with_cpu:
         v, cores, ref_ids = cpu_reference_lines_per_sec(16)

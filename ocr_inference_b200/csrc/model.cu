@@ -238,8 +238,31 @@ int load_ocr(Loader& L, int vocab) {
   const int ks[3] = {5, 7, 9};
   for (int u = 0; u < 3; ++u) {
     const std::string p = "unit" + std::to_string(u + 1);
-    BDRC_TRY(L.conv(p + ".res_old", 256, cin, 1, 1, true));
-    BDRC_TRY(L.conv(p + ".res_data", 256, cin, 1, 1, true));
+    // res = conv1x1(old) + conv1x1(data) as ONE GEMM: in unit 1 old == data (weights add), later the two
+    // inputs are adjacent channel slices [old | data] of one buffer (weights concatenate along K)
+    {
+      const BlobTensor* wo = L.get(p + ".res_old.weight", {256, cin, 1});
+      const BlobTensor* wd = L.get(p + ".res_data.weight", {256, cin, 1});
+      const BlobTensor* bo = L.get(p + ".res_old.bias", {256});
+      const BlobTensor* bd = L.get(p + ".res_data.bias", {256});
+      if (!wo || !wd || !bo || !bd) return BDRC_ERR_WEIGHTS;
+      const int kin = (u == 0) ? cin : 2 * cin;
+      std::vector<float> wc((size_t)256 * kin), bc(256);
+      for (int o = 0; o < 256; ++o) {
+        bc[o] = bo->data[o] + bd->data[o];
+        for (int c = 0; c < cin; ++c) {
+          if (u == 0) {
+            wc[(size_t)o * kin + c] = wo->data[(size_t)o * cin + c] + wd->data[(size_t)o * cin + c];
+          } else {
+            wc[(size_t)o * kin + c] = wo->data[(size_t)o * cin + c];
+            wc[(size_t)o * kin + cin + c] = wd->data[(size_t)o * cin + c];
+          }
+        }
+      }
+      ConvWeights cw;
+      BDRC_TRY(conv_pack_weights(L.ctx, wc.data(), bc.data(), 256, kin, 1, 1, &cw));
+      L.m->conv[p + ".res"] = cw;
+    }
     BDRC_TRY(L.conv(p + ".conv_a", 256, cin, 1, ks[u], true));
     BDRC_TRY(L.conv(p + ".conv_b", 256, 256, 1, ks[u], true));
     BDRC_TRY(L.conv(p + ".conv_c", 256, 256, 1, ks[u], true));
@@ -525,25 +548,26 @@ int ocr_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const bf16* lines, int L, int
   w1.Cin = OCR_CPAD;   // activation view has OCR_CPAD channels per time step
   BDRC_TRY(conv_launch(ctx, "ocr.conv1", w1, mk1d(lines, L, Wt, OCR_CPAD, 3, 2, 1, c1, 128, 1), s));
   BDRC_TRY(conv_launch(ctx, "ocr.conv2", m->conv["conv2"], mk1d(c1, L, T2, 128, 3, 2, 1, b0, 128, 1), s));
-  bf16* old = b0;
-  bf16* data = b0;
-  int cin = 128;
+  // Each unit writes its outputs into one 512-channel "pair" buffer P = [res | data]; the next unit's
+  // residual GEMM reads the whole pair (K = 512), its k-tap convs read the data slice.
+  bf16* pairs[2] = {b1, b2};
+  const bf16* prev = b0;       // unit input: c2 (128 ch) for unit 1, else the previous pair buffer
+  int prev_ld = 128, data_off = 0, cin = 128;
   const int ks[3] = {5, 7, 9};
-  // free buffers rotate among b1..b4 (+ b0 once it is no longer referenced)
+  bf16* da = b3;
+  bf16* db = b4;
   for (int u = 0; u < 3; ++u) {
     const std::string p = "unit" + std::to_string(u + 1);
-    bf16* pool[5] = {b0, b1, b2, b3, b4};
-    bf16* fr[5]; int nf = 0;
-    for (int i = 0; i < 5; ++i) if (pool[i] != old && pool[i] != data) fr[nf++] = pool[i];
-    bf16* res = fr[0]; bf16* da = fr[1]; bf16* db = fr[2];
-    // res = conv1x1(old) + conv1x1(data)   (second GEMM accumulates through the residual input)
-    BDRC_TRY(conv_launch(ctx, "ocr.res1x1", m->conv[p + ".res_old"], mk1d(old, L, T, cin, 1, 1, 1, res, 256, 0), s));
+    bf16* P = pairs[u & 1];
     {
-      ConvArgs a = mk1d(data, L, T, cin, 1, 1, 1, res, 256, 0);
-      a.residual = res; a.res_ld = 256;
-      BDRC_TRY(conv_launch(ctx, "ocr.res1x1", m->conv[p + ".res_data"], a, s));
+      ConvArgs a = mk1d(prev, L, T, prev_ld, 1, 1, 1, P, 512, 0);
+      BDRC_TRY(conv_launch(ctx, "ocr.res1x1", m->conv[p + ".res"], a, s));
     }
-    BDRC_TRY(conv_launch(ctx, "ocr.convk", m->conv[p + ".conv_a"], mk1d(data, L, T, cin, ks[u], 1, 1, da, 256, 1), s));
+    {
+      ConvArgs a = mk1d(prev, L, T, prev_ld, ks[u], 1, 1, da, 256, 1);
+      a.in_coff = data_off;
+      BDRC_TRY(conv_launch(ctx, "ocr.convk", m->conv[p + ".conv_a"], a, s));
+    }
     BDRC_TRY(conv_launch(ctx, "ocr.convk", m->conv[p + ".conv_b"], mk1d(da, L, T, 256, ks[u], 1, 1, db, 256, 1), s));
     BDRC_TRY(conv_launch(ctx, "ocr.convk", m->conv[p + ".conv_c"], mk1d(db, L, T, 256, ks[u], 1, 1, da, 256, 0), s));
     const FcWeights& f1 = m->fc[p + ".se_fc1"];
@@ -552,14 +576,17 @@ int ocr_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const bf16* lines, int L, int
     BDRC_TRY(se_gate_launch(ctx, da, L, T, 256, f1.w, f1.b, 32, f2.w, f2.b, gate, s));
     bdrc_prof_end(ctx, s);
     bdrc_prof_begin(ctx, "ocr.se_apply", 0, s);
-    BDRC_TRY(se_apply_launch(ctx, res, da, gate, L, T, 256, db, s));
+    BDRC_TRY(se_apply_launch(ctx, P, 512, da, gate, L, T, 256, P + 256, 512, s));
     bdrc_prof_end(ctx, s);
-    data = db; old = res; cin = 256;
+    prev = P; prev_ld = 512; data_off = 256; cin = 256;
   }
-  bf16* pool[5] = {b0, b1, b2, b3, b4};
-  bf16* fr[5]; int nf = 0;
-  for (int i = 0; i < 5; ++i) if (pool[i] != old && pool[i] != data) fr[nf++] = pool[i];
-  BDRC_TRY(conv_launch(ctx, "ocr.conv3", m->conv["conv3"], mk1d(data, L, T, 256, 11, 1, 2, fr[0], 512, 1), s));
+  (void)cin;
+  bf16* fr[2] = {pairs[1], b3};   // pairs[1] (unit 2's pair) is dead once unit 3 has consumed it
+  {
+    ConvArgs a = mk1d(prev, L, T, 512, 11, 1, 2, fr[0], 512, 1);
+    a.in_coff = 256;
+    BDRC_TRY(conv_launch(ctx, "ocr.conv3", m->conv["conv3"], a, s));
+  }
   BDRC_TRY(conv_launch(ctx, "ocr.conv4", m->conv["conv4"], mk1d(fr[0], L, T, 512, 1, 1, 1, fr[1], 512, 1), s));
   {
     ConvArgs a = mk1d(fr[1], L, T, 512, 1, 1, 1, logits, V, 0);

@@ -618,9 +618,9 @@ se_gate_kernel(const bf16* __restrict__ d, int T, int C, const float* __restrict
   }
 }
 
-__global__ void se_apply_kernel(const bf16* __restrict__ res, const bf16* __restrict__ d,
+__global__ void se_apply_kernel(const bf16* __restrict__ res, int res_ld, const bf16* __restrict__ d,
                                 const float* __restrict__ gate, int T, int C, size_t total8,
-                                bf16* __restrict__ out) {
+                                bf16* __restrict__ out, int out_ld) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total8) return;
   const int C8 = C / 8;
@@ -628,12 +628,12 @@ __global__ void se_apply_kernel(const bf16* __restrict__ res, const bf16* __rest
   const size_t row = idx / C8;          // l*T + t
   const int l = (int)(row / T);
   float r[8], dv[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(res) + idx), r);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * res_ld + c8 * 8)), r);
   unpack8(__ldg(reinterpret_cast<const uint4*>(d) + idx), dv);
   const float* gp = gate + (size_t)l * C + c8 * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(dv[j], gp[j], r[j]), 0.f);
-  reinterpret_cast<uint4*>(out)[idx] = pack8(o);
+  *reinterpret_cast<uint4*>(out + row * out_ld + c8 * 8) = pack8(o);
 }
 
 }  // namespace
@@ -758,11 +758,11 @@ int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const floa
   return 0;
 }
 
-int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* gate, int L, int T,
-                    int C, bf16* out, cudaStream_t s) {
-  BDRC_REQUIRE(ctx, C % 8 == 0, "se_apply: C %% 8 != 0");
+int se_apply_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, const float* gate, int L, int T,
+                    int C, bf16* out, int out_ld, cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0 && res_ld % 8 == 0 && out_ld % 8 == 0, "se_apply: C, res_ld, out_ld must be multiples of 8");
   const size_t total8 = (size_t)L * T * (C / 8);
-  se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(res, d, gate, T, C, total8, out);
+  se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(res, res_ld, d, gate, T, C, total8, out, out_ld);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

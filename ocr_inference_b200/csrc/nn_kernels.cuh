@@ -38,9 +38,9 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
 int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
                    const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
                    cudaStream_t s);
-// data = relu(res + d * gate)
-int se_apply_launch(bdrc_ctx* ctx, const bf16* res, const bf16* d, const float* gate, int L, int T,
-                    int C, bf16* out, cudaStream_t s);
+// data = relu(res + d * gate); res rows have stride res_ld, out rows stride out_ld (channel slices of wider buffers)
+int se_apply_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, const float* gate, int L, int T,
+                    int C, bf16* out, int out_ld, cudaStream_t s);
 
 // Stem + max-pool fused on the tensor cores (stem_tc.cu): u8 tiles [N][512][512] (3 identical channels
 // folded) -> bf16 NHWC [N][128][128][64].  w_bf16: [64 cout][64 k] with k = 8 * kernel_row + kernel_col.

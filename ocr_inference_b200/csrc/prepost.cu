@@ -555,13 +555,20 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
   int* status = reinterpret_cast<int*>(canvas + align_up((size_t)L * Ht * Wt, 256));
   BDRC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)L * sizeof(int), s));
   dim3 grid(ceil_div(Wt, 128), Ht, L);
+  bdrc_prof_begin(ctx, "a-7.canvas", 0, s);
   ocr_canvas_kernel<<<grid, 128, 0, s>>>(crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status);
+  bdrc_prof_end(ctx, s);
   BDRC_CHECK_LAUNCH(ctx);
+  bdrc_prof_begin(ctx, "a-7.zero_pad_channels", 0, s);
   if (lines_bf16 && Cpad > Ht)   // zero the padding channels Ht..Cpad-1
     BDRC_CUDA(ctx, cudaMemsetAsync(lines_bf16, 0, (size_t)L * Wt * Cpad * sizeof(bf16), s));
+  bdrc_prof_end(ctx, s);
   adaptive::SrcGrayBatch src{canvas, Ht, Wt};
   adaptive::SinkOcrLines sink{reinterpret_cast<bf16*>(lines_bf16), lines_f32, Ht, Wt, Cpad};
-  return adaptive::launch(ctx, src, sink, L, Ht, Wt, s);
+  bdrc_prof_begin(ctx, "a-7.adaptive_threshold", 0, s);
+  const int rc = adaptive::launch(ctx, src, sink, L, Ht, Wt, s);
+  bdrc_prof_end(ctx, s);
+  return rc;
 }
 
 int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout, int blank,
@@ -575,7 +582,9 @@ int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int
   if (smem > 48 * 1024)
     BDRC_CUDA(ctx, cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
+  bdrc_prof_begin(ctx, "a-9.ctc_greedy", 0, (cudaStream_t)stream);
   ctc_greedy_kernel<<<L, 512, smem, (cudaStream_t)stream>>>(logits, V, T, layout, blank, ids, lens);
+  bdrc_prof_end(ctx, (cudaStream_t)stream);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
