@@ -371,6 +371,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
+constexpr int CTC_ROWS = 128;
 __global__ void __launch_bounds__(512)
 ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, int blank,
                   int32_t* __restrict__ ids, int32_t* __restrict__ lens) {
@@ -381,20 +382,31 @@ ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, in
   const float* base = logits + (size_t)l * V * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   if (layout == BDRC_LAYOUT_TV) {
-    for (int t = warp; t < T; t += nwarp) {
-      const float* row = base + (size_t)t * V;
-      float bv = -INFINITY; int bi = 0x7fffffff;
-      for (int v = lane; v < V; v += 32) {
-        const float x = row[v];
-        if (bi == 0x7fffffff || better(x, v, bv, bi)) { bv = x; bi = v; }
+    // [T][V] rows are short (V = 77 -> 308 B) and unaligned: stream the line through shared memory in
+    // chunks of CTC_ROWS time steps with fully coalesced loads (every thread keeps several in flight),
+    // then one thread per time step scans its row (row pitch V|1 is odd: conflict-free).
+    float* buf = reinterpret_cast<float*>(sm + 2 * T);
+    const int pitch = V | 1;
+    for (int t0 = 0; t0 < T; t0 += CTC_ROWS) {
+      const int rows = min(CTC_ROWS, T - t0);
+      const float* src = base + (size_t)t0 * V;
+      const int n = rows * V;
+#pragma unroll 8
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = i / V, c = i - r * V;
+        buf[r * pitch + c] = __ldg(src + i);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+      __syncthreads();
+      if (threadIdx.x < rows) {
+        const float* row = buf + threadIdx.x * pitch;
+        float bv = row[0]; int bi = 0;
+        for (int v = 1; v < V; ++v) {
+          const float x = row[v];
+          if (better(x, v, bv, bi)) { bv = x; bi = v; }
+        }
+        am[t0 + threadIdx.x] = bi;
       }
-      if (lane == 0) am[t] = bi;
+      __syncthreads();
     }
   } else {
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
@@ -578,7 +590,9 @@ int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int
   BDRC_REQUIRE(ctx, logits && ids && lens && V > 0 && T > 0 && T <= 20000 &&
                         (layout == BDRC_LAYOUT_TV || layout == BDRC_LAYOUT_VT),
                "ctc_greedy: bad arguments (V=%d T=%d)", V, T);
-  const size_t smem = (size_t)2 * T * sizeof(int);
+  const size_t smem = (size_t)2 * T * sizeof(int) +
+                      (layout == BDRC_LAYOUT_TV ? (size_t)CTC_ROWS * (V | 1) * sizeof(float) : 0);
+  BDRC_REQUIRE(ctx, smem <= 200 * 1024, "ctc_greedy: V * 128 + 2 T exceeds the shared-memory budget (V=%d T=%d)", V, T);
   if (smem > 48 * 1024)
     BDRC_CUDA(ctx, cudaFuncSetAttribute(ctc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));

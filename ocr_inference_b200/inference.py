@@ -155,7 +155,8 @@ class Detection:
                 ups.append(d)
                 evs.append(ev)
         outs = []
-        group = 2   # 2 landscape pages = 48 tiles = one forward chunk; later groups upload meanwhile
+        group = 3   # pages per forward call (72 tiles of a landscape page: ~4 whole waves per ResNet stage on 148
+        #             SMs); later groups upload meanwhile
         for g0 in range(0, len(ups), group):
             for d, ev in zip(ups[g0:g0 + group], evs[g0:g0 + group]):
                 compute.wait_event(ev)
