@@ -208,6 +208,10 @@ int bdrc_conv2d_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int Cin,
                      const float* w_host, const float* bias_host, int Cout, int R, int S,
                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                      const void* residual, int relu, int out_fp32, void* y, void* stream);
+/* Test hook: depthwise 3x3 (pad = dilation, no bias) on bf16 NHWC x [N][H][W][C], weights fp32 [9][C] on the
+ * host, y like x; synchronises the stream.  Used by tools/ and tests to exercise the kernel variants directly. */
+int bdrc_depthwise3x3_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int C, int dil,
+                           const float* w9c_host, void* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 // Context management and the small C-ABI entry points that are not tied to one stage.
 #include "common.cuh"
+#include "nn_kernels.cuh"
 
 extern "C" {
 
@@ -104,6 +105,21 @@ int bdrc_conv2d_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int Cin,
   conv_free_weights(&cw);
   if (rc) return rc;
   if (e != cudaSuccess) return bdrc_fail(ctx, BDRC_ERR_CUDA, "conv2d_test: %s", cudaGetErrorString(e));
+  return BDRC_OK;
+}
+
+int bdrc_depthwise3x3_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int C, int dil,
+                           const float* w9c_host, void* y, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  float* w = nullptr;
+  BDRC_CUDA(ctx, cudaMalloc(&w, (size_t)9 * C * sizeof(float)));
+  cudaMemcpy(w, w9c_host, (size_t)9 * C * sizeof(float), cudaMemcpyHostToDevice);
+  int rc = depthwise3x3_launch(ctx, reinterpret_cast<const bf16*>(x), C, 0, N, H, W, C, dil, w,
+                               reinterpret_cast<bf16*>(y), C, 0, (cudaStream_t)stream);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(w);
+  if (rc) return rc;
+  if (e != cudaSuccess) return bdrc_fail(ctx, BDRC_ERR_CUDA, "depthwise3x3_test: %s", cudaGetErrorString(e));
   return BDRC_OK;
 }
 

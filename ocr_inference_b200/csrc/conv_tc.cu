@@ -323,8 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int G = p.G;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const int unit_id = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // CTA or CTA pair
@@ -522,7 +521,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* rows = smem;
   uint8_t* bmat = rows + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES;
   uint8_t* bar_base = bmat + SLAB_B_BYTES;

@@ -213,20 +213,22 @@ depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int
   }
 }
 
-// Depthwise 3x3, dilation 1, TMA-fed row ring.  A CTA owns (image, 64-channel chunk, 32-pixel column
-// band, segment of DWR_ROWS output rows).  Input rows (34 px x 64 ch = 4352 B, halo and channel tail
+// Depthwise 3x3, dilation 1, TMA-fed row ring.  A CTA owns (image, 64-channel chunk, DWR_PX-pixel column
+// band, segment of DWR_ROWS output rows).  Input rows ((DWR_PX + 2) px x 64 ch, halo and channel tail
 // zero-filled by TMA out-of-bounds handling) stream through an 8-slot shared-memory ring, each loaded
 // exactly once; thread (px, 8-channel group) reads its 3 neighbours of the arriving row and feeds the
 // three output rows that row contributes to, so an output costs 3 LDS.128 + 72 FMA and the 72 weights
 // stay in registers.  Summation order per output is (r, s) row-major as in the direct kernel.
-constexpr int DWR_PX = 32, DWR_SLOTS = 8, DWR_ROWS = 32;
+constexpr int DWR_PX = 32, DWR_SLOTS = 8, DWR_ROWS = 32, DWR_THREADS = DWR_PX * 8;
 constexpr int DWR_SLOT_BYTES = (DWR_PX + 2) * 128;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DWR_THREADS)
 depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, int W, int C,
                       const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff, int* errflag) {
   extern __shared__ __align__(128) uint8_t dwr_smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwr_smem_raw) + 127) & ~uintptr_t(127));
+  // 128-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t makes the
+  // compiler forget the address space and emit generic LD instead of LDS)
+  uint8_t* ring = dwr_smem_raw + ((128u - (tcptx::smem_u32(dwr_smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[DWR_SLOTS];
   const int xt_n = W / DWR_PX, chunks = (C + 63) / 64, segs = (H + DWR_ROWS - 1) / DWR_ROWS;
   int item = blockIdx.x;
@@ -279,13 +281,14 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
     uint4 v[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) v[s] = *reinterpret_cast<const uint4*>(row + s * 128);
-    // The slot is refilled by TMA (async proxy) right after the barrier.  Arriving at a barrier does not
-    // wait for this thread's outstanding shared-memory LOADS, and an async-proxy write is not ordered
-    // behind them: pin the loaded registers (forces the loads to have returned) and fence the proxies
-    // before the barrier.  (Without this a few output pixels per launch were wrong, run to run.)
-#pragma unroll
-    for (int s = 0; s < 3; ++s) asm volatile("" ::"r"(v[s].x), "r"(v[s].y), "r"(v[s].z), "r"(v[s].w) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // The slot is refilled by TMA (async proxy) right after the barrier.  Arriving at a barrier does not wait
+    // for this thread's outstanding shared-memory LOADS (the scoreboard only stalls an instruction that reads
+    // their destination registers) and an async-proxy write is not ordered behind them, so a refill could
+    // overtake a load still in flight: wrong pixels, different from run to run (tools/dw_check.py,
+    // tests/test_gpu_determinism.py).  __threadfence_block() compiles to MEMBAR.SC.CTA + DEPBAR on the load
+    // scoreboard: every thread's loads have returned before it arrives.  ("Using" the registers in an asm
+    // statement does not help: ptxas drops instructions whose result is unused.)
+    __threadfence_block();
     __syncthreads();
     if (tid == 0 && k + DWR_SLOTS < rows_in) issue(k + DWR_SLOTS);
 #pragma unroll
@@ -317,7 +320,7 @@ aspp_dw3_kernel(const __grid_constant__ CUtensorMap tmap, int C, int r0, int r1,
                 bf16* __restrict__ o0, bf16* __restrict__ o1, bf16* __restrict__ o2, float* __restrict__ mean_out,
                 int* errflag) {
   extern __shared__ __align__(128) uint8_t aspp_smem_raw[];
-  uint8_t* slab = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aspp_smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* slab = aspp_smem_raw + ((128u - (tcptx::smem_u32(aspp_smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t bar;
   __shared__ float part[32][64];
   const int chunks = C / 64;
@@ -682,7 +685,7 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "depthwise: cuTensorMapEncodeTiled failed: %d", (int)r);
     const int items = N * ((C + 63) / 64) * ((H + DWR_ROWS - 1) / DWR_ROWS) * (W / DWR_PX);
-    depthwise_ring_kernel<<<items, 256, DWR_SLOTS * DWR_SLOT_BYTES + 128, s>>>(map, N, H, W, C, w9c, out, out_ld,
+    depthwise_ring_kernel<<<items, DWR_THREADS, DWR_SLOTS * DWR_SLOT_BYTES + 128, s>>>(map, N, H, W, C, w9c, out, out_ld,
                                                                               out_coff, ctx->d_errflag);
     BDRC_CHECK_LAUNCH(ctx);
     return 0;

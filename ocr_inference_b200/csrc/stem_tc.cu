@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1)
 stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restrict__ wb, const float* __restrict__ bias,
                     bf16* __restrict__ out, int* errflag) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                         // 5 x [128][128 B] swizzled; reused as S[640][128 B]
   uint8_t* sB = smem + SMEM_A;                // [64][128 B] swizzled
   uint8_t* sP = sB + SMEM_B;                  // input patch

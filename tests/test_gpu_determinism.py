@@ -31,3 +31,35 @@ def test_ocr_forward_bit_reproducible(engine):
     ref = engine.ocr_forward(model, x).clone()
     for _ in range(6):
         assert torch.equal(engine.ocr_forward(model, x), ref)
+
+
+@pytest.mark.parametrize("shape", [(48, 128, 128, 304), (48, 32, 32, 256), (5, 64, 64, 64)])
+def test_depthwise_ring_kernel_in_isolation(engine, shape):
+    """The TMA row-ring depthwise kernel alone, on random data: equal to the register-strip kernel up to the
+    fp32 summation order, and bit-identical from run to run (the slot-refill race showed up here 20/20 times)."""
+    import ctypes as C
+    import os
+
+    import numpy as np
+
+    N, H, W, Cn = shape
+    g = torch.Generator(device="cpu").manual_seed(H + Cn)
+    x = torch.randn((N, H, W, Cn), generator=g).to(torch.bfloat16).cuda()
+    w = np.ascontiguousarray(np.random.default_rng(Cn).standard_normal((9, Cn)).astype(np.float32))
+
+    def run():
+        y = torch.empty_like(x)
+        rc = engine.lib.bdrc_depthwise3x3_test(engine.ctx.h, x.data_ptr(), N, H, W, Cn, 1, w.ctypes.data, y.data_ptr(),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        engine.ctx.check(rc, "depthwise3x3_test")
+        return y
+
+    os.environ["BDRC_NO_DW_RING"] = "1"
+    try:
+        ref = run()
+    finally:
+        del os.environ["BDRC_NO_DW_RING"]
+    first = run()
+    assert float((first.float() - ref.float()).abs().max()) <= 0.02 * float(ref.float().abs().max())
+    for _ in range(10):
+        assert torch.equal(run(), first)
