@@ -81,9 +81,10 @@ def main():
 
     # a-2 ------------------------------------------------------------------------------------------
     seg = eng.load_model(1, seg_weights_fitted(11), 1)
-    tsets = [(torch.rand((48, 512, 512), device=dev) > 0.2).to(torch.uint8) for _ in range(4)]
-    ms = timeit(lambda t: eng.seg_forward(seg, t, lowres=True), tsets, reps=12)
-    add("a-2", "DeepLabV3+/R34 forward, 48 tiles (2 pages), bf16 tcgen05", ms, flops=48 * seg_flops_per_tile(1), unit_n=2)
+    tsets = [(torch.rand((148, 512, 512), device=dev) > 0.2).to(torch.uint8) for _ in range(3)]
+    ms = timeit(lambda t: eng.seg_forward(seg, t, lowres=True), tsets, reps=9, warm=3)
+    add("a-2", "DeepLabV3+/R34 forward, 148 tiles (one chunk, 6.2 pages), bf16 tcgen05", ms,
+        flops=148 * seg_flops_per_tile(1), unit_n=148 / 24)
 
     # a-3 ------------------------------------------------------------------------------------------
     meta = dict(H0=H, W0=W, Hc=H, Wc=W, nty=4, ntx=6, pad_x=0, pad_y=0)
