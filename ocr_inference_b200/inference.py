@@ -155,22 +155,38 @@ class Detection:
                 ups.append(d)
                 evs.append(ev)
         outs = []
-        group = 3   # pages per forward call (72 tiles of a landscape page: ~4 whole waves per ResNet stage on 148
-        #             SMs); later groups upload meanwhile
-        for g0 in range(0, len(ups), group):
+        # pages per forward call: a small first group starts computing after two uploads, then groups of 6
+        # landscape pages (144 tiles: one 148-tile chunk, ~whole waves per ResNet stage); later groups upload meanwhile
+        sizes, left = [], len(ups)
+        while left > 0:
+            sizes.append(min(left, 2 if not sizes else 6))
+            left -= sizes[-1]
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        copy_out = getattr(self, "_copy_out", None) or torch.cuda.Stream(dev)
+        self._copy_out = copy_out
+        if not hasattr(self, "_host_bufs"):
+            self._host_bufs = {}
+        for g0, group in zip(starts, sizes):
             for d, ev in zip(ups[g0:g0 + group], evs[g0:g0 + group]):
                 compute.wait_event(ev)
                 d.record_stream(compute)
-            for m in self._predict_device_batch(ups[g0:g0 + group], thr):
-                key = ("mask_host", len(outs), tuple(m.shape))
-                h = self._host_bufs.get(key) if hasattr(self, "_host_bufs") else None
-                if h is None:
-                    if not hasattr(self, "_host_bufs"):
-                        self._host_bufs = {}
-                    h = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
-                    self._host_bufs[key] = h
-                h.copy_(m, non_blocking=True)
-                outs.append(h)
+            masks = self._predict_device_batch(ups[g0:g0 + group], thr)
+            done = torch.cuda.Event()
+            done.record(compute)
+            # masks go home on their own stream: a D2H copy queued on the compute stream would hold back the
+            # next group's kernels for its whole duration
+            copy_out.wait_event(done)
+            with torch.cuda.stream(copy_out):
+                for m in masks:
+                    key = ("mask_host", len(outs), tuple(m.shape))
+                    h = self._host_bufs.get(key)
+                    if h is None:
+                        h = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
+                        self._host_bufs[key] = h
+                    h.copy_(m, non_blocking=True)
+                    m.record_stream(copy_out)
+                    outs.append(h)
+        copy_out.synchronize()
         compute.synchronize()
         return [o.numpy().copy() if copy else o.numpy() for o in outs]
 
