@@ -268,6 +268,33 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     by = {}
     for n, t, f in prof:
         by[n] = by.get(n, 0.0) + t / steps
+    # the same path on a page-batch-sized set of lines (8 x the C1 set): what a multi-page caller sees
+    big = [eng.pack_crops(crops) for _ in range(8)]
+    import torch as _t
+    pad16 = lambda t: _t.nn.functional.pad(t, (0, (-int(t.numel())) % 16))   # crop offsets must stay 16-byte aligned
+    dev8 = _t.cat([pad16(b[0]) for b in big])
+    sizes = [int(pad16(b[0]).numel()) for b in big]
+    hw8 = _t.cat([b[1] for b in big])
+    off8 = _t.cat([b[2] + sum(sizes[:i]) for i, b in enumerate(big)])
+    L8 = 8 * C1_LINES
+
+    def step_big():
+        lines, _ = eng.ocr_prepare_lines(dev8, hw8, off8, L8, 80, 2000, False)
+        return eng.ctc_greedy(eng.ocr_forward(ocr.ocr_session, lines), blank=blank)
+
+    for _ in range(2):
+        step_big()
+    torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(5):
+        ids8, lens8 = step_big()
+    b1.record()
+    torch.cuda.synchronize()
+    ms_big = b0.elapsed_time(b1) / 5
+    ids1, lens1 = step_device()
+    valid = _t.arange(ids1.shape[1], device=ids1.device)[None, :] < lens1[:, None]     # ids beyond lens are unwritten
+    same_big = bool(_t.equal(lens8[:C1_LINES], lens1) and _t.equal(ids8[:C1_LINES][valid], ids1[valid]))
     for _ in range(2):
         texts = ocr.run_batch(crops, pre_pad=False)
     t0 = time.perf_counter()
@@ -280,6 +307,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
         "workload": f"C1: {C1_LINES} ragged glyph-line crops -> resize/pad/binarise -> Easter2 (CTC-trained on synthetic "
                     "glyphs) -> greedy CTC -> text",
         "lines_per_sec": C1_LINES / (ms / 1e3), "ms_per_step": ms, "launches_per_step": int(launches),
+        "lines_per_sec_batch_of_512": L8 / (ms_big / 1e3), "batch_of_512_equals_batch_of_64": same_big,
         "e2e_lines_per_sec": C1_LINES / (e2e_ms / 1e3), "e2e_ms_per_step": e2e_ms,
         "e2e_api": "OCRInference.run_batch(host crops) -> list[str]",
         "h2d_bytes_per_step": int(sum(c.nbytes for c in crops)),

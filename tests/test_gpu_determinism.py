@@ -63,3 +63,21 @@ def test_depthwise_ring_kernel_in_isolation(engine, shape):
     assert float((first.float() - ref.float()).abs().max()) <= 0.02 * float(ref.float().abs().max())
     for _ in range(10):
         assert torch.equal(run(), first)
+
+
+def test_batching_is_exact(engine):
+    """Tiles of different pages and lines of different pages share batches (SURVEY 8a note: every reduction is per
+    batch element).  The results of an element must not depend on what else is in the batch, bit for bit --
+    whatever tile shape, accumulator interleave or CTA pairing the batch size selects."""
+    seg = engine.load_model(1, nets.seg_weights(11, 1, 3), 1)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = (torch.rand((10, 512, 512), device="cuda", generator=g) > 0.2).to(torch.uint8)
+    full = engine.seg_forward(seg, x, lowres=True).clone()
+    for n in (1, 3, 4):
+        assert torch.equal(engine.seg_forward(seg, x[:n], lowres=True), full[:n]), n
+    ocr = engine.load_model(2, nets.easter2_weights(7, 77, 80), 77)
+    xl = torch.sign(torch.randn((70, 2000, 128), device="cuda", generator=g)).to(torch.bfloat16)
+    xl[:, :, 80:] = 0
+    big = engine.ocr_forward(ocr, xl).clone()
+    for n in (1, 6, 64):
+        assert torch.equal(engine.ocr_forward(ocr, xl[:n]), big[:n]), n
