@@ -108,3 +108,26 @@ def test_page_sharding_world_size_2_gloo():
         assert p.exitcode == 0
     assert [r[0] for r in res] == [i * 10 for i in range(11)]
     assert [r[1] for r in res] == [0] * 5 + [1] * 6
+
+
+def test_pipeline_pool_plumbing_without_gpu():
+    """PipelinePool: pages through shared memory to worker processes, results back in input order, FAILED
+    tuples and masks-on-request preserved (a stand-in pipeline: the real one needs a B200)."""
+    import numpy as np
+
+    from ocr_inference_b200.data import OpStatus
+    from ocr_inference_b200.pool import PipelinePool, _echo_factory
+
+    pages = [np.full((4 + i, 6, 3), i, np.uint8) for i in range(7)] + [np.zeros((1, 5, 3), np.uint8)]
+    with PipelinePool(devices=(0, 1), procs_per_device=2, factory=_echo_factory, start_timeout=120) as pool:
+        assert len(pool) == 4
+        out = pool.run_ocr_many(pages, k_factor=2.0)
+        out2 = pool.run_ocr_many(pages[:2])
+    assert [o[0] for o in out] == [OpStatus.SUCCESS] * 7 + [OpStatus.FAILED]
+    assert out[-1][1] == "No lines detected"
+    for i, (st, payload) in enumerate(out[:7]):
+        assert payload[0] is None and payload[2] == [f"sum={int(pages[i].sum())} k=2.0"] and payload[3] in (0.0, 1.0)
+    assert out2[1][1][2] == [f"sum={int(pages[1].sum())} k=None"]
+    with PipelinePool(devices=(0,), procs_per_device=1, factory=_echo_factory, return_masks=True, start_timeout=120) as pool:
+        st, payload = pool.run_ocr_many(pages[3:4])[0]
+        assert np.array_equal(payload[0], pages[3][..., 0])

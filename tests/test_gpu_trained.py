@@ -111,3 +111,30 @@ def test_pipeline_page_to_text_trained_recogniser(engine, monkeypatch):
         assert st == OpStatus.SUCCESS
         assert [l.text for l in res[2]] == [l.text for l in ocr_lines] and res[3] == angle
     torch.cuda.synchronize()
+
+
+def test_pipeline_pool_matches_in_process_run(engine):
+    """PipelinePool (2 worker processes on the GPU, pages through shared memory) returns what run_ocr returns."""
+    from ocr_inference_b200.data import CharsetEncoder, LineDetectionConfig, OCRModelConfig, OpStatus
+    from ocr_inference_b200.inference import OCRPipeline
+    from ocr_inference_b200.pool import PipelinePool
+    from ocr_inference_b200.weights import write_blob
+
+    ocr_cfg = OCRModelConfig(write_blob(easter2_weights_fitted()), "Easter2", 2000, 80, "input", "output", True, False,
+                             CharsetEncoder.STACK, synth.CHARSET_76, True, "fitted")
+    line_cfg = LineDetectionConfig("", write_blob(seg_weights_fitted(11)), "deeplabv3plus-r34", 512, ["line"])
+    pages = [synth.text_page(90 + i, 1024, 1536, n_lines=(3, 3))[0] for i in range(3)]
+    pipe = OCRPipeline(ocr_cfg, line_cfg, None, engine=engine)
+    want = [pipe.run_ocr(p, k_factor=2.0, bbox_tolerance=2.5) for p in pages]
+    with PipelinePool(ocr_cfg, line_cfg, devices=(0,), procs_per_device=2) as pool:
+        got = pool.run_ocr_many(pages + pages, k_factor=2.0, bbox_tolerance=2.5)
+    assert len(got) == 6
+    for i, (st, payload) in enumerate(got):
+        wst, wpay = want[i % 3]
+        assert st == wst
+        if st == OpStatus.SUCCESS:
+            assert payload[0] is None
+            assert [l.text for l in payload[2]] == [l.text for l in wpay[2]]
+            assert [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h) for l in payload[1]] == \
+                [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h) for l in wpay[1]]
+            assert payload[3] == wpay[3]
