@@ -510,24 +510,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 // base offset = s the results are wrong), so a window that starts at any 128-byte row reads what TMA wrote.  All 9 weight tiles stay resident (72 KB).  A CTA owns a contiguous range
 // of "super rows" (4 output rows = 4 interleaved accumulators); consecutive super rows reuse 2 of their 6
 // input rows, slots are released tap-row by tap-row with tcgen05.commit so the ring (7 slots) never stalls.
-constexpr int SLAB_SLOTS = 7;
+// SLAB<1>: one CTA, 7 slots, whole weight tiles resident, consecutive super rows reuse 2 of their 6 rows.
+// SLAB<2>: CTA pair (cta_group::2, M = 256): CTA r of the pair owns output rows 8t + 4r .. + 3 of pair tile t,
+//          loads its own 6 input rows and HALF of every weight tile (36 KB), which frees room for 9 slots.
 constexpr uint32_t SLAB_ROW_BYTES = 17 * 1024;        // 130 px x 128 B = 16640, padded to 1024
 constexpr uint32_t SLAB_ROW_TX = 130 * 128;
-constexpr uint32_t SLAB_B_TAP_BYTES = 64 * 128;       // 8 KB per filter tap
-constexpr uint32_t SLAB_B_BYTES = 9 * SLAB_B_TAP_BYTES;
-constexpr size_t SLAB_SMEM = 1024 + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES + SLAB_B_BYTES + 1024 + 2 * OUT_STAGE_BYTES;
+template <int CTAS> struct SlabCfg {
+  static constexpr int SLOTS = CTAS == 2 ? 9 : 7;
+  static constexpr uint32_t B_TAP_BYTES = 64 / CTAS * 128;       // 8 KB (4 KB per CTA of a pair) per filter tap
+  static constexpr uint32_t B_BYTES = 9 * B_TAP_BYTES;
+  static constexpr size_t SMEM = 1024 + (size_t)SLOTS * SLAB_ROW_BYTES + B_BYTES + 1024 + 2 * OUT_STAGE_BYTES;
+};
 
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
+  using Cfg = SlabCfg<CTAS>;
+  constexpr int SLOTS = Cfg::SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* rows = smem;
-  uint8_t* bmat = rows + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES;
-  uint8_t* bar_base = bmat + SLAB_B_BYTES;
+  uint8_t* bmat = rows + (size_t)SLOTS * SLAB_ROW_BYTES;
+  uint8_t* bar_base = bmat + Cfg::B_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* empty_bar = full_bar + SLAB_SLOTS;
-  uint64_t* bfull_bar = empty_bar + SLAB_SLOTS;
+  uint64_t* empty_bar = full_bar + SLOTS;
+  uint64_t* bfull_bar = empty_bar + SLOTS;
   uint64_t* tfull_bar = bfull_bar + 1;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
@@ -535,56 +543,79 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_per_img = p.Hout / 4;
-  // contiguous range of super rows for this CTA
-  const int st_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
-  const int st_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int unit_id = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int rows_per_tile = 4 * CTAS;
+  const int tiles_per_img = p.Hout / rows_per_tile;
+  // contiguous range of (pair) super rows for this CTA (pair)
+  const int st_begin = (int)(((long long)p.total_tiles * unit_id) / n_units);
+  const int st_end = (int)(((long long)p.total_tiles * (unit_id + 1)) / n_units);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < SLAB_SLOTS; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
     mbar_init(smem_u32(bfull_bar), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 8);
+      mbar_init(smem_u32(&tempty_bar[i]), 8 * CTAS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    const uint32_t full0 = CTAS == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+    const uint32_t bfull = CTAS == 2 ? mapa_u32(smem_u32(bfull_bar), 0) : smem_u32(bfull_bar);
     if (elect_one()) {
-      mbar_arrive_expect_tx(smem_u32(bfull_bar), SLAB_B_BYTES);
-      for (int t = 0; t < 9; ++t)
-        tma_load_2d(smem_u32(bmat) + (uint32_t)t * SLAB_B_TAP_BYTES, &tmapB, smem_u32(bfull_bar), t * BK, 0);
+      if (cta_rank == 0) mbar_arrive_expect_tx(bfull, (uint32_t)CTAS * Cfg::B_BYTES);
+      for (int t = 0; t < 9; ++t) {
+        if (CTAS == 2)
+          tma_load_2d_2sm(smem_u32(bmat) + (uint32_t)t * Cfg::B_TAP_BYTES, &tmapB, bfull, t * BK, (int)cta_rank * 32);
+        else
+          tma_load_2d(smem_u32(bmat) + (uint32_t)t * Cfg::B_TAP_BYTES, &tmapB, bfull, t * BK, 0);
+      }
     }
     __syncwarp();
     uint32_t L = 0;   // row-load counter: load L goes to slot L % SLOTS, use (L / SLOTS)
     for (int st = st_begin; st < st_end; ++st) {
-      const int img = st / tiles_per_img, y0 = (st - img * tiles_per_img) * 4;
-      const bool carry = (st > st_begin) && (y0 != 0);    // rows y0-1, y0 are the previous super row's last two
+      const int img = st / tiles_per_img;
+      const int y0 = (st - img * tiles_per_img) * rows_per_tile + 4 * (int)cta_rank;
+      // single CTA: rows y0-1, y0 are the previous super row's last two (pairs skip 4 rows: nothing to reuse)
+      const bool carry = CTAS == 1 && (st > st_begin) && (y0 != 0);
       for (int q = carry ? 2 : 0; q < 6; ++q) {
-        const uint32_t slot = L % SLAB_SLOTS, use = L / SLAB_SLOTS;
+        const uint32_t slot = L % SLOTS, use = L / SLOTS;
         mbar_wait(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
         if (elect_one()) {
-          const uint32_t fb = smem_u32(&full_bar[slot]);
-          mbar_arrive_expect_tx(fb, SLAB_ROW_TX);
-          tma_load_4d(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
+          const uint32_t fb = full0 + slot * 8u;
+          if (CTAS == 2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2u * SLAB_ROW_TX);
+            tma_load_4d_2sm(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
+          } else {
+            mbar_arrive_expect_tx(fb, SLAB_ROW_TX);
+            tma_load_4d(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
+          }
         }
         __syncwarp();
         ++L;
@@ -592,65 +623,79 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
-    uint32_t base = 0, waited = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int st = st_begin; st < st_end; ++st) {
-      const int y0 = (st % tiles_per_img) * 4;
-      const bool next_carry = (st + 1 < st_end) && (y0 + 4 < p.Hout);
-      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 4 * 64);
-      for (int r = 0; r < 3; ++r) {
-        while (waited <= base + (uint32_t)r + 3u) {
-          mbar_wait(smem_u32(&full_bar[waited % SLAB_SLOTS]), (waited / SLAB_SLOTS) & 1, p.errflag, 3);
-          ++waited;
-        }
+    if (cta_rank == 0) {
+      mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
+      uint32_t base = 0, waited = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int st = st_begin; st < st_end; ++st) {
+        const int y0 = (st % tiles_per_img) * rows_per_tile;
+        const bool next_carry = CTAS == 1 && (st + 1 < st_end) && (y0 + 4 < p.Hout);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 4 * 64);
+        for (int r = 0; r < 3; ++r) {
+          while (waited <= base + (uint32_t)r + 3u) {
+            mbar_wait(smem_u32(&full_bar[waited % SLOTS]), (waited / SLOTS) & 1, p.errflag, 3);
+            ++waited;
+          }
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3 + s) * SLAB_B_TAP_BYTES);
+            for (int s = 0; s < 3; ++s) {
+              const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3 + s) * Cfg::B_TAP_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
+              for (int k = 0; k < BK / UMMA_K; ++k) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint32_t slot = (base + (uint32_t)(r + g)) % SLAB_SLOTS;
-                const uint32_t a_addr = smem_u32(rows) + slot * SLAB_ROW_BYTES + (uint32_t)s * 128u;
-                tc_mma_bf16(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
-                            bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
+                for (int g = 0; g < 4; ++g) {
+                  const uint32_t slot = (base + (uint32_t)(r + g)) % SLOTS;
+                  const uint32_t a_addr = smem_u32(rows) + slot * SLAB_ROW_BYTES + (uint32_t)s * 128u;
+                  if (CTAS == 2)
+                    tc_mma_bf16_2sm(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
+                                    bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
+                  else
+                    tc_mma_bf16(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
+                                bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
+                }
+              }
+            }
+            // release the rows whose last use was this tap row (in both CTAs of a pair)
+            auto release = [&](uint32_t ln) {
+              if (CTAS == 2) tc_commit_2sm(smem_u32(&empty_bar[ln % SLOTS])); else tc_commit(smem_u32(&empty_bar[ln % SLOTS]));
+            };
+            if (r < 2) {
+              release(base + (uint32_t)r);
+            } else {
+              release(base + 2u);
+              release(base + 3u);
+              if (!next_carry) {
+                release(base + 4u);
+                release(base + 5u);
               }
             }
           }
-          // release the rows whose last use was this tap row
-          if (r < 2) {
-            tc_commit(smem_u32(&empty_bar[(base + (uint32_t)r) % SLAB_SLOTS]));
-          } else {
-            tc_commit(smem_u32(&empty_bar[(base + 2u) % SLAB_SLOTS]));
-            tc_commit(smem_u32(&empty_bar[(base + 3u) % SLAB_SLOTS]));
-            if (!next_carry) {
-              tc_commit(smem_u32(&empty_bar[(base + 4u) % SLAB_SLOTS]));
-              tc_commit(smem_u32(&empty_bar[(base + 5u) % SLAB_SLOTS]));
-            }
-          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          if (CTAS == 2) tc_commit_2sm(smem_u32(&tfull_bar[acc])); else tc_commit(smem_u32(&tfull_bar[acc]));
         }
         __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        base += next_carry ? 4u : 6u;
       }
-      if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      base += next_carry ? 4u : 6u;
     }
   } else if (warp >= 4) {
-    epilogue_loop<1, 1>(p, &tmapO, stage_out, tfull_bar, tempty_bar, tmem_base, 0u, st_begin, st_end, 1);
+    epilogue_loop<CTAS, 1>(p, &tmapO, stage_out, tfull_bar, tempty_bar, tmem_base, cta_rank, st_begin, st_end, 1);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -758,6 +803,12 @@ bool slab_eligible(const ConvWeights& w, const ConvArgs& a) {
 int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  // The pair variant (BDRC_TC_SLAB=2) is correct but measured SLOWER than the single-CTA one (608 against 674
+  // TFLOP/s at 148 tiles): at N = 64 the operand path is bound by the 4 KB of A per MMA, which pairing does not
+  // reduce, and the pair adds a coupled accumulator hand-off.  Default: single CTA.
+  int ctas = 1;
+  if (const char* e = getenv("BDRC_TC_SLAB"))
+    if (atoi(e) == 2 && a.Hout % 8 == 0) ctas = 2;
   CUtensorMap mapA, mapB, mapO;
   {
     const cuuint64_t ld = (cuuint64_t)a.in_ld;
@@ -774,7 +825,7 @@ int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, 
     const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
     cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
     cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, 64};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(64 / ctas)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -794,13 +845,13 @@ int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, 
   }
   TcParams p;
   p.tiles_n = 1; p.tiles_w = 1; p.tiles_h = a.Hout; p.n_img = a.N;
-  p.total_tiles = a.N * (a.Hout / 4);
+  p.total_tiles = a.N * (a.Hout / (4 * ctas));
   p.BW = 128; p.BH = 1; p.BN = 64; p.stages = 0; p.G = 4;
   p.R = 3; p.S = 3; p.kchunks = 1;
   p.stride_h = p.stride_w = 1; p.pad_h = p.pad_w = 1; p.dil_h = p.dil_w = 1;
   p.par_c = a.in_ld;
   p.Hout = a.Hout; p.Wout = a.Wout; p.Cout = w.Cout;
-  p.idesc = make_idesc_bf16(BM, 64);
+  p.idesc = make_idesc_bf16(BM * ctas, 64);
   p.tmem_cols = 512;
   p.bias = a.bias_override ? a.bias_override : w.b;
   p.bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
@@ -813,11 +864,32 @@ int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, 
   p.head_w = nullptr; p.head_b = nullptr; p.head_out = nullptr; p.head_C = 0; p.head_ld = 0;
   static bool attr_set = false;
   if (!attr_set) {
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM));
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)SlabCfg<1>::SMEM));
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)SlabCfg<2>::SMEM));
     attr_set = true;
   }
-  const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-  conv_tc_slab_kernel<<<grid, NUM_THREADS, SLAB_SMEM, s>>>(mapA, mapB, mapO, p);
+  if (ctas == 2) {
+    const int pairs = ctx->sm_count / 2;
+    const int units = p.total_tiles < pairs ? p.total_tiles : pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SlabCfg<2>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<2>, mapA, mapB, mapO, p));
+  } else {
+    const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+    conv_tc_slab_kernel<1><<<grid, NUM_THREADS, SlabCfg<1>::SMEM, s>>>(mapA, mapB, mapO, p);
+  }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
