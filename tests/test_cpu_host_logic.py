@@ -131,3 +131,30 @@ def test_pipeline_pool_plumbing_without_gpu():
     with PipelinePool(devices=(0,), procs_per_device=1, factory=_echo_factory, return_masks=True, start_timeout=120) as pool:
         st, payload = pool.run_ocr_many(pages[3:4])[0]
         assert np.array_equal(payload[0], pages[3][..., 0])
+
+
+def test_model_config_readers_match_reference_layout(tmp_path):
+    """read_*_model_config: the reference's model_config.json keys -> the config dataclasses (utils.py:162-207,
+    349-393); a .bdrcw container next to the named .onnx is preferred."""
+    import json
+
+    from ocr_inference_b200 import utils
+    from ocr_inference_b200.data import CharsetEncoder
+
+    d = tmp_path / "Woodblock"
+    d.mkdir()
+    (d / "model_config.json").write_text(json.dumps({
+        "onnx-model": "OCRModel.onnx", "architecture": "Easter2", "version": "1.0", "input_width": 2000,
+        "input_height": 80, "input_layer": "input", "output_layer": "output", "encoder": "stack",
+        "squeeze_channel_dim": "yes", "swap_hw": "no", "charset": "abc§", "add_blank": "yes"}), encoding="utf-8")
+    cfg = utils.read_ocr_model_config(str(d / "model_config.json"))
+    assert cfg.model_file == f"{d}/OCRModel.onnx" and cfg.squeeze_channel and not cfg.swap_hw and cfg.add_blank
+    assert cfg.encoder == CharsetEncoder.STACK and utils.get_charset(cfg.charset) == ["a", "b", "c", "§"]
+    (d / "OCRModel.bdrcw").write_bytes(b"x")
+    assert utils.read_ocr_model_config(str(d / "model_config.json")).model_file == f"{d}/OCRModel.bdrcw"
+    (d / "line.json").write_text(json.dumps({"checkpoint": "c.pth", "onnx-model": "lines.onnx", "architecture": "deeplabv3",
+                                              "patch_size": "512", "classes": ["line"]}))
+    lc = utils.read_line_model_config(str(d / "line.json"))
+    assert (lc.onnx_file, lc.patch_size, lc.classes) == (f"{d}/lines.onnx", 512, ["line"])
+    lay = utils.read_layout_model_config(str(d / "line.json"))
+    assert lay.architecture == f"{d}/deeplabv3" and lay.patch_size == 512
