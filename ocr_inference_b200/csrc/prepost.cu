@@ -239,6 +239,32 @@ __global__ void seg_post_kernel(const PostParams p) {
   for (int c = 0; c < p.C; ++c) o[c] = ((m >> c) & 1) ? 255 : 0;
 }
 
+// fast path of the common case (line model, low-res fp32 logits [nt][P/4][P/4], no page resize): 16 consecutive
+// mask bytes per thread and one 16-byte store (the generic kernel writes single bytes).  Same arithmetic, in the
+// same expression, as logit_at(): the decisions are identical.
+__global__ void seg_post_line_lowres_kernel(const PostParams p) {
+  const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int y = blockIdx.y;
+  if (x16 >= p.W0) return;
+  uint32_t bits = 0;
+  const int n = min(16, p.W0 - x16);
+  for (int j = 0; j < n; ++j) bits |= (logit_at(p, y, x16 + j, 0) >= p.thr_logit ? 1u : 0u) << j;
+  uint8_t* o = p.mask + (size_t)y * p.W0 + x16;
+  if (n == 16 && (p.W0 & 15) == 0) {
+    uint4 v;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t b = (bits >> (4 * q)) & 15u;
+      w[q] = ((b & 1u) ? 0x000000FFu : 0u) | ((b & 2u) ? 0x0000FF00u : 0u) | ((b & 4u) ? 0x00FF0000u : 0u) |
+             ((b & 8u) ? 0xFF000000u : 0u);
+    }
+    *reinterpret_cast<uint4*>(o) = v;
+  } else {
+    for (int j = 0; j < n; ++j) o[j] = ((bits >> j) & 1u) ? 255 : 0;
+  }
+}
+
 // fast path: sigmoid, one class, full-res logits, no resize: 4 pixels per thread
 __global__ void seg_post_line_fast_kernel(const float* __restrict__ logits, int ntx, int P, int H0,
                                           int W0, float thr_logit, uint8_t* __restrict__ mask) {
@@ -493,6 +519,9 @@ static int seg_post_common(bdrc_ctx* ctx, const float* logits, int nty, int ntx,
   if (torch_path) {
     dim3 grid(ceil_div(W0, 128), H0);
     seg_post_torch_kernel<<<grid, 128, 0, s>>>(p);
+  } else if (mode == BDRC_POST_SIGMOID && C == 1 && lowres && Hc == H0 && Wc == W0 && patch % 16 == 0) {
+    dim3 grid(ceil_div(ceil_div(W0, 16), 128), H0);
+    seg_post_line_lowres_kernel<<<grid, 128, 0, s>>>(p);
   } else if (mode == BDRC_POST_SIGMOID && C == 1 && !lowres && Hc == H0 && Wc == W0 &&
              patch % 4 == 0) {
     dim3 grid(ceil_div(ceil_div(W0, 4), 128), H0);
