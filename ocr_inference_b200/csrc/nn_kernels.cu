@@ -216,18 +216,20 @@ depthwise_kernel(const bf16* __restrict__ in, int in_ld, int in_coff, int N, int
 // Depthwise 3x3, dilation 1, TMA-fed row ring.  A CTA owns (image, 64-channel chunk, DWR_PX-pixel column
 // band, segment of DWR_ROWS output rows).  Input rows ((DWR_PX + 2) px x 64 ch, halo and channel tail
 // zero-filled by TMA out-of-bounds handling) stream through an 8-slot shared-memory ring, each loaded
-// exactly once; thread (px, 8-channel group) reads its 3 neighbours of the arriving row and feeds the
-// three output rows that row contributes to, so an output costs 3 LDS.128 + 72 FMA and the 72 weights
-// stay in registers.  Summation order per output is (r, s) row-major as in the direct kernel.
-constexpr int DWR_PX = 32, DWR_SLOTS = 8, DWR_ROWS = 32, DWR_THREADS = DWR_PX * 8;
+// exactly once; a thread reads the neighbours of its pixels in the arriving row and feeds the three output
+// rows that row contributes to (no vertical re-reads).  Summation order per output is (r, s) row-major.
+constexpr int DWR_PX = 32, DWR_SLOTS = 8, DWR_ROWS = 32;
 constexpr int DWR_SLOT_BYTES = (DWR_PX + 2) * 128;
 
-__global__ void __launch_bounds__(DWR_THREADS)
+// Thread mapping: lane = channel PAIR (32 lanes x 2 = the 64 channels of the chunk), warp = 4 consecutive pixels:
+// 18 register-resident weights per thread (a (pixel, 8 channels) mapping needs 72 and fits only 2 CTAs per SM),
+// conflict-free 128-byte shared-memory rows, neighbouring pixels of a thread share their loads (6 LDS per 4
+// outputs), a warp's store is one full 128-byte line.  ncu: the kernel is instruction-issue bound (69 % of the
+// issue slots), not bandwidth bound; packed fma.rn.f32x2 made it slower.
+__global__ void __launch_bounds__(256)
 depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, int W, int C,
-                      const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff, int* errflag) {
+                       const float* __restrict__ w9c, bf16* __restrict__ out, int out_ld, int out_coff, int* errflag) {
   extern __shared__ __align__(128) uint8_t dwr_smem_raw[];
-  // 128-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t makes the
-  // compiler forget the address space and emit generic LD instead of LDS)
   uint8_t* ring = dwr_smem_raw + ((128u - (tcptx::smem_u32(dwr_smem_raw) & 127u)) & 127u);
   __shared__ __align__(8) uint64_t full_bar[DWR_SLOTS];
   const int xt_n = W / DWR_PX, chunks = (C + 63) / 64, segs = (H + DWR_ROWS - 1) / DWR_ROWS;
@@ -240,8 +242,8 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
   const int ya = seg * DWR_ROWS, yb = min(H, ya + DWR_ROWS);
   const int rows_in = yb - ya + 2;             // input rows ya-1 .. yb
   const int tid = threadIdx.x;
-  const int c8 = tid & 7, px = tid >> 3;
-  const bool cvalid = c0 + c8 * 8 < C;
+  const int lane = tid & 31, pb = (tid >> 5) * 4;
+  const bool cvalid = c0 + 2 * lane < C;
 
   if (tid == 0) {
     for (int i = 0; i < DWR_SLOTS; ++i) tcptx::mbar_init(tcptx::smem_u32(&full_bar[i]), 1);
@@ -258,29 +260,22 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
   if (tid == 0)
     for (int k = 0; k < DWR_SLOTS && k < rows_in; ++k) issue(k);
 
-  float w[9][8];
+  float2 w[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-    if (cvalid) {
-      w0 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c0 + c8 * 8));
-      w1 = __ldg(reinterpret_cast<const float4*>(w9c + k * C + c0 + c8 * 8 + 4));
-    }
-    w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
-    w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
-  }
-  float a_prev[8], a_cur[8], a_next[8];
+  for (int k = 0; k < 9; ++k)
+    w[k] = cvalid ? __ldg(reinterpret_cast<const float2*>(w9c + k * C + c0 + 2 * lane)) : make_float2(0.f, 0.f);
+  float2 a_prev[4], a_cur[4], a_next[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a_prev[j] = a_cur[j] = a_next[j] = 0.f;
-  bf16* obase = out + ((size_t)n * H * W + x0 + px) * out_ld + out_coff + c0 + c8 * 8;
+  for (int q = 0; q < 4; ++q) a_prev[q] = a_cur[q] = a_next[q] = make_float2(0.f, 0.f);
+  bf16* obase = out + ((size_t)n * H * W + x0 + pb) * out_ld + out_coff + c0 + 2 * lane;
 
   for (int k = 0; k < rows_in; ++k) {
     const int i = ya - 1 + k;                  // input row
     tcptx::mbar_wait(tcptx::smem_u32(&full_bar[k % DWR_SLOTS]), (uint32_t)((k / DWR_SLOTS) & 1), errflag, 9);
-    const uint8_t* row = ring + (size_t)(k % DWR_SLOTS) * DWR_SLOT_BYTES + px * 128 + c8 * 16;
-    uint4 v[3];
+    const uint8_t* row = ring + (size_t)(k % DWR_SLOTS) * DWR_SLOT_BYTES + pb * 128 + lane * 4;
+    uint32_t v[6];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) v[s] = *reinterpret_cast<const uint4*>(row + s * 128);
+    for (int j = 0; j < 6; ++j) v[j] = *reinterpret_cast<const uint32_t*>(row + j * 128);
     // The slot is refilled by TMA (async proxy) right after the barrier.  Arriving at a barrier does not wait
     // for this thread's outstanding shared-memory LOADS (the scoreboard only stalls an instruction that reads
     // their destination registers) and an async-proxy write is not ordered behind them, so a refill could
@@ -291,20 +286,27 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap, int N, int H, in
     __threadfence_block();
     __syncthreads();
     if (tid == 0 && k + DWR_SLOTS < rows_in) issue(k + DWR_SLOTS);
+    float2 f[6];   // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      float f[8];
-      unpack8(v[s], f);
+    for (int j = 0; j < 6; ++j) f[j] = make_float2(__uint_as_float(v[j] << 16), __uint_as_float(v[j] & 0xFFFF0000u));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a_next[j] = fmaf(f[j], w[s][j], a_next[j]);          // this row is the r = 0 row of output i + 1
-        a_cur[j] = fmaf(f[j], w[3 + s][j], a_cur[j]);        //             the r = 1 row of output i
-        a_prev[j] = fmaf(f[j], w[6 + s][j], a_prev[j]);      //             the r = 2 row of output i - 1
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        // (packed fma.rn.f32x2 / FFMA2 was tried here: 0.93 ms against 0.85 ms per 148 tiles with scalar FFMA)
+        a_next[q].x = fmaf(f[q + s].x, w[s].x, a_next[q].x);          // r = 0 row of output i + 1
+        a_next[q].y = fmaf(f[q + s].y, w[s].y, a_next[q].y);
+        a_cur[q].x = fmaf(f[q + s].x, w[3 + s].x, a_cur[q].x);        // r = 1 row of output i
+        a_cur[q].y = fmaf(f[q + s].y, w[3 + s].y, a_cur[q].y);
+        a_prev[q].x = fmaf(f[q + s].x, w[6 + s].x, a_prev[q].x);      // r = 2 row of output i - 1
+        a_prev[q].y = fmaf(f[q + s].y, w[6 + s].y, a_prev[q].y);
       }
+      if (i - 1 >= ya && cvalid) {
+        const __nv_bfloat162 o = __floats2bfloat162_rn(a_prev[q].x, a_prev[q].y);
+        *reinterpret_cast<__nv_bfloat162*>(obase + ((size_t)(i - 1) * W + q) * out_ld) = o;
+      }
+      a_prev[q] = a_cur[q]; a_cur[q] = a_next[q]; a_next[q] = make_float2(0.f, 0.f);
     }
-    if (i - 1 >= ya && cvalid) *reinterpret_cast<uint4*>(obase + (size_t)(i - 1) * W * out_ld) = pack8(a_prev);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { a_prev[j] = a_cur[j]; a_cur[j] = a_next[j]; a_next[j] = 0.f; }
   }
 }
 
@@ -685,7 +687,7 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "depthwise: cuTensorMapEncodeTiled failed: %d", (int)r);
     const int items = N * ((C + 63) / 64) * ((H + DWR_ROWS - 1) / DWR_ROWS) * (W / DWR_PX);
-    depthwise_ring_kernel<<<items, DWR_THREADS, DWR_SLOTS * DWR_SLOT_BYTES + 128, s>>>(map, N, H, W, C, w9c, out, out_ld,
+    depthwise_ring_kernel<<<items, 256, DWR_SLOTS * DWR_SLOT_BYTES + 128, s>>>(map, N, H, W, C, w9c, out, out_ld,
                                                                               out_coff, ctx->d_errflag);
     BDRC_CHECK_LAUNCH(ctx);
     return 0;
