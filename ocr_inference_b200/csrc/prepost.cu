@@ -16,6 +16,23 @@ struct LinCoef {
   float w0, w1;
 };
 
+// `scale` = 1.0 / ((double)dsize / (double)ssize), hoisted by callers that evaluate many pixels of one resize
+__device__ __forceinline__ LinCoef lin_coef_scaled(int d, int ssize, double scale, bool vertical) {
+  float fx = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+  int sx = (int)floorf(fx);
+  fx = fx - (float)sx;
+  if (!vertical) {
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= ssize - 1) { fx = 0.f; sx = ssize - 1; }
+  }
+  LinCoef c;
+  c.i0 = min(max(sx, 0), ssize - 1);
+  c.i1 = min(max(sx + 1, 0), ssize - 1);
+  c.w0 = 1.0f - fx;
+  c.w1 = fx;
+  return c;
+}
+
 __device__ __forceinline__ LinCoef lin_coef(int d, int ssize, int dsize, bool vertical) {
   const double scale = 1.0 / ((double)dsize / (double)ssize);
   float fx = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
@@ -341,19 +358,39 @@ float sigmoid_logit_threshold(float thr) {
 __global__ void ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__ hw,
                                   const int64_t* __restrict__ off, int Ht, int Wt, int pre_pad,
                                   uint8_t* __restrict__ canvas, int* __restrict__ status) {
+  // per (line, canvas row) constants -- the double-precision geometry of _pad_ocr_line and the vertical resize
+  // coefficients -- are computed once per block (fp64 divisions per pixel dominated the first version)
+  __shared__ int g_i[6];          // rh, rw, top, left, cy.i0, cy.i1
+  __shared__ float g_f[2];        // cy.w0, cy.w1
+  __shared__ double g_scale_x;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int l = blockIdx.z;
-  if (x >= Wt) return;
   const int h = hw[2 * l], w0 = hw[2 * l + 1];
   const int w = pre_pad ? w0 + 2 * h : w0;     // _pre_pad hstacks an h x h white patch each side
+  if (threadIdx.x == 0) {
+    int rh = 0, rw = 0, top = 0, left = 0;
+    LinCoef cy = {0, 0, 1.f, 0.f};
+    double scale_x = 1.0;
+    if (h > 0 && w0 > 0) {
+      // geometry of _pad_ocr_line / pad_to_width / pad_to_height in Python float (double) math
+      const double wr = (double)Wt / (double)w, hr = (double)Ht / (double)h;
+      if (wr <= hr) { rw = Wt; rh = (int)((double)h * wr); top = (Ht - rh) / 2; left = 0; }
+      else { rh = Ht; rw = (int)((double)w * hr); top = 0; left = (Wt - rw) / 2; }
+      if (rh > 0 && rw > 0) {
+        scale_x = 1.0 / ((double)rw / (double)w);
+        if (y >= top && y < top + rh) cy = lin_coef(y - top, h, rh, true);
+      }
+    }
+    g_i[0] = rh; g_i[1] = rw; g_i[2] = top; g_i[3] = left; g_i[4] = cy.i0; g_i[5] = cy.i1;
+    g_f[0] = cy.w0; g_f[1] = cy.w1;
+    g_scale_x = scale_x;
+  }
+  __syncthreads();
+  if (x >= Wt) return;
   uint8_t g = 0;
   if (h > 0 && w0 > 0) {
-    // geometry of _pad_ocr_line / pad_to_width / pad_to_height in Python float (double) math
-    const double wr = (double)Wt / (double)w, hr = (double)Ht / (double)h;
-    int rh, rw, top, left;
-    if (wr <= hr) { rw = Wt; rh = (int)((double)h * wr); top = (Ht - rh) / 2; left = 0; }
-    else { rh = Ht; rw = (int)((double)w * hr); top = 0; left = (Wt - rw) / 2; }
+    const int rh = g_i[0], rw = g_i[1], top = g_i[2], left = g_i[3];
     if (rh <= 0 || rw <= 0) {
       if (x == 0 && y == 0) status[l] = 1;   // cv2.resize would raise on an empty target
     } else if (y >= top && y < top + rh && x >= left && x < left + rw) {
@@ -373,7 +410,8 @@ __global__ void ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32
         fetch(2 * dy + 1, 2 * dx, c); fetch(2 * dy + 1, 2 * dx + 1, d);
         for (int k = 0; k < 3; ++k) px[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
       } else {
-        const LinCoef cx = lin_coef(dx, w, rw, false), cy = lin_coef(dy, h, rh, true);
+        const LinCoef cx = lin_coef_scaled(dx, w, g_scale_x, false);
+        const LinCoef cy = {g_i[4], g_i[5], g_f[0], g_f[1]};
         const int a0 = fix11(cx.w0), a1 = fix11(cx.w1), b0 = fix11(cy.w0), b1 = fix11(cy.w1);
         int s00[3], s01[3], s10[3], s11[3];
         fetch(cy.i0, cx.i0, s00); fetch(cy.i0, cx.i1, s01);
