@@ -292,6 +292,13 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     b1.record()
     torch.cuda.synchronize()
     ms_big = b0.elapsed_time(b1) / 5
+    eng.profile(True)
+    for _ in range(3):
+        step_big()
+    torch.cuda.synchronize()
+    prof_big = [(n_, t_, f_) for (n_, t_, f_) in eng.profile_results() if f_ > 0]
+    eng.profile(False)
+    big_tf = sum(x[2] for x in prof_big) / (sum(x[1] for x in prof_big) / 1e3) / 1e12 if prof_big else 0.0
     ids1, lens1 = step_device()
     valid = _t.arange(ids1.shape[1], device=ids1.device)[None, :] < lens1[:, None]     # ids beyond lens are unwritten
     same_big = bool(_t.equal(lens8[:C1_LINES], lens1) and _t.equal(ids8[:C1_LINES][valid], ids1[valid]))
@@ -316,6 +323,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
                      "achieved": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (tc_fl / (tc_ms / 1e3) / 1e12) / peak_tf if tc_ms else 0.0, "peak_source": peak_src,
                      "share_of_step": tc_ms / steps / ms if ms else None},
+        "roofline_batch_of_512": {"achieved": big_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": big_tf / peak_tf},
         "lines_equal_to_truth": sum(a == b for a, b in zip(texts, want)) / C1_LINES,
         "ms_by_kernel": {k: round(v, 4) for k, v in sorted(by.items(), key=lambda kv: -kv[1])},
     }
