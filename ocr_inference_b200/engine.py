@@ -345,8 +345,12 @@ class Engine:
         return dev, torch.from_numpy(hw).to(self.device), torch.from_numpy(off).to(self.device)
 
     def ocr_prepare_lines(self, crops_dev, hw_dev, off_dev, L: int, Ht: int, Wt: int, pre_pad: bool,
-                          want_f32: bool = False):
-        lines = torch.empty((L, Wt, OCR_CPAD), dtype=torch.bfloat16, device=self.device)
+                          want_f32: bool = False, out: torch.Tensor | None = None):
+        """`out` (optional): a contiguous bf16 [L, Wt, OCR_CPAD] slice of a larger line batch to fill."""
+        if out is not None and (tuple(out.shape) != (L, Wt, OCR_CPAD) or out.dtype != torch.bfloat16
+                                or not out.is_contiguous()):
+            raise ValueError("ocr_prepare_lines: out must be a contiguous bf16 [L, Wt, OCR_CPAD] tensor")
+        lines = out if out is not None else torch.empty((L, Wt, OCR_CPAD), dtype=torch.bfloat16, device=self.device)
         f32 = torch.empty((L, Ht, Wt), dtype=torch.float32, device=self.device) if want_f32 else None
         ws = self._workspace("ocr_prep", int(self.lib.bdrc_ocr_prepare_workspace_bytes(L, Ht, Wt)))
         self._check(self.lib.bdrc_ocr_prepare_lines(

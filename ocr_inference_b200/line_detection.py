@@ -31,6 +31,70 @@ def get_contours(image: np.ndarray):
     return found
 
 
+class RowCompaction:
+    """The rows of a mask that hold any foreground, each run of them followed by one empty separator row.
+
+    cv2.findContours scans every pixel, and on a text page most rows are empty.  Border following only looks at
+    8-neighbours, runs of occupied rows stay separated by an empty row, and dropping empty rows keeps the raster
+    order of the start points, so the contours of the compacted mask are the contours of the page -- same
+    points, same list order -- once their y coordinates go back through `ymap`
+    (tests/test_cpu_host_logic.py checks this against cv2 on the full mask).  `small` is None when compaction
+    would not pay (most rows occupied)."""
+
+    def __init__(self, mask: np.ndarray, worth: float = 0.6):
+        self.small = self.ymap = None
+        H = int(mask.shape[0])
+        occ = mask.max(axis=1) != 0
+        n_occ = int(np.count_nonzero(occ))
+        self.empty = n_occ == 0
+        if self.empty or H < 64:
+            return
+        d = np.diff(occ.astype(np.int8))
+        starts = list(np.flatnonzero(d == 1) + 1)
+        ends = list(np.flatnonzero(d == -1) + 1)
+        if occ[0]:
+            starts.insert(0, 0)
+        if occ[-1]:
+            ends.append(H)
+        self.y0, self.y1 = int(starts[0]), int(ends[-1])          # first occupied row, one past the last
+        if n_occ + len(starts) > worth * H:
+            return
+        small = np.zeros((n_occ + len(starts), mask.shape[1]), mask.dtype)
+        ymap = np.zeros(small.shape[0], np.int32)
+        o = 0
+        for a, b in zip(starts, ends):
+            small[o:o + b - a] = mask[a:b]
+            ymap[o:o + b - a] = np.arange(a, b, dtype=np.int32)
+            ymap[o + b - a] = b                                    # separator row (never on a contour)
+            o += b - a + 1
+        self.small, self.ymap = small, ymap
+
+    def contours(self):
+        found, _ = cv2.findContours(self.small, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        if len(found) < 8:
+            for c in found:
+                c[:, 0, 1] = self.ymap[c[:, 0, 1]]
+            return found
+        # many small contours: one gather over all points, then views of it (no per-contour numpy round trip)
+        pts = np.concatenate(found, axis=0)
+        pts[:, 0, 1] = self.ymap[pts[:, 0, 1]]
+        out, o = [], 0
+        for c in found:
+            out.append(pts[o:o + len(c)])
+            o += len(c)
+        return tuple(out)
+
+
+def get_contours_compact(mask: np.ndarray, rows: "RowCompaction | None" = None):
+    """get_contours(mask) through the row compaction (identical result, a fraction of the pixels scanned)."""
+    if mask.ndim != 2 or mask.dtype != np.uint8:
+        return get_contours(mask)
+    rows = rows or RowCompaction(mask)
+    if rows.empty:
+        return ()
+    return rows.contours() if rows.small is not None else get_contours(mask)
+
+
 def optimize_countour(cnt, e: float = 0.001):
     return cv2.approxPolyDP(cnt, e * cv2.arcLength(cnt, True), True)
 
@@ -56,11 +120,13 @@ def rotate_from_angle(image: np.ndarray, angle: float) -> np.ndarray:
 
 
 def get_rotation_angle_from_lines(line_mask: np.ndarray, max_angle: float = 5.0, debug_angles: bool = False,
-                                  _contours=None) -> float:
+                                  _contours=None, _areas=None) -> float:
     """Mean minAreaRect angle of the big blobs (> 0.1 % of the page), :107-142.  `_contours` (internal):
     the result of get_contours(line_mask) when the caller already has it."""
     found = get_contours(line_mask) if _contours is None else _contours
-    blobs = [c for c in found if cv2.contourArea(c) > line_mask.shape[0] * line_mask.shape[1] * 0.001]
+    areas = [cv2.contourArea(c) for c in found] if _areas is None else _areas
+    big = line_mask.shape[0] * line_mask.shape[1] * 0.001
+    blobs = [c for c, a in zip(found, areas) if a > big]
     angles = [cv2.minAreaRect(c)[2] for c in blobs]
     low = [a for a in angles if abs(a) != 0.0 and a < max_angle]
     high = [a for a in angles if abs(a) != 90.0 and a > (90 - max_angle)]
@@ -73,21 +139,40 @@ def get_rotation_angle_from_lines(line_mask: np.ndarray, max_angle: float = 5.0,
     return 0
 
 
+class Mask3(np.ndarray):
+    """The (H, W, 3) mask build_raw_line_data returns (:235,241 GRAY2RGB), remembering the 1-channel mask it
+    replicates: get_line_threshold converts it straight back with BGR2GRAY (:375-376), which is the identity on
+    replicated channels (tests/test_cpu_host_logic.py), so the 19 MB conversion is skipped.  Views and copies do
+    not inherit the link."""
+
+    gray = None
+    rows = None          # RowCompaction of `gray`
+
+    def __array_finalize__(self, obj):
+        self.gray = self.rows = None
+
+
 def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold: float = 0.5):
     """:212-244 -> (rotated image, rotated 3-channel mask, contours with area > 10, angle)."""
     if line_mask.ndim == 3:
         line_mask = cv2.cvtColor(line_mask, cv2.COLOR_BGR2GRAY)
-    found = get_contours(line_mask)
-    angle = get_rotation_angle_from_lines(line_mask, _contours=found)
+    rows = RowCompaction(line_mask) if line_mask.ndim == 2 and line_mask.dtype == np.uint8 else None
+    found = get_contours_compact(line_mask, rows)
+    areas = [cv2.contourArea(c) for c in found]
+    angle = get_rotation_angle_from_lines(line_mask, _contours=found, _areas=areas)
     if angle > rot_threshold:
         out_mask = rotate_from_angle(line_mask, angle)
         out_img = rotate_from_angle(image, angle)
-        found = get_contours(out_mask)
+        rows = RowCompaction(out_mask)
+        found = get_contours_compact(out_mask, rows)
+        areas = [cv2.contourArea(c) for c in found]
     else:
         # unrotated: the reference runs the identical findContours call a second time (:238); reuse it
         out_mask, out_img = line_mask, image
-    contours = [c for c in found if cv2.contourArea(c) > 10]
-    return out_img, cv2.cvtColor(out_mask, cv2.COLOR_GRAY2RGB), contours, angle
+    contours = [c for c, a in zip(found, areas) if a > 10]
+    mask3 = cv2.cvtColor(out_mask, cv2.COLOR_GRAY2RGB).view(Mask3)
+    mask3.gray, mask3.rows = out_mask, rows
+    return out_img, mask3, contours, angle
 
 
 def filter_line_contours(image: np.ndarray, line_contours, threshold: float = 0.01) -> list:
@@ -115,15 +200,29 @@ def build_line_data(contour: np.ndarray, optimize: bool = True) -> Line:
 
 def get_line_threshold(line_prediction: np.ndarray, slice_width: int = 20) -> float:
     """:362-421: census of contours in vertical slices; median centre-y of the fullest slice // n."""
-    if line_prediction.ndim == 3:
+    gray = getattr(line_prediction, "gray", None)
+    rows = None
+    if gray is not None and gray.shape == line_prediction.shape[:2]:
+        rows = getattr(line_prediction, "rows", None)
+        line_prediction = gray
+    elif line_prediction.ndim == 3:
         line_prediction = cv2.cvtColor(line_prediction, cv2.COLOR_BGR2GRAY)
-    x, y, w, h = cv2.boundingRect(line_prediction)
+    if rows is None and line_prediction.ndim == 2 and line_prediction.dtype == np.uint8:
+        rows = RowCompaction(line_prediction)
+    if rows is not None and rows.small is not None:
+        # the slices of the compacted mask hold the same contours (rows between y and y + h that are empty
+        # carry none); only the top edge of each bounding box has to go back through ymap
+        x, _, w, _ = cv2.boundingRect(rows.small)
+        y = rows.y0
+        src, ymap = rows.small, rows.ymap
+    else:
+        x, y, w, h = cv2.boundingRect(line_prediction)
+        src, ymap = line_prediction[y:y + h], None
     x_steps = (w // slice_width) // 2
     census = []
     for step in range(1, x_steps + 1):
         x0 = x + x_steps * step
-        found, _ = cv2.findContours(line_prediction[y:y + h, x0:x0 + slice_width], cv2.RETR_LIST,
-                                    cv2.CHAIN_APPROX_SIMPLE)
+        found, _ = cv2.findContours(src[:, x0:x0 + slice_width], cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
         census.append((len(found), found))
     if not census:
         return 0.0
@@ -134,6 +233,8 @@ def get_line_threshold(line_prediction: np.ndarray, slice_width: int = 20) -> fl
     centers = []
     for c in found:
         _, cy, _, ch = cv2.boundingRect(c)
+        if ymap is not None:
+            cy = int(ymap[cy]) - y
         centers.append(cy + (ch // 2))
     return float(np.median(centers) // n) if centers else 0.0
 
@@ -143,16 +244,16 @@ def sort_bbox_centers(bbox_centers: list[tuple[int, int]], line_threshold: float
     the row list is returned reversed."""
     if not bbox_centers:
         return []
-    rows, cur = [], []
+    rows, cur, ysum = [], [], 0
     for c in bbox_centers:
-        if cur:
-            if abs(np.mean([p[1] for p in cur]) - c[1]) > line_threshold:
-                cur.sort(key=lambda p: p[0])
-                rows.append(cur.copy())
-                cur.clear()
-            cur.append(c)
-        else:
-            cur.append(c)
+        # running integer sum: ysum / len(cur) is the same float64 as np.mean of the ys (exact sums below 2**53)
+        if cur and abs(ysum / len(cur) - c[1]) > line_threshold:
+            cur.sort(key=lambda p: p[0])
+            rows.append(cur.copy())
+            cur.clear()
+            ysum = 0
+        cur.append(c)
+        ysum += int(c[1])
     if cur:
         rows.append(cur)
     for r in rows:
@@ -163,23 +264,17 @@ def sort_bbox_centers(bbox_centers: list[tuple[int, int]], line_threshold: float
 def group_line_chunks(sorted_bbox_centers, lines: list[Line], adaptive_grouping: bool = True) -> list[Line]:
     """:489-548: rows with several chunks are merged into the convex hull of their contours."""
     out = []
+    first = {}
+    for ln in lines:              # the reference scans `lines` for the first one with this centre (:505-512)
+        first.setdefault(ln.center, ln)
     for centers in sorted_bbox_centers:
         if len(centers) > 1:
-            stack = []
-            for c in centers:
-                for ln in lines:
-                    if c == ln.center:
-                        stack.append(ln.contour)
-                        break
+            stack = [first[c].contour for c in centers if c in first]
             hull = cv2.convexHull(np.vstack(stack))
             x, y, w, h = cv2.boundingRect(hull)
             out.append(Line(generate_guid(clock_seq=23), hull, BBox(x, y, w, h), (x + (w // 2), y + (h // 2))))
         else:
-            for c in centers:
-                for ln in lines:
-                    if c == ln.center:
-                        out.append(ln)
-                        break
+            out.extend(first[c] for c in centers if c in first)
     return out
 
 

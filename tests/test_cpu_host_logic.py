@@ -51,6 +51,97 @@ def test_sort_bbox_centers_edge_cases():
     assert ld.sort_bbox_centers(c, 20) == og.sort_centers(c, 20) == [[(7, 120)], [(5, 58), (30, 60)], [(10, 12), (50, 10)]]
 
 
+def test_sort_and_group_randomised_against_oracle():
+    """The O(1) running mean and the first-match dictionary give what the reference's np.mean / list scans give,
+    duplicates of a centre included."""
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(1, 60))
+        cs = [(int(rng.integers(0, 3000)), int(rng.integers(0, 2000) // 7 * 7)) for _ in range(n)]
+        if n > 3:
+            cs[n // 2] = cs[0]                                   # a repeated centre
+        thr = float(rng.integers(0, 60))
+        assert ld.sort_bbox_centers(list(cs), thr) == og.sort_centers(list(cs), thr)
+        contours = [np.array([[[x - 5, y - 3]], [[x + 5, y - 3]], [[x + 5, y + 3 + i % 3]], [[x - 5, y + 3]]], np.int32)
+                    for i, (x, y) in enumerate(cs)]
+        lines = [ld.Line(ld.generate_guid(23), c, ld.BBox(*cv2.boundingRect(c)), ctr) for c, ctr in zip(contours, cs)]
+        rows = ld.sort_bbox_centers(list(cs), thr)
+        got = ld.group_line_chunks(rows, lines)
+        # restatement of line_detection.py:489-548 with the reference's list scans
+        want = []
+        for centers in rows:
+            if len(centers) > 1:
+                stack = []
+                for c in centers:
+                    for ln in lines:
+                        if c == ln.center:
+                            stack.append(ln.contour)
+                            break
+                want.append(cv2.convexHull(np.vstack(stack)))
+            else:
+                for c in centers:
+                    for ln in lines:
+                        if c == ln.center:
+                            want.append(ln.contour)
+                            break
+        assert len(got) == len(want) and all(np.array_equal(g.contour, w) for g, w in zip(got, want))
+
+
+def _random_band_mask(rng, H, W):
+    """Blobs with holes, ragged edges and specks in a few row bands; sometimes touching the image border."""
+    m = np.zeros((H, W), np.uint8)
+    for _ in range(int(rng.integers(1, 7))):
+        y = int(rng.integers(0, H - 20))
+        h = int(rng.integers(3, 40))
+        x0, x1 = sorted(int(v) for v in rng.integers(0, W, 2))
+        band = (cv2.GaussianBlur(rng.normal(0, 1, (h, max(x1 - x0, 1))).astype(np.float32), (0, 0), 2.0) > -0.05)
+        m[y:y + h, x0:x0 + band.shape[1]] |= band[: H - y].astype(np.uint8) * 255
+    for _ in range(int(rng.integers(0, 12))):
+        m[int(rng.integers(0, H)), int(rng.integers(0, W))] = 255
+    if rng.random() < 0.3:
+        m[0, : W // 3] = 255
+    if rng.random() < 0.3:
+        m[H - 1, W // 2:] = 255
+    if rng.random() < 0.2:
+        m[:, 0] = 255                                            # every row occupied: no compaction
+    return m
+
+
+def test_row_compaction_gives_cv2_contours_and_census():
+    """findContours / get_line_threshold through RowCompaction equal cv2 on the full mask: same contours, same
+    points, same list order, same threshold."""
+    rng = np.random.default_rng(12)
+    n_compacted = 0
+    for trial in range(60):
+        H, W = int(rng.integers(64, 500)), int(rng.integers(40, 700))
+        m = _random_band_mask(rng, H, W) if trial else np.zeros((H, W), np.uint8)
+        want, _ = cv2.findContours(m, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        rows = ld.RowCompaction(m)
+        n_compacted += rows.small is not None
+        got = ld.get_contours_compact(m, rows)
+        assert len(got) == len(want)
+        assert all(g.dtype == w.dtype and np.array_equal(g, w) for g, w in zip(got, want))
+        assert ld.get_line_threshold(m) == og.line_threshold(m)
+        _, m3, cs, ang = ld.build_raw_line_data(np.zeros((H, W, 3), np.uint8), m)
+        _, om, ocs, oang = og.build_raw_line_data(np.zeros((H, W, 3), np.uint8), m)
+        assert ang == oang and len(cs) == len(ocs) and all(np.array_equal(a, b) for a, b in zip(cs, ocs))
+        assert ld.get_line_threshold(m3) == og.line_threshold(om)
+    assert n_compacted > 30
+
+
+def test_mask3_link_is_the_identity_conversion():
+    """BGR2GRAY of a channel-replicated image is the channel (all 256 values), so get_line_threshold may read the
+    1-channel mask build_raw_line_data remembers; views and copies drop the link."""
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    assert np.array_equal(cv2.cvtColor(cv2.cvtColor(v, cv2.COLOR_GRAY2RGB), cv2.COLOR_BGR2GRAY), v)
+    page, boxes = synthetic.page(701, 600, 900)
+    mask = synthetic.band_mask(boxes, 600, 900)
+    _, m3, _, _ = ld.build_raw_line_data(page, mask)
+    assert isinstance(m3, np.ndarray) and m3.shape == (600, 900, 3) and m3.gray is mask
+    assert m3[:300].gray is None and m3.copy().gray is None and True
+    assert ld.get_line_threshold(m3) == ld.get_line_threshold(np.array(m3)) == og.line_threshold(np.array(m3))
+
+
 def test_roi_mask_equals_full_page_fill():
     page, boxes = synthetic.page(9, 400, 600)
     mask = synthetic.band_mask(boxes, 400, 600)

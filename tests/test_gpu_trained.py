@@ -106,10 +106,59 @@ def test_pipeline_page_to_text_trained_recogniser(engine, monkeypatch):
           f"equal to the page's transcription: {sum(l.text in want for l in ocr_lines)}/{len(truth)}")
     assert same >= int(np.ceil(0.95 * len(texts)))
     # the threaded batch entry point returns exactly what the single-page call returns
-    batch = pipe.run_ocr_batch([page, page, page], workers=3, k_factor=2.0, bbox_tolerance=2.5)
+    batch = pipe.run_ocr_batch([page, page, page], workers=3, staged=False, k_factor=2.0, bbox_tolerance=2.5)
     for st, res in batch:
         assert st == OpStatus.SUCCESS
         assert [l.text for l in res[2]] == [l.text for l in ocr_lines] and res[3] == angle
+    torch.cuda.synchronize()
+
+
+def _same_page_result(got, want):
+    from ocr_inference_b200.data import OpStatus
+
+    assert got[0] == want[0]
+    if got[0] != OpStatus.SUCCESS:
+        assert got[1] == want[1]
+        return
+    g, w = got[1], want[1]
+    assert np.array_equal(np.asarray(g[0]), np.asarray(w[0]))
+    assert [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h, l.center) for l in g[1]] == \
+        [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h, l.center) for l in w[1]]
+    assert all(np.array_equal(a.contour, b.contour) for a, b in zip(g[1], w[1]))
+    assert [(l.text, l.encoding) for l in g[2]] == [(l.text, l.encoding) for l in w[2]]
+    assert g[3] == w[3] and type(g[3]) is float
+
+
+def test_run_ocr_batch_staged_equals_page_by_page(engine):
+    """The staged schedule of run_ocr_batch (pages grouped through the segmentation network, host geometry on
+    worker threads, all crops of a chunk through the recogniser as one batch) returns exactly what run_ocr
+    returns page by page: mixed page sizes, a rotated page, a page without lines, a grayscale page (takes the
+    page-by-page route), more pages than one chunk."""
+    import cv2
+
+    from ocr_inference_b200.data import CharsetEncoder, LineDetectionConfig, OCRModelConfig, OpStatus
+    from ocr_inference_b200.inference import OCRPipeline
+
+    pipe = OCRPipeline(OCRModelConfig(easter2_weights_fitted(), "Easter2", 2000, 80, "input", "output", True, False,
+                                      CharsetEncoder.STACK, synth.CHARSET_76, True, "fitted"),
+                       LineDetectionConfig("", seg_weights_fitted(11), "deeplabv3plus-r34", 512, ["line"]), None,
+                       engine=engine)
+    pages = [synth.text_page(300 + i, 1024, 1536, n_lines=(3, 4))[0] for i in range(5)]
+    pages.append(synth.text_page(310, 2048, 3072)[0])
+    pages.append(synth.text_page(311, 1300, 900, n_lines=(4, 4))[0])
+    rot = cv2.warpAffine(pages[0], cv2.getRotationMatrix2D((768, 512), -2.0, 1), (1536, 1024), borderValue=(215, 215, 215))
+    pages.append(rot)
+    pages.append(np.full((700, 1100, 3), 220, np.uint8))                 # no lines
+    pages.append(pages[1][..., 0].copy())                                 # 2-D input: not a staged page
+    kw = dict(k_factor=2.0, bbox_tolerance=2.5)
+    want = [pipe.run_ocr(p, **kw) for p in pages]
+    assert sum(w[0] == OpStatus.SUCCESS for w in want) >= 7
+    for workers, chunk in ((4, 48), (2, 4), (1, 3)):
+        got = pipe.run_ocr_batch(pages, workers=workers, chunk_pages=chunk, **kw)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            _same_page_result(g, w)
+    print("angles:", [w[1][3] if w[0] == OpStatus.SUCCESS else w[1] for w in want])
     torch.cuda.synchronize()
 
 

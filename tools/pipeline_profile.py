@@ -23,6 +23,12 @@ def build_pipeline(eng):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    if os.environ.get("CVT"):
+        import cv2
+
+        cv2.setNumThreads(int(os.environ["CVT"]))
+    if os.environ.get("SWI"):
+        sys.setswitchinterval(float(os.environ["SWI"]))
     eng = get_engine(0)
     pipe = build_pipeline(eng)
     pages = [synthetic.text_page(3003 + i)[0] for i in range(n)]
@@ -56,13 +62,14 @@ def main():
         delattr(pipe, name)   # drop the timing wrappers (they synchronise the device)
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     batch = [pages[i % n] for i in range(nb)]
-    for workers in (1, 4, 8, 12, 16):
-        pipe.run_ocr_batch(batch[:workers], workers=workers)
-        t0 = time.perf_counter()
-        out = pipe.run_ocr_batch(batch, workers=workers)
-        dt = time.perf_counter() - t0
-        nl = sum(len(r[1][2]) for r in out if r[0] == OpStatus.SUCCESS)
-        print(f"run_ocr_batch workers={workers}: {nb / dt:.1f} pages/s, {nl / dt:.0f} lines/s")
+    for staged, ws in ((False, (1, 4, 6)), (True, (1, 2, 3, 4, 6, 8))):
+        for workers in ws:
+            pipe.run_ocr_batch(batch, workers=workers, staged=staged)
+            t0 = time.perf_counter()
+            out = pipe.run_ocr_batch(batch, workers=workers, staged=staged)
+            dt = time.perf_counter() - t0
+            nl = sum(len(r[1][2]) for r in out if r[0] == OpStatus.SUCCESS)
+            print(f"run_ocr_batch staged={staged} workers={workers}: {nb / dt:.1f} pages/s, {nl / dt:.0f} lines/s")
 
 
 if __name__ == "__main__":
