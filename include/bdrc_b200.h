@@ -61,6 +61,12 @@ int bdrc_profile_count(bdrc_ctx* ctx);
 /* synchronises the recorded events; ms and flops are per launch, name is a static string */
 int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double* flops);
 
+/* host-side staging helper (no GPU work): copies n byte ranges src[i][0..nbytes[i]) to dst + dst_off[i]
+ * with up to `threads` native threads.  Used to pack ragged line crops into one pinned upload buffer:
+ * the reference assembles its OCR input line by line in numpy (BDRC/inference.py:336-347, 618-666). */
+int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_t* dst_off, int n, void* dst,
+                     int threads);
+
 /* ---- models: replaces ort.InferenceSession(path)  BDRC/inference.py:128-130, 294 ------- */
 /* blob_host: a "BDRCW1" weight container (see ocr_inference_b200/weights.py), fp32 OIHW
  * tensors with BN already folded (the ONNX files the reference loads are folded too).

@@ -29,6 +29,7 @@ _SIGS = {
     "bdrc_profile_count": (c_int, [c_void_p]),
     "bdrc_profile_get": (c_int, [c_void_p, c_int, C.POINTER(C.c_char_p), C.POINTER(c_float),
                                  C.POINTER(c_double)]),
+    "bdrc_host_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
     "bdrc_load_weights": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, C.POINTER(c_void_p)]),
     "bdrc_free_model": (None, [c_void_p]),
     "bdrc_seg_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

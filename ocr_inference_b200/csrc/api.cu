@@ -1,4 +1,8 @@
 // Context management and the small C-ABI entry points that are not tied to one stage.
+#include <cstring>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 #include "nn_kernels.cuh"
 
@@ -80,6 +84,44 @@ int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double*
   if (name) *name = ctx->prof_name[i].c_str();
   if (ms) *ms = t;
   if (flops) *flops = ctx->prof_flops[i];
+  return BDRC_OK;
+}
+
+// Host-side staging: n ragged byte ranges -> one (pinned) buffer, copied by a few native threads.
+// One Python thread packing 64 line crops (19 MB) with numpy runs at memcpy speed of one core (~2 ms);
+// this call releases the GIL once and splits the bytes evenly, so OCRInference.run_batch's upload
+// is bound by the PCIe copy instead (BDRC/inference.py:336-347 builds its batch line by line).
+int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_t* dst_off, int n, void* dst,
+                     int threads) {
+  if (n < 0 || (n > 0 && (!src || !nbytes || !dst_off || !dst))) return BDRC_ERR_ARG;
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] < 0 || dst_off[i] < 0 || (nbytes[i] > 0 && !src[i])) return BDRC_ERR_ARG;
+    total += nbytes[i];
+  }
+  if (total == 0) return BDRC_OK;
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 16), total / (1 << 20)));
+  auto work = [&](int t) {
+    // thread t copies bytes [lo, hi) of the concatenated stream
+    const int64_t lo = total * t / T, hi = total * (t + 1) / T;
+    int64_t pos = 0;
+    for (int i = 0; i < n && pos < hi; ++i) {
+      const int64_t a = std::max(lo, pos), b = std::min(hi, pos + nbytes[i]);
+      if (b > a)
+        std::memcpy(static_cast<uint8_t*>(dst) + dst_off[i] + (a - pos), static_cast<const uint8_t*>(src[i]) + (a - pos),
+                    (size_t)(b - a));
+      pos += nbytes[i];
+    }
+  };
+  if (T == 1) {
+    work(0);
+    return BDRC_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(T - 1);
+  for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
   return BDRC_OK;
 }
 

@@ -70,3 +70,30 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_gather_packs_ragged_ranges():
+    """bdrc_host_gather (host-only entry point, runs without a GPU): ragged byte ranges land at their offsets,
+    whatever the thread count; empty ranges and n = 0 are fine; bad arguments are refused."""
+    import numpy as np
+
+    from ocr_inference_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    srcs = [rng.integers(0, 256, int(n), dtype=np.uint8) for n in (3_000_001, 0, 17, 5_242_880, 1, 2_000_000)]
+    nb = np.array([s.size for s in srcs], dtype=np.int64)
+    off = np.zeros(len(srcs), dtype=np.int64)
+    off[1:] = np.cumsum((nb[:-1] + 15) // 16 * 16)
+    ptrs = np.array([s.ctypes.data for s in srcs], dtype=np.uint64)
+    for threads in (1, 3, 8, 64):
+        dst = np.full(int(off[-1] + nb[-1]) + 32, 0xAB, np.uint8)
+        assert lib.bdrc_host_gather(ptrs.ctypes.data, nb.ctypes.data, off.ctypes.data, len(srcs), dst.ctypes.data,
+                                    threads) == 0
+        for s, o in zip(srcs, off):
+            assert np.array_equal(dst[o:o + s.size], s)
+        assert (dst[-32:] == 0xAB).all()
+    assert lib.bdrc_host_gather(None, None, None, 0, None, 4) == 0
+    bad = nb.copy()
+    bad[2] = -1
+    assert lib.bdrc_host_gather(ptrs.ctypes.data, bad.ctypes.data, off.ctypes.data, len(srcs), dst.ctypes.data, 2) != 0
