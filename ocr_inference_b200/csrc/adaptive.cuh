@@ -46,6 +46,27 @@ struct SrcPageTiles {
     const int g = (p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + 16384) >> 15;
     return (float)g;
   }
+  // four horizontally adjacent pixels x .. x+3 of one tile row (x % 4 == 0, all inside the tile): three
+  // 32-bit loads instead of twelve byte loads.  Returns false where the caller must go pixel by pixel
+  // (quad straddling the page edge, or a row that is not 4-byte aligned).
+  __device__ __forceinline__ bool gray4(int img, int y, int x, float* v) const {
+    const int ty = img / ntx, tx = img - ty * ntx;
+    const int py = ty * patch + y, px = tx * patch + x;
+    if (py >= Hc || px >= Wc) {
+      v[0] = v[1] = v[2] = v[3] = 255.f;
+      return true;
+    }
+    const uint8_t* p = page + ((size_t)py * Wc + px) * 3;
+    if (px + 3 >= Wc || (reinterpret_cast<uintptr_t>(p) & 3)) return false;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    // bytes: w0 = r0 g0 b0 r1, w1 = g1 b1 r2 g2, w2 = b2 r3 g3 b3 (little endian)
+    v[0] = (float)(int)(((w0 & 255u) * 9798u + ((w0 >> 8) & 255u) * 19235u + ((w0 >> 16) & 255u) * 3735u + 16384u) >> 15);
+    v[1] = (float)(int)(((w0 >> 24) * 9798u + (w1 & 255u) * 19235u + ((w1 >> 8) & 255u) * 3735u + 16384u) >> 15);
+    v[2] = (float)(int)((((w1 >> 16) & 255u) * 9798u + (w1 >> 24) * 19235u + (w2 & 255u) * 3735u + 16384u) >> 15);
+    v[3] = (float)(int)((((w2 >> 8) & 255u) * 9798u + ((w2 >> 16) & 255u) * 19235u + (w2 >> 24) * 3735u + 16384u) >> 15);
+    return true;
+  }
 };
 
 // batch of single-channel u8 images [n][H][W]
@@ -56,6 +77,13 @@ struct SrcGrayBatch {
   int iw() const { return W; }
   __device__ __forceinline__ float gray(int i, int y, int x) const {
     return (float)img[((size_t)i * H + y) * W + x];
+  }
+  __device__ __forceinline__ bool gray4(int i, int y, int x, float* v) const {
+    const uint8_t* p = img + ((size_t)i * H + y) * W + x;
+    if (reinterpret_cast<uintptr_t>(p) & 3) return false;
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    v[0] = (float)(w & 255u); v[1] = (float)((w >> 8) & 255u); v[2] = (float)((w >> 16) & 255u); v[3] = (float)(w >> 24);
+    return true;
   }
 };
 
@@ -127,13 +155,25 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
     //  per SM, 0.197 ms per page against 0.130 ms for this version -- the kernel is bound by shared-memory
     //  load latency at 3 CTAs per SM, ncu: 58 % of stalls are short-scoreboard, issue slots 36 % busy)
     if (b < n_blocks) {
-      for (int i = threadIdx.x; i < RB * GW; i += THREADS) {
-        const int r = i / GW, c = i - r * GW;
+      // four pixels per item: tile columns x0 - 28 + 4q .. + 3 (a 4-aligned superset of the 82 staged columns),
+      // staged column c = 4q - 3 + j; quads 7 .. 14 are the strip itself
+      constexpr int NQ = (GW + 3 + 3) / 4;   // 22
+      for (int i = threadIdx.x; i < RB * NQ; i += THREADS) {
+        const int r = i / NQ, q = i - r * NQ;
         const int y = min(RB * b + r, IH - 1);
-        const int x = min(max(x0 + c - KR, 0), IW - 1);
-        const float v = src.gray(img, y, x);
-        g[r * GSTRIDE + c] = v;
-        if (c >= KR && c < KR + SW) gc[((RB * b + r) & (RING - 1)) * SW + c - KR] = (uint8_t)v;
+        const int xq = x0 - 28 + 4 * q;
+        float v[4];
+        if (!(xq >= 0 && xq + 3 < IW && src.gray4(img, y, xq, v))) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = src.gray(img, y, min(max(xq + j, 0), IW - 1));
+        }
+        float* gr = g + r * GSTRIDE + 4 * q - 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * q - 3 + j >= 0 && 4 * q - 3 + j < GW) gr[j] = v[j];
+        if (q >= 7 && q < 7 + SW / 4)
+          *reinterpret_cast<uint32_t*>(gc + ((RB * b + r) & (RING - 1)) * SW + 4 * (q - 7)) =
+              (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
       }
     }
     __syncthreads();
@@ -181,8 +221,15 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
       const int c = threadIdx.x % SW, r4 = RB * ob + (threadIdx.x / SW) * 4;   // output rows r4 .. r4+3
       float v[2 * KR + 4];
       if (r4 - KR >= 0 && r4 + 3 + KR < IH) {
+        const int s0 = (r4 - KR) & (RING - 1);     // warp-uniform (one r4 per warp)
+        if (s0 + 2 * KR + 4 <= RING) {             // window does not wrap: immediate offsets, no index math
+          const float* rp = ring + s0 * SW + c;
 #pragma unroll
-        for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[((r4 - KR + i) & (RING - 1)) * SW + c];
+          for (int i = 0; i < 2 * KR + 4; ++i) v[i] = rp[i * SW];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[((s0 + i) & (RING - 1)) * SW + c];
+        }
       } else {   // replicate border at the top / bottom of the image
 #pragma unroll
         for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[(min(max(r4 - KR + i, 0), IH - 1) & (RING - 1)) * SW + c];
