@@ -60,6 +60,18 @@ struct TcParams {
 
 using namespace tcptx;
 
+// BDRC_PDL=1 launches the conv kernels with programmatic dependent launch (the next kernel's barrier init / TMEM
+// allocation overlaps the tail of this one).  Measured on B200 and left OFF: C1 at 64 lines gains 3 % (69.5 k ->
+// 71.8 k lines/s), but 8 queued C2 steps (1456 back-to-back launches) drop from 515 to 199 pages/s -- with deep
+// queues of cluster launches the early-resident CTAs of kernel N+1 appear to hold back kernel N's tail.
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("BDRC_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
   return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
@@ -373,6 +385,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only parameters, shared memory and TMEM; the activations are the previous kernel's
+  griddep_launch();
+  griddep_wait();
 
   const int k_iters = p.R * p.S * p.kchunks;
 
@@ -583,6 +598,9 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only parameters, shared memory and TMEM; the activations are the previous kernel's
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -878,17 +896,29 @@ int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, 
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SlabCfg<2>::SMEM;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<2>, mapA, mapB, mapO, p));
   } else {
     const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-    conv_tc_slab_kernel<1><<<grid, NUM_THREADS, SlabCfg<1>::SMEM, s>>>(mapA, mapB, mapO, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SlabCfg<1>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<1>, mapA, mapB, mapO, p));
   }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
@@ -993,17 +1023,29 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, mapA, mapB, mapO, p));
   } else {
     int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-    conv_tc_kernel<1><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(mapA, mapB, mapO, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, mapA, mapB, mapO, p));
   }
   BDRC_CHECK_LAUNCH(ctx);
   return 0;

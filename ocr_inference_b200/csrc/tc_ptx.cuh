@@ -191,4 +191,11 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel in the stream drains;
+// griddep_wait() returns once that kernel has completed and its writes are visible, and must precede every
+// access to global memory the predecessor may have touched.  griddep_launch() lets the NEXT kernel do the same.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace tcptx
