@@ -149,6 +149,21 @@ int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
                       const double* ctrl_host, const double* params_host, int n_ctrl,
                       uint8_t* dst, void* workspace, size_t workspace_bytes, void* stream);
 
+/* cubic B-spline sampling, scipy.ndimage.map_coordinates(order=3, mode='constant', cval=0): what the
+ * reference's run_tps asks for by calling map_coordinates with its defaults (image_dewarping.py:66-72).
+ * Step 1 (scipy's spline_filter): u8 image -> fp64 spline coefficients [H][W][C], bdrc_spline3_coef_bytes()
+ * bytes of device memory, each channel filtered on its own along axis 0 then axis 1 (mirror boundary).
+ * Step 2: sample the coefficients at explicit coordinates (fp64 [2][H][W] = (row, col)) or at the
+ * thin-plate-spline image of the output grid (same arguments as bdrc_tps_remap_u8). */
+size_t bdrc_spline3_coef_bytes(int H, int W, int C);
+int bdrc_spline3_prefilter_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, double* coef,
+                              void* stream);
+int bdrc_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C, const double* coords,
+                        uint8_t* dst, void* stream);
+int bdrc_tps_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C,
+                            const double* ctrl_host, const double* params_host, int n_ctrl,
+                            uint8_t* dst, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a-5: extract_line_images  BDRC/line_detection.py:330-359 --------------------------- */
 /* Inputs shared by both calls: page u8 HWC [H][W][C] (C = 1 or 3, device); for each line l the
  * filled-contour mask of its bounding-box ROI roi_host[l] = (x, y, w, h) -- rasterised by the

@@ -223,6 +223,135 @@ __global__ void remap_kernel(const uint8_t* __restrict__ src, int H, int W, int 
   sample_bilinear_const(src, H, W, C, (double)coords[i], (double)coords[(size_t)H * W + i], dst + i * C);
 }
 
+
+// ---- scipy.ndimage.map_coordinates(order=3, mode='constant', cval=0): the sampling the reference's run_tps
+// intends (image_dewarping.py:66-72 calls map_coordinates with its defaults) ---------------------------------
+// Two steps, as in scipy: (1) spline_filter: the image becomes cubic B-spline coefficients by a causal +
+// anticausal first-order recursion with pole z = sqrt(3) - 2 along each axis (axis 0 first), mirror boundary;
+// (2) every output sample is a 4 x 4 weighted sum of coefficients, taps mirrored at the border, 0 outside
+// [0, n-1].  All arithmetic is fp64 and unfused (scipy's C is compiled without FMA contraction), so the
+// interpolation step is bit-identical to scipy given the same coefficients; the coefficients agree to a few ulp.
+constexpr double SPL_Z = -0.26794919243112270647;   // sqrt(3) - 2
+constexpr int SPL_INIT_TERMS = 80;                  // |z|^80 < 2e-46: the causal start-up sum has converged
+
+// one thread per line; element i of the line lives at base[i * stride]
+template <typename Tin>
+__device__ __forceinline__ void spline_filter_line(const Tin* in, double* c, int n, size_t stride) {   // in may alias c
+  const double z = SPL_Z;
+  const double gain = __dmul_rn(1.0 - z, 1.0 - 1.0 / z);
+  if (n == 1) {
+    c[0] = (double)in[0];
+    return;
+  }
+  // causal start (ni_splines.c:_init_causal_mirror), truncated where z^i has vanished
+  const double z_n_1 = pow(z, (double)(n - 1));
+  double c0 = __dadd_rn(__dmul_rn((double)in[0], gain), __dmul_rn(z_n_1, __dmul_rn((double)in[(size_t)(n - 1) * stride], gain)));
+  double z_i = z;
+  const int terms = min(n - 2, SPL_INIT_TERMS);
+  for (int i = 1; i <= terms; ++i) {
+    const double a = __dmul_rn((double)in[(size_t)i * stride], gain);
+    const double b = __dmul_rn((double)in[(size_t)(n - 1 - i) * stride], gain);
+    c0 = __dadd_rn(c0, __dmul_rn(z_i, __dadd_rn(a, __dmul_rn(z_n_1, b))));
+    z_i = __dmul_rn(z_i, z);
+  }
+  c0 = c0 / __dadd_rn(1.0, -__dmul_rn(z_n_1, z_n_1));
+  double prev = c0;
+  c[0] = c0;
+#pragma unroll 8
+  for (int i = 1; i < n; ++i) {
+    prev = __dadd_rn(__dmul_rn((double)in[(size_t)i * stride], gain), __dmul_rn(z, prev));
+    c[(size_t)i * stride] = prev;
+  }
+  // anticausal start (_init_anticausal_mirror) and sweep
+  double nxt = __dmul_rn(__dadd_rn(__dmul_rn(z, c[(size_t)(n - 2) * stride]), prev), z) / __dadd_rn(__dmul_rn(z, z), -1.0);
+  c[(size_t)(n - 1) * stride] = nxt;
+#pragma unroll 8
+  for (int i = n - 2; i >= 0; --i) {
+    nxt = __dmul_rn(z, __dadd_rn(nxt, -c[(size_t)i * stride]));
+    c[(size_t)i * stride] = nxt;
+  }
+}
+
+// axis 0: lines run down the image; thread t = x * C + ch, neighbours are adjacent in memory (coalesced)
+__global__ void spline3_filter_axis0_kernel(const uint8_t* __restrict__ src, int H, int W, int C, double* __restrict__ coef) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * C) return;
+  spline_filter_line(src + t, coef + t, H, (size_t)W * C);
+}
+
+// axis 1: lines run along the rows of the coefficient image, in place; thread t = y * C + ch
+__global__ void spline3_filter_axis1_kernel(double* __restrict__ coef, int H, int W, int C) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * C) return;
+  const int y = t / C, ch = t - y * C;
+  double* line = coef + (size_t)y * W * C + ch;
+  // the gain of this axis is applied inside spline_filter_line as well (scipy multiplies per axis)
+  spline_filter_line(line, line, W, (size_t)C);
+}
+
+__device__ __forceinline__ void spline3_weights(double x, double* w) {
+  // ni_splines.c:get_spline_interpolation_weights, order 3
+  x = __dadd_rn(x, -floor(x));
+  const double y = x, z = __dadd_rn(1.0, -x);
+  w[1] = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(y, y), __dadd_rn(y, -2.0)), 3.0), 4.0) / 6.0;
+  w[2] = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(z, z), __dadd_rn(z, -2.0)), 3.0), 4.0) / 6.0;
+  w[0] = __dmul_rn(__dmul_rn(z, z), z) / 6.0;
+  w[3] = __dadd_rn(__dadd_rn(__dadd_rn(1.0, -w[0]), -w[1]), -w[2]);
+}
+
+__device__ __forceinline__ int spline_mirror(int idx, int n) {
+  // ni_interpolation.c border mapping of the filter taps for mode 'constant' (whole-sample mirror)
+  if (n <= 1) return 0;
+  const int s2 = 2 * n - 2;
+  if (idx < 0) {
+    idx = s2 * (-idx / s2) + idx;
+    return idx <= 1 - n ? idx + s2 : -idx;
+  }
+  if (idx >= n) {
+    idx -= s2 * (idx / s2);
+    if (idx >= n) idx = s2 - idx;
+  }
+  return idx;
+}
+
+__device__ __forceinline__ void sample_cubic_const(const double* __restrict__ coef, int H, int W, int C, double r,
+                                                   double c, uint8_t* o) {
+  if (!(r >= 0.0 && r <= (double)(H - 1) && c >= 0.0 && c <= (double)(W - 1))) {
+    for (int k = 0; k < C; ++k) o[k] = 0;
+    return;
+  }
+  const int sr = (int)floor(r) - 1, sc = (int)floor(c) - 1;
+  double wr[4], wc[4];
+  spline3_weights(r, wr);
+  spline3_weights(c, wc);
+  int ri[4], ci[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ri[i] = spline_mirror(sr + i, H);
+    ci[i] = spline_mirror(sc + i, W);
+  }
+  for (int k = 0; k < C; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(coef[((size_t)ri[i] * W + ci[j]) * C + k], wr[i]), wc[j]));
+    // ni_interpolation.c CASE_INTERP_OUT_UINT: t > 0 ? t + 0.5 : 0, clamped, truncated
+    t = t > 0.0 ? __dadd_rn(t, 0.5) : 0.0;
+    o[k] = (uint8_t)(t > 255.0 ? 255.0 : t);
+  }
+}
+
+__global__ void remap_cubic_kernel(const double* __restrict__ coef, int H, int W, int C,
+                                   const double* __restrict__ coords, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const size_t i = (size_t)y * W + x;
+  sample_cubic_const(coef, H, W, C, coords[i], coords[(size_t)H * W + i], dst + i * C);
+}
+
 constexpr int TPS_MAX_CTRL = 64;
 struct TpsParams {
   int n;
@@ -230,9 +359,11 @@ struct TpsParams {
   double par[TPS_MAX_CTRL + 3][2];
 };
 
-// thin-plate-spline transform of the output grid index (row, col), then bilinear sampling
+// thin-plate-spline transform of the output grid index (row, col), then bilinear (CUBIC = false) or cubic
+// B-spline (CUBIC = true, `src` then holds fp64 spline coefficients) sampling
 // (tps.ThinPlateSpline.transform: [U(|p - c_j|), 1, p] @ parameters, U(r) = r^2 log r)
-__global__ void tps_remap_kernel(const uint8_t* __restrict__ src, int H, int W, int C,
+template <bool CUBIC>
+__global__ void tps_remap_kernel(const void* __restrict__ src, int H, int W, int C,
                                  const TpsParams* __restrict__ tp, uint8_t* __restrict__ dst) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
@@ -248,7 +379,10 @@ __global__ void tps_remap_kernel(const uint8_t* __restrict__ src, int H, int W, 
     orow += u * tp->par[j][0];
     ocol += u * tp->par[j][1];
   }
-  sample_bilinear_const(src, H, W, C, orow, ocol, dst + ((size_t)y * W + x) * C);
+  if (CUBIC)
+    sample_cubic_const(reinterpret_cast<const double*>(src), H, W, C, orow, ocol, dst + ((size_t)y * W + x) * C);
+  else
+    sample_bilinear_const(reinterpret_cast<const uint8_t*>(src), H, W, C, orow, ocol, dst + ((size_t)y * W + x) * C);
 }
 
 // workspace carve-up shared by the two extract entry points
@@ -475,13 +609,14 @@ int bdrc_remap_bilinear_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int 
   return 0;
 }
 
-int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, const double* ctrl_host,
-                      const double* params_host, int n_ctrl, uint8_t* dst, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+static int tps_remap_any(bdrc_ctx* ctx, bool cubic, const void* src, int H, int W, int C, const double* ctrl_host,
+                        const double* params_host, int n_ctrl, uint8_t* dst, void* workspace, size_t workspace_bytes,
+                        void* stream) {
   if (!ctx) return BDRC_ERR_ARG;
-  BDRC_REQUIRE(ctx, src && dst && ctrl_host && params_host && n_ctrl >= 1 && n_ctrl <= TPS_MAX_CTRL && C >= 1 && C <= 4,
-               "tps_remap_u8: bad arguments (at most %d control points)", TPS_MAX_CTRL);
-  BDRC_REQUIRE(ctx, workspace && workspace_bytes >= sizeof(TpsParams), "tps_remap_u8: workspace too small");
+  BDRC_REQUIRE(ctx, src && dst && ctrl_host && params_host && n_ctrl >= 1 && n_ctrl <= TPS_MAX_CTRL && C >= 1 && C <= 4 &&
+                   H > 0 && W > 0,
+               "tps_remap: bad arguments (at most %d control points)", TPS_MAX_CTRL);
+  BDRC_REQUIRE(ctx, workspace && workspace_bytes >= sizeof(TpsParams), "tps_remap: workspace too small");
   TpsParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.n = n_ctrl;
@@ -490,7 +625,47 @@ int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, co
   cudaStream_t s = (cudaStream_t)stream;
   BDRC_CUDA(ctx, cudaMemcpyAsync(workspace, &tp, sizeof(tp), cudaMemcpyHostToDevice, s));
   BDRC_CUDA(ctx, cudaStreamSynchronize(s));   // tp lives on this stack frame
-  tps_remap_kernel<<<dim3(ceil_div(W, 128), H), 128, 0, s>>>(src, H, W, C, reinterpret_cast<const TpsParams*>(workspace), dst);
+  const dim3 grid(ceil_div(W, 128), H);
+  if (cubic)
+    tps_remap_kernel<true><<<grid, 128, 0, s>>>(src, H, W, C, reinterpret_cast<const TpsParams*>(workspace), dst);
+  else
+    tps_remap_kernel<false><<<grid, 128, 0, s>>>(src, H, W, C, reinterpret_cast<const TpsParams*>(workspace), dst);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, const double* ctrl_host,
+                      const double* params_host, int n_ctrl, uint8_t* dst, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return tps_remap_any(ctx, false, src, H, W, C, ctrl_host, params_host, n_ctrl, dst, workspace, workspace_bytes, stream);
+}
+
+int bdrc_tps_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C, const double* ctrl_host,
+                            const double* params_host, int n_ctrl, uint8_t* dst, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return tps_remap_any(ctx, true, coef, H, W, C, ctrl_host, params_host, n_ctrl, dst, workspace, workspace_bytes, stream);
+}
+
+size_t bdrc_spline3_coef_bytes(int H, int W, int C) {
+  return H > 0 && W > 0 && C > 0 ? (size_t)H * W * C * sizeof(double) : 0;
+}
+
+int bdrc_spline3_prefilter_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, double* coef, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, src && coef && H > 0 && W > 0 && C >= 1 && C <= 4, "spline3_prefilter_u8: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  spline3_filter_axis0_kernel<<<ceil_div(W * C, 64), 64, 0, s>>>(src, H, W, C, coef);
+  BDRC_CHECK_LAUNCH(ctx);
+  spline3_filter_axis1_kernel<<<ceil_div(H * C, 64), 64, 0, s>>>(coef, H, W, C);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int bdrc_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C, const double* coords, uint8_t* dst,
+                        void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_REQUIRE(ctx, coef && dst && coords && H > 0 && W > 0 && C >= 1 && C <= 4, "remap_cubic_u8: bad arguments");
+  remap_cubic_kernel<<<dim3(ceil_div(W, 128), H), 128, 0, (cudaStream_t)stream>>>(coef, H, W, C, coords, dst);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

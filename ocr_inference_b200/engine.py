@@ -268,6 +268,42 @@ class Engine:
                                                self.stream), "tps_remap_u8")
         return out
 
+    def spline3_prefilter(self, img: torch.Tensor) -> torch.Tensor:
+        """u8 HWC image -> fp64 cubic B-spline coefficients [H, W, C] (scipy.ndimage.spline_filter, order 3)."""
+        img = img.contiguous()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        Cn = int(img.shape[2]) if img.dim() == 3 else 1
+        coef = torch.empty((H, W, Cn), dtype=torch.float64, device=self.device)
+        assert coef.numel() * 8 == int(self.lib.bdrc_spline3_coef_bytes(H, W, Cn))
+        self._check(self.lib.bdrc_spline3_prefilter_u8(self.ctx.h, img.data_ptr(), H, W, Cn, coef.data_ptr(), self.stream),
+                    "spline3_prefilter_u8")
+        return coef
+
+    def remap_cubic(self, img: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:
+        """scipy.ndimage.map_coordinates(order=3, mode='constant', cval=0) per channel; coords fp64 [2, H, W]."""
+        coef = self.spline3_prefilter(img)
+        H, W, Cn = (int(v) for v in coef.shape)
+        coords = coords.to(device=self.device, dtype=torch.float64).contiguous()
+        if tuple(coords.shape) != (2, H, W):
+            raise ValueError("remap_cubic: coords must be [2, H, W]")
+        out = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.bdrc_remap_cubic_u8(self.ctx.h, coef.data_ptr(), H, W, Cn, coords.data_ptr(), out.data_ptr(),
+                                                 self.stream), "remap_cubic_u8")
+        return out
+
+    def tps_remap_cubic(self, img: torch.Tensor, ctrl: np.ndarray, params: np.ndarray) -> torch.Tensor:
+        """Thin-plate-spline dewarp with cubic B-spline sampling (the reference's intended run_tps)."""
+        coef = self.spline3_prefilter(img)
+        H, W, Cn = (int(v) for v in coef.shape)
+        out = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        c = np.ascontiguousarray(ctrl, dtype=np.float64)
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        ws = self._workspace("tps", int(self.lib.bdrc_tps_workspace_bytes()))
+        self._check(self.lib.bdrc_tps_remap_cubic_u8(self.ctx.h, coef.data_ptr(), H, W, Cn, c.ctypes.data, p.ctypes.data,
+                                                     int(c.shape[0]), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     self.stream), "tps_remap_cubic_u8")
+        return out
+
     # ---- a-5 -----------------------------------------------------------------------------
     def pack_masks(self, masks: list[np.ndarray], rois: list[tuple[int, int, int, int]]):
         """ROI masks (filled contours) -> one device buffer + host geometry arrays."""

@@ -8,8 +8,10 @@ Deviation from the reference, on purpose: reference run_tps (:22-74) cannot run
 (`npt.NDArray(list)` raises TypeError at :42, and the corner control points are scaled twice at
 :55-56).  This module implements the INTENDED behaviour: np.asarray control points, corners scaled
 once, thin-plate spline with alpha = 0.5 (thin-plate-spline==1.2.0 algorithm) and -- as
-north_star specifies -- order-1 (bilinear) sampling with constant-0 border instead of scipy's
-default order-3 spline.  Parity is checked against scipy.ndimage.map_coordinates(order=1).
+north_star specifies -- order-1 (bilinear) sampling with constant-0 border by default.  `order=3` selects
+scipy's default cubic B-spline sampling, i.e. exactly what the reference's map_coordinates call would compute
+(spline prefilter + 4x4 taps, both on the GPU in fp64).  Parity is checked against
+scipy.ndimage.map_coordinates(order=1 / order=3).
 """
 from __future__ import annotations
 
@@ -50,9 +52,13 @@ class ThinPlateSpline:
         return np.hstack([U, np.ones((len(X), 1)), X]) @ self.parameters
 
 
-def run_tps(image: np.ndarray, input_pts, output_pts, add_corners: bool = True, alpha: float = 0.5) -> np.ndarray:
+def run_tps(image: np.ndarray, input_pts, output_pts, add_corners: bool = True, alpha: float = 0.5,
+            order: int = 1) -> np.ndarray:
     """Intended behaviour of image_dewarping.run_tps (:22-74): fit output grid -> input coordinates,
-    resample every channel bilinearly on the GPU."""
+    resample every channel on the GPU, bilinearly (order=1) or with the cubic B-spline of scipy's
+    map_coordinates default (order=3)."""
+    if order not in (1, 3):
+        raise ValueError("run_tps: order must be 1 (bilinear) or 3 (cubic B-spline)")
     from .inference import get_engine
 
     if image.ndim == 2:
@@ -67,7 +73,8 @@ def run_tps(image: np.ndarray, input_pts, output_pts, add_corners: bool = True, 
     tps = ThinPlateSpline(alpha).fit(inp, out)
     eng = get_engine()
     src = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
-    return eng.tps_remap(src, tps.control_points, tps.parameters).cpu().numpy()
+    remap = eng.tps_remap_cubic if order == 3 else eng.tps_remap
+    return remap(src, tps.control_points, tps.parameters).cpu().numpy()
 
 
 def _slice_center(mask_roi: np.ndarray, x0: int, x1: int, gx: int, gy: int):
@@ -117,9 +124,10 @@ def get_global_tps_line(line_data: list) -> int:
     return deltas.index(pick)
 
 
-def apply_global_tps(image: np.ndarray, line_mask: np.ndarray, line_data: list):
+def apply_global_tps(image: np.ndarray, line_mask: np.ndarray, line_data: list, order: int = 1):
     """:267-289."""
     d = line_data[get_global_tps_line(line_data)]
     if d["input_pts"] is None or d["output_pts"] is None:
         raise ValueError("input_pts and output_pts must not be None when tps is True")
-    return run_tps(image, d["output_pts"], d["input_pts"]), run_tps(line_mask, d["output_pts"], d["input_pts"])
+    return (run_tps(image, d["output_pts"], d["input_pts"], order=order),
+            run_tps(line_mask, d["output_pts"], d["input_pts"], order=order))

@@ -350,7 +350,9 @@ class OCRPipeline:
 
     # ---- stage 3 (inference.py:535-589) --------------------------------------------------
     def apply_dewarping(self, rot_img, rot_mask, filtered_contours, page_angle, use_tps: bool = False,
-                        tps_threshold: float = 0.25):
+                        tps_threshold: float = 0.25, spline_order: int = 1):
+        """`spline_order` (addition): 1 = bilinear resampling (north_star), 3 = scipy's default cubic B-spline,
+        what the reference's map_coordinates call computes."""
         import cv2
 
         from .image_dewarping import apply_global_tps, check_for_tps
@@ -362,7 +364,7 @@ class OCRPipeline:
         if ratio <= tps_threshold:
             return OpStatus.SUCCESS, DewarpingResult(rot_img, rot_mask, filtered_contours, page_angle, False,
                                                      tps_ratio=ratio)
-        dew_img, dew_mask = apply_global_tps(rot_img, rot_mask, tps_line_data)
+        dew_img, dew_mask = apply_global_tps(rot_img, rot_mask, tps_line_data, order=spline_order)
         if dew_mask.ndim == 3:
             dew_mask = cv2.cvtColor(dew_mask, cv2.COLOR_RGB2GRAY)
         d_img, d_mask, contours, new_angle = build_raw_line_data(dew_img, dew_mask)

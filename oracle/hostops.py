@@ -526,6 +526,57 @@ def remap_bilinear_ref(image: np.ndarray, coords: np.ndarray) -> np.ndarray:
                      for c in range(image.shape[2])], axis=-1)
 
 
+def remap_cubic_ref(image: np.ndarray, coords: np.ndarray) -> np.ndarray:
+    """The call the reference makes (image_dewarping.py:66-72): scipy.ndimage.map_coordinates with its
+    defaults -- order=3 cubic B-spline, prefilter, mode='constant', cval=0 -- per channel."""
+    import scipy.ndimage
+
+    return np.stack([scipy.ndimage.map_coordinates(image[..., c], coords) for c in range(image.shape[2])], axis=-1)
+
+
+def spline3_interp_numpy(coef: np.ndarray, r: float, c: float) -> float:
+    """Restatement of scipy's cubic interpolation step on prefiltered coefficients (ni_interpolation.c
+    NI_GeometricTransform + ni_splines.c get_spline_interpolation_weights, mode 'constant'): bitwise equal to
+    scipy given scipy's own coefficients (tests/test_oracle_closed_forms.py); small cases only."""
+    import math
+
+    H, W = coef.shape
+    if r < 0 or r > H - 1 or c < 0 or c > W - 1:
+        return 0.0
+
+    def weights(x):
+        x = x - math.floor(x)
+        y, z = x, 1.0 - x
+        w = [z * z * z / 6.0, (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0, (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0, 1.0]
+        for i in range(3):
+            w[3] -= w[i]
+        return w
+
+    def mirror(i, n):
+        if n <= 1:
+            return 0
+        s2 = 2 * n - 2
+        if i < 0:
+            i = s2 * int(-i / s2) + i
+            return i + s2 if i <= 1 - n else -i
+        if i >= n:
+            i -= s2 * int(i / s2)
+            if i >= n:
+                i = s2 - i
+        return i
+
+    sr, sc = math.floor(r) - 1, math.floor(c) - 1
+    wr, wc = weights(r), weights(c)
+    t = 0.0
+    for i in range(4):
+        for j in range(4):
+            v = coef[mirror(sr + i, H), mirror(sc + j, W)]
+            v *= wr[i]
+            v *= wc[j]
+            t += v
+    return t
+
+
 # ------------------------------------------------------------------------------------------
 # a-11 torch-path pre/post  (BDRC/utils.py:967-1051, 1100-1108, 444-454; inference.py:943-956)
 # ------------------------------------------------------------------------------------------

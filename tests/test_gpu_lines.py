@@ -71,6 +71,58 @@ def test_tps_remap_matches_oracle(engine):
     assert d2[safe].max() <= 1 and d2[outside].max() == 0
 
 
+@pytest.mark.parametrize("shape,C", [((240, 320), 3), ((70, 45), 1), ((2, 300), 3), ((130, 3), 1), ((1, 64), 1)])
+def test_remap_cubic_matches_scipy(engine, shape, C):
+    """bdrc_spline3_prefilter_u8 + bdrc_remap_cubic_u8 against scipy.ndimage.map_coordinates with its defaults
+    (order 3, prefilter, constant 0): coefficients to a few ulp, samples bit-exact except where the fp64 value sits
+    within 1e-9 of a .5 rounding boundary."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(31)
+    H, W = shape
+    img = rng.integers(0, 256, (H, W, C), dtype=np.uint8)
+    coef = engine.spline3_prefilter(_dev(img)).cpu().numpy()
+    for k in range(C):
+        ref_coef = ndi.spline_filter(img[..., k], 3, output=np.float64, mode="constant")
+        assert np.abs(coef[..., k] - ref_coef).max() <= 1e-9 * max(1.0, np.abs(ref_coef).max())
+    rr, cc = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    coords = np.stack([rr + 3 * np.sin(cc / 17) - 0.7, cc + 2.5 * np.cos(rr / 13) + 0.4])
+    coords[:, 0, : min(W, 4)] = np.array([[-0.4, 0.0, H - 1.0, H - 0.5], [0.0, W - 1.0, 0.0, 1.0]])[:, : min(W, 4)]
+    got = engine.remap_cubic(_dev(img), torch.from_numpy(coords)).cpu().numpy()
+    ref = ho.remap_cubic_ref(img, coords)
+    exact = np.stack([ndi.map_coordinates(img[..., k], coords, output=np.float64) for k in range(C)], axis=-1)
+    tie = np.abs((exact + 0.5) - np.round(exact + 0.5)) < 1e-9
+    assert got.shape == ref.shape and np.array_equal(got[~tie], ref[~tie])
+    assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1 and tie.mean() < 1e-3
+
+
+def test_tps_remap_cubic_matches_scipy(engine):
+    """run_tps(order=3): thin-plate-spline coordinates + cubic sampling, against the oracle's TPS restatement fed
+    to scipy's map_coordinates defaults (the reference's intended call)."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(6)
+    H, W = 300, 500
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), (0, 0), 1.5)
+    out_pts = np.array([[150, 50], [150, 150], [150, 250], [150, 350], [150, 450]], float)
+    in_pts = out_pts + np.array([[8, 0], [-5, 0], [-9, 0], [-4, 0], [7, 0]], float)
+    corners = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]) * [H, W]
+    tps = ThinPlateSpline(0.5).fit(np.concatenate([out_pts, corners]), np.concatenate([in_pts, corners]))
+    grid = np.indices((H, W), dtype=np.float64).transpose(1, 2, 0).reshape(-1, 2)
+    coords = tps.transform(grid).reshape(H, W, 2).transpose(2, 0, 1)
+    ref = ho.remap_cubic_ref(img, coords)
+    from ocr_inference_b200.image_dewarping import run_tps
+    got = run_tps(img, out_pts.tolist(), in_pts.tolist(), order=3)
+    r, c = coords
+    safe = (r > 1e-9) & (r < H - 1 - 1e-9) & (c > 1e-9) & (c < W - 1 - 1e-9)
+    outside = (r < -1e-9) | (r > H - 1 + 1e-9) | (c < -1e-9) | (c > W - 1 + 1e-9)
+    d = np.abs(got.astype(int) - ref.astype(int)).max(axis=-1)
+    # coordinates agree to ~1e-12 (different summation order / log): at most a rounding tie away
+    assert d[safe].max() <= 1 and (d[safe] > 0).mean() < 1e-3
+    assert d[outside].max() == 0 and (safe | outside).mean() > 0.99
+    assert (got != run_tps(img, out_pts.tolist(), in_pts.tolist(), order=1)).mean() > 0.2   # it is not the bilinear path
+
+
 def _page_with_mask(seed, H, W, rgb=False, zero_blocks=False):
     page, boxes = synthetic.page(seed, H, W, rgb=rgb)
     if zero_blocks:

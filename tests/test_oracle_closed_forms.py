@@ -63,3 +63,20 @@ def test_dilate_anchor_convention():
         ys, xs = np.nonzero(d)
         up, down, left, right = ho.dilate_rect_anchor(kw, kh)
         assert (20 - ys.min(), ys.max() - 20, 20 - xs.min(), xs.max() - 20) == (up, down, left, right)
+
+
+def test_spline3_interpolation_restatement_is_scipy_bitwise():
+    """The 4x4-tap cubic B-spline step (weights, mirrored taps, constant-0 outside, summation order) restated in
+    oracle/hostops.py equals scipy.ndimage.map_coordinates(order=3) bit for bit on scipy's own coefficients --
+    this is the arithmetic csrc/lines.cu:sample_cubic_const follows."""
+    import scipy.ndimage as ndi
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53)).astype(np.uint8)
+    coef = ndi.spline_filter(img, 3, output=np.float64, mode="constant")
+    pts = np.stack([rng.uniform(-2, 39, 1500), rng.uniform(-2, 55, 1500)])
+    pts[:, :50] = np.round(pts[:, :50])
+    pts[0, 50:60], pts[1, 60:70], pts[0, 70:80] = 36.0, 52.0, 0.0
+    want = ndi.map_coordinates(img, pts, order=3, mode="constant", cval=0.0, output=np.float64)
+    got = np.array([ho.spline3_interp_numpy(coef, pts[0, k], pts[1, k]) for k in range(pts.shape[1])])
+    assert np.array_equal(got, want)
