@@ -156,8 +156,9 @@ int bdrc_tps_remap_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C,
  * Step 2: sample the coefficients at explicit coordinates (fp64 [2][H][W] = (row, col)) or at the
  * thin-plate-spline image of the output grid (same arguments as bdrc_tps_remap_u8). */
 size_t bdrc_spline3_coef_bytes(int H, int W, int C);
+size_t bdrc_spline3_workspace_bytes(int H, int W, int C);   /* device scratch between the two axes */
 int bdrc_spline3_prefilter_u8(bdrc_ctx* ctx, const uint8_t* src, int H, int W, int C, double* coef,
-                              void* stream);
+                              void* workspace, size_t workspace_bytes, void* stream);
 int bdrc_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C, const double* coords,
                         uint8_t* dst, void* stream);
 int bdrc_tps_remap_cubic_u8(bdrc_ctx* ctx, const double* coef, int H, int W, int C,

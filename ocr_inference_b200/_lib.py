@@ -58,7 +58,9 @@ _SIGS = {
     "bdrc_tps_remap_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "bdrc_spline3_coef_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "bdrc_spline3_prefilter_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "bdrc_spline3_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bdrc_spline3_prefilter_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                          c_void_p]),
     "bdrc_remap_cubic_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "bdrc_tps_remap_cubic_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),

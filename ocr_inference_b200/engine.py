@@ -275,8 +275,9 @@ class Engine:
         Cn = int(img.shape[2]) if img.dim() == 3 else 1
         coef = torch.empty((H, W, Cn), dtype=torch.float64, device=self.device)
         assert coef.numel() * 8 == int(self.lib.bdrc_spline3_coef_bytes(H, W, Cn))
-        self._check(self.lib.bdrc_spline3_prefilter_u8(self.ctx.h, img.data_ptr(), H, W, Cn, coef.data_ptr(), self.stream),
-                    "spline3_prefilter_u8")
+        ws = self._workspace("spline3", int(self.lib.bdrc_spline3_workspace_bytes(H, W, Cn)))
+        self._check(self.lib.bdrc_spline3_prefilter_u8(self.ctx.h, img.data_ptr(), H, W, Cn, coef.data_ptr(),
+                                                       ws.data_ptr(), ws.numel(), self.stream), "spline3_prefilter_u8")
         return coef
 
     def remap_cubic(self, img: torch.Tensor, coords: torch.Tensor) -> torch.Tensor:

@@ -71,7 +71,8 @@ def test_tps_remap_matches_oracle(engine):
     assert d2[safe].max() <= 1 and d2[outside].max() == 0
 
 
-@pytest.mark.parametrize("shape,C", [((240, 320), 3), ((70, 45), 1), ((2, 300), 3), ((130, 3), 1), ((1, 64), 1)])
+@pytest.mark.parametrize("shape,C", [((240, 320), 3), ((70, 45), 1), ((2, 300), 3), ((130, 3), 1), ((1, 64), 1),
+                                     ((700, 900), 3), ((257, 513), 1), ((321, 256), 2)])
 def test_remap_cubic_matches_scipy(engine, shape, C):
     """bdrc_spline3_prefilter_u8 + bdrc_remap_cubic_u8 against scipy.ndimage.map_coordinates with its defaults
     (order 3, prefilter, constant 0): coefficients to a few ulp, samples bit-exact except where the fp64 value sits
