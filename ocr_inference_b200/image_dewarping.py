@@ -131,3 +131,30 @@ def apply_global_tps(image: np.ndarray, line_mask: np.ndarray, line_data: list, 
         raise ValueError("input_pts and output_pts must not be None when tps is True")
     return (run_tps(image, d["output_pts"], d["input_pts"], order=order),
             run_tps(line_mask, d["output_pts"], d["input_pts"], order=order))
+
+
+def get_line_images_via_local_tps(image: np.ndarray, line_data: list, k_factor: float = 1.7, order: int = 1) -> list:
+    """:292-342: one thin-plate-spline dewarp per curved line (page and that line's filled contour), then the
+    shrink-k masked crop of line_detection.get_line_image with bbox_tolerance 2.0; the adapted k carries over
+    to the following lines.  `line_data` is check_for_tps's second result."""
+    from .line_detection import get_line_image
+
+    current_k = k_factor
+    out = []
+    for line in line_data:
+        mask = np.zeros(image.shape[:2], np.uint8)
+        cv2.drawContours(mask, [line["contour"]], -1, (255, 255, 255), -1)
+        _, _, _, bbox_h = cv2.boundingRect(line["contour"])
+        if line["tps"] is True:
+            if line["input_pts"] is None or line["output_pts"] is None:
+                raise ValueError("input_pts and output_pts must not be None when tps is True")
+            img = run_tps(image, line["output_pts"], line["input_pts"], order=order)
+            # run_tps replicates a 1-channel mask to 3 channels (:36-37); get_line_image takes channel 0 of it
+            mask = run_tps(mask, line["output_pts"], line["input_pts"], order=order)[..., 0]
+            line_img, adapted_k = get_line_image(img, mask, bbox_h, bbox_tolerance=2.0, k_factor=current_k)
+            if current_k != adapted_k:
+                current_k = adapted_k
+        else:
+            line_img, _ = get_line_image(image, mask, bbox_h, bbox_tolerance=2.0, k_factor=current_k)
+        out.append(line_img)
+    return out

@@ -124,6 +124,61 @@ def test_tps_remap_cubic_matches_scipy(engine):
     assert (got != run_tps(img, out_pts.tolist(), in_pts.tolist(), order=1)).mean() > 0.2   # it is not the bilinear path
 
 
+@pytest.mark.parametrize("order", [1, 3])
+def test_global_and_local_tps_dewarp_on_a_curved_page(engine, order):
+    """check_for_tps -> apply_global_tps / get_line_images_via_local_tps on a page whose text bands are bent:
+    the dewarped page equals the oracle's TPS restatement resampled by scipy (order 1 or the reference's
+    default order 3); straight lines of the local variant equal get_line_image."""
+    from ocr_inference_b200 import image_dewarping as idw
+    from ocr_inference_b200 import line_detection as ld
+
+    H, W = 700, 1100
+    page, boxes = synthetic.page(41, H, W, n_lines=(4, 4))
+    mask = synthetic.band_mask(boxes, H, W, thin=0.4)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    bend = (yy + 45.0 * np.sin(xx / W * np.pi)).astype(np.float32)
+    page_c = cv2.remap(page, xx, bend, cv2.INTER_LINEAR, borderValue=(215, 215, 215))
+    mask_c = cv2.remap(mask, xx, bend, cv2.INTER_NEAREST)
+    _, mask3, contours, _ = ld.build_raw_line_data(page_c, mask_c)
+    filtered = ld.filter_line_contours(mask3, contours)
+    ratio, data = idw.check_for_tps(page_c, filtered)
+    assert ratio > 0.25 and any(d["tps"] for d in data)
+    d = data[idw.get_global_tps_line(data)]
+    dew_img, dew_mask = idw.apply_global_tps(page_c, np.asarray(mask3), data, order=order)
+    corners = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]) * [H, W]
+    tps = ThinPlateSpline(0.5).fit(np.concatenate([np.asarray(d["output_pts"], float), corners]),
+                                   np.concatenate([np.asarray(d["input_pts"], float), corners]))
+    grid = np.indices((H, W), dtype=np.float64).transpose(1, 2, 0).reshape(-1, 2)
+    coords = tps.transform(grid).reshape(H, W, 2).transpose(2, 0, 1)
+    ref_fn = ho.remap_cubic_ref if order == 3 else ho.remap_bilinear_ref
+    r, c = coords
+    safe = (r > 1e-9) & (r < H - 1 - 1e-9) & (c > 1e-9) & (c < W - 1 - 1e-9)
+    outside = (r < -1e-9) | (r > H - 1 + 1e-9) | (c < -1e-9) | (c > W - 1 + 1e-9)
+    for got, src in ((dew_img, page_c), (dew_mask, np.asarray(mask3))):
+        dd = np.abs(got.astype(int) - ref_fn(src, coords).astype(int)).max(axis=-1)
+        assert dd[safe].max() <= 1 and (dd[safe] > 0).mean() < 1e-3 and dd[outside].max() == 0
+    # the dewarped bands are straighter than the bent ones
+    _, m3d, cd, _ = ld.build_raw_line_data(dew_img, cv2.cvtColor(dew_mask, cv2.COLOR_RGB2GRAY))
+    ratio_after, _ = idw.check_for_tps(dew_img, ld.filter_line_contours(m3d, cd))
+    assert ratio_after <= ratio
+    # local variant: one dewarp per curved line; straight lines are plain get_line_image crops
+    lines = idw.get_line_images_via_local_tps(page_c, data, k_factor=1.7, order=order)
+    assert len(lines) == len(data) and all(im.ndim == 3 and im.shape[0] > 0 for im in lines)
+    k = 1.7
+    for dline, im in zip(data, lines):
+        m = np.zeros((H, W), np.uint8)
+        cv2.drawContours(m, [dline["contour"]], -1, 255, -1)
+        bh = cv2.boundingRect(dline["contour"])[3]
+        if dline["tps"] is True:
+            wi = idw.run_tps(page_c, dline["output_pts"], dline["input_pts"], order=order)
+            wm = idw.run_tps(m, dline["output_pts"], dline["input_pts"], order=order)[..., 0]
+            want, k2 = ld.get_line_image(wi, wm, bh, bbox_tolerance=2.0, k_factor=k)
+            k = k2 if k2 != k else k
+        else:
+            want, _ = ld.get_line_image(page_c, m, bh, bbox_tolerance=2.0, k_factor=k)
+        assert np.array_equal(im, want)
+
+
 def _page_with_mask(seed, H, W, rgb=False, zero_blocks=False):
     page, boxes = synthetic.page(seed, H, W, rgb=rgb)
     if zero_blocks:
