@@ -173,13 +173,17 @@ class Engine:
         meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)
         return tiles, meta
 
-    def seg_tile_rgb(self, page: torch.Tensor, patch: int = PATCH):
-        """torch-path collate (utils.multi_image_collate_fn): fp32 RGB tiles [N,P,P,3] in [0,255]."""
+    def seg_tile_rgb(self, page: torch.Tensor, patch: int = PATCH, out: torch.Tensor | None = None):
+        """torch-path collate (utils.multi_image_collate_fn): fp32 RGB tiles [N,P,P,3] in [0,255].
+        `out` (optional) is a preallocated [N,P,P,3] fp32 slice of a larger tile batch (several images per
+        forward call, as the reference's collate function batches them)."""
         H0, W0 = int(page.shape[0]), int(page.shape[1])
         Hc, Wc = clamp_size_torch(H0, W0, patch)
         page = page.contiguous()
         nty, ntx = math.ceil(Hc / patch), math.ceil(Wc / patch)
-        tiles = torch.empty((nty * ntx, patch, patch, 3), dtype=torch.float32, device=self.device)
+        tiles = out if out is not None else torch.empty((nty * ntx, patch, patch, 3), dtype=torch.float32,
+                                                        device=self.device)
+        assert tuple(tiles.shape) == (nty * ntx, patch, patch, 3) and tiles.is_contiguous()
         self._check(self.lib.bdrc_seg_tile_rgb(self.ctx.h, page.data_ptr(), H0, W0, Hc, Wc, patch,
                                                tiles.data_ptr(), self.stream), "seg_tile_rgb")
         meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)

@@ -735,6 +735,72 @@ class ModernBookFormatLayoutDetection:
         logits = eng.seg_forward(self.model, tiles)
         return eng.seg_postprocess_torch(logits, meta, class_threshold).cpu().numpy()
 
+    def predict_masks_batch(self, images: Sequence[np.ndarray], class_threshold: float = 0.8,
+                            max_tiles: int = 148) -> list[np.ndarray]:
+        """[predict_masks(i) for i in images] with the tiles of several images sharing one forward call -- what
+        the reference's DataLoader + multi_image_collate_fn (utils.py:1142-1172, batch_size images per step) does.
+        Uploads run ahead on a copy stream and masks return through pinned buffers on a third one; images are
+        grouped while their tiles fit `max_tiles` (one 148-tile chunk of the network)."""
+        from .engine import clamp_size_torch
+
+        eng, dev = self.engine, self.engine.device
+        compute = torch.cuda.current_stream(dev)
+        copy_in = getattr(self, "_copy_in", None) or torch.cuda.Stream(dev)
+        copy_out = getattr(self, "_copy_out", None) or torch.cuda.Stream(dev)
+        self._copy_in, self._copy_out = copy_in, copy_out
+        if not hasattr(self, "_host_bufs"):
+            self._host_bufs = {}
+        n_tiles = []
+        for img in images:
+            Hc, Wc = clamp_size_torch(int(img.shape[0]), int(img.shape[1]), 512)
+            n_tiles.append((-(-Hc // 512)) * (-(-Wc // 512)))
+        ups, evs = [], []
+        copy_in.wait_stream(compute)
+        with torch.cuda.stream(copy_in):
+            for img in images:
+                d = torch.from_numpy(np.ascontiguousarray(img[..., :3], dtype=np.uint8)).to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+                ups.append(d)
+                evs.append(ev)
+        outs: list = [None] * len(images)
+        i = 0
+        while i < len(images):
+            j, tot = i, 0
+            while j < len(images) and (j == i or tot + n_tiles[j] <= max_tiles):
+                tot += n_tiles[j]
+                j += 1
+            for k in range(i, j):
+                compute.wait_event(evs[k])
+                ups[k].record_stream(compute)
+            tiles = torch.empty((tot, 512, 512, 3), dtype=torch.float32, device=dev)
+            metas, o = [], 0
+            for k in range(i, j):
+                _, meta = eng.seg_tile_rgb(ups[k], out=tiles[o:o + n_tiles[k]])
+                metas.append(meta)
+                o += n_tiles[k]
+            logits = eng.seg_forward(self.model, tiles)
+            o, masks = 0, []
+            for k, meta in zip(range(i, j), metas):
+                masks.append(eng.seg_postprocess_torch(logits[o:o + n_tiles[k]], meta, class_threshold))
+                o += n_tiles[k]
+            done = torch.cuda.Event()
+            done.record(compute)
+            copy_out.wait_event(done)
+            with torch.cuda.stream(copy_out):
+                for k, m in zip(range(i, j), masks):
+                    key = (k, tuple(m.shape))
+                    h = self._host_bufs.get(key)
+                    if h is None:
+                        h = self._host_bufs[key] = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
+                    h.copy_(m, non_blocking=True)
+                    m.record_stream(copy_out)
+                    outs[k] = h
+            i = j
+        copy_out.synchronize()
+        compute.synchronize()
+        return [o.numpy().copy() for o in outs]
+
     def post_process_sample(self, prediction: np.ndarray, class_index: int):
         import cv2
 
@@ -770,7 +836,9 @@ class ModernBookFormatLayoutDetection:
                     raise ValueError(f"ERROR: provided filter classes: {filter_classes} are not part of the model's classes!")
         os.makedirs(output_dir, exist_ok=True)
         paths = sorted(p for p in glob(os.path.join(directory, "*")) if p.lower().endswith((".jpg", ".png", ".jpeg")))
-        for p in paths:
-            img = cv2.cvtColor(cv2.imread(p, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
-            masks = self.predict_masks(img, class_threshold)
-            self.extract_json_data({"image_name": os.path.basename(p)}, masks, filter_classes, output_dir)
+        step = max(1, int(batch_size))
+        for b0 in range(0, len(paths), step):
+            chunk = paths[b0:b0 + step]
+            imgs = [cv2.cvtColor(cv2.imread(p, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for p in chunk]
+            for p, masks in zip(chunk, self.predict_masks_batch(imgs, class_threshold)):
+                self.extract_json_data({"image_name": os.path.basename(p)}, masks, filter_classes, output_dir)

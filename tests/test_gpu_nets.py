@@ -127,6 +127,25 @@ def test_ocr_forward_and_decode(engine, conv_engine):
     print("identical decoded lines:", same, "of", len(crops), "; safe steps:", safe.mean())
 
 
+def test_modern_layout_batch_equals_per_image(engine):
+    """predict_masks_batch (tiles of several images in one forward call, mixed page sizes incl. the clamp
+    branches) returns exactly what predict_masks returns image by image."""
+    from ocr_inference_b200.data import LayoutDetectionConfig
+    from ocr_inference_b200.inference import ModernBookFormatLayoutDetection
+
+    classes = ["background", "image", "line", "caption", "margin"]
+    det = ModernBookFormatLayoutDetection(LayoutDetectionConfig(nets.seg_weights(13, 5, 3), "", "deeplabv3plus", 512, classes),
+                                          engine=engine)
+    sizes = [(472, 1300), (700, 1100), (1024, 1536), (2300, 1200), (400, 4300), (600, 600)]
+    pages = [synth.page(4100 + i, h, w, rgb=True)[0] for i, (h, w) in enumerate(sizes)]
+    want = [det.predict_masks(p, 0.8) for p in pages]
+    for max_tiles in (148, 8):
+        got = det.predict_masks_batch(pages, 0.8, max_tiles=max_tiles)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w)
+
+
 def test_modern_layout_run_writes_json(engine, tmp_path):
     """ModernBookFormatLayoutDetection.run (config C4): directory of images -> per-image bbox JSON,
     masks equal to the oracle's torch-path post-processing of the oracle logits away from ties."""
