@@ -46,26 +46,28 @@ struct SrcPageTiles {
     const int g = (p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + 16384) >> 15;
     return (float)g;
   }
-  // four horizontally adjacent pixels x .. x+3 of one tile row (x % 4 == 0, all inside the tile): three
-  // 32-bit loads instead of twelve byte loads.  Returns false where the caller must go pixel by pixel
-  // (quad straddling the page edge, or a row that is not 4-byte aligned).
-  __device__ __forceinline__ bool gray4(int img, int y, int x, float* v) const {
+  // four horizontally adjacent pixels x .. x+3 of one tile row (x % 4 == 0, all inside the tile) as raw words:
+  // three 32-bit loads instead of twelve byte loads.  Returns 1 (raw holds the 12 RGB bytes), 2 (all four
+  // pixels lie in the 255 padding) or 0 where the caller must go pixel by pixel (quad straddling the page
+  // edge, or a row that is not 4-byte aligned).  conv4 turns the raw words into gray values.
+  static constexpr int WORDS = 3;
+  __device__ __forceinline__ int load4(int img, int y, int x, uint32_t* raw) const {
     const int ty = img / ntx, tx = img - ty * ntx;
     const int py = ty * patch + y, px = tx * patch + x;
-    if (py >= Hc || px >= Wc) {
-      v[0] = v[1] = v[2] = v[3] = 255.f;
-      return true;
-    }
+    if (py >= Hc || px >= Wc) return 2;
     const uint8_t* p = page + ((size_t)py * Wc + px) * 3;
-    if (px + 3 >= Wc || (reinterpret_cast<uintptr_t>(p) & 3)) return false;
+    if (px + 3 >= Wc || (reinterpret_cast<uintptr_t>(p) & 3)) return 0;
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    raw[0] = __ldg(q); raw[1] = __ldg(q + 1); raw[2] = __ldg(q + 2);
+    return 1;
+  }
+  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v) const {
+    const uint32_t w0 = raw[0], w1 = raw[1], w2 = raw[2];
     // bytes: w0 = r0 g0 b0 r1, w1 = g1 b1 r2 g2, w2 = b2 r3 g3 b3 (little endian)
     v[0] = (float)(int)(((w0 & 255u) * 9798u + ((w0 >> 8) & 255u) * 19235u + ((w0 >> 16) & 255u) * 3735u + 16384u) >> 15);
     v[1] = (float)(int)(((w0 >> 24) * 9798u + (w1 & 255u) * 19235u + ((w1 >> 8) & 255u) * 3735u + 16384u) >> 15);
     v[2] = (float)(int)((((w1 >> 16) & 255u) * 9798u + (w1 >> 24) * 19235u + (w2 & 255u) * 3735u + 16384u) >> 15);
     v[3] = (float)(int)((((w2 >> 8) & 255u) * 9798u + ((w2 >> 16) & 255u) * 19235u + (w2 >> 24) * 3735u + 16384u) >> 15);
-    return true;
   }
 };
 
@@ -78,12 +80,16 @@ struct SrcGrayBatch {
   __device__ __forceinline__ float gray(int i, int y, int x) const {
     return (float)img[((size_t)i * H + y) * W + x];
   }
-  __device__ __forceinline__ bool gray4(int i, int y, int x, float* v) const {
+  static constexpr int WORDS = 1;
+  __device__ __forceinline__ int load4(int i, int y, int x, uint32_t* raw) const {
     const uint8_t* p = img + ((size_t)i * H + y) * W + x;
-    if (reinterpret_cast<uintptr_t>(p) & 3) return false;
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    if (reinterpret_cast<uintptr_t>(p) & 3) return 0;
+    raw[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return 1;
+  }
+  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v) const {
+    const uint32_t w = raw[0];
     v[0] = (float)(w & 255u); v[1] = (float)((w >> 8) & 255u); v[2] = (float)((w >> 16) & 255u); v[3] = (float)(w >> 24);
-    return true;
   }
 };
 
@@ -136,7 +142,7 @@ struct SinkOcrLines {
 };
 
 template <class Src, class Sink>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int strips_x) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* g = reinterpret_cast<float*>(smem_raw);                 // [RB][GSTRIDE]  staged gray block
@@ -149,21 +155,43 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
   const int x0 = sx * SW;
   const int n_blocks = (IH + RB - 1) / RB;
 
-  for (int b = 0; b < n_blocks + 2; ++b) {
-    // ---- stage gray rows [RB*b, RB*b + RB) x columns [x0 - KR, x0 + SW + KR), clamped to the image ----
-    // (prefetching the next block into registers during the filter passes was tried: 128 registers, 2 CTAs
-    //  per SM, 0.197 ms per page against 0.130 ms for this version -- the kernel is bound by shared-memory
-    //  load latency at 3 CTAs per SM, ncu: 58 % of stalls are short-scoreboard, issue slots 36 % busy)
-    if (b < n_blocks) {
-      // four pixels per item: tile columns x0 - 28 + 4q .. + 3 (a 4-aligned superset of the 82 staged columns),
-      // staged column c = 4q - 3 + j; quads 7 .. 14 are the strip itself
-      constexpr int NQ = (GW + 3 + 3) / 4;   // 22
-      for (int i = threadIdx.x; i < RB * NQ; i += THREADS) {
+  // Staging works on quads: tile columns x0 - 28 + 4q .. + 3 (a 4-aligned superset of the 82 staged columns),
+  // staged column c = 4q - 3 + j; quads 7 .. 14 are the strip itself.  The raw words of block b + 1 are loaded
+  // into registers BEFORE the filter passes of block b and converted / stored after them, so the global-load
+  // latency (the top stall of the previous version: long scoreboard) hides behind ~100 FMAs per pixel.
+  constexpr int NQ = (GW + 3 + 3) / 4;                       // 22
+  constexpr int ITEMS = RB * NQ;                             // 704
+  constexpr int NIT = (ITEMS + THREADS - 1) / THREADS;       // 3
+  uint32_t raw[NIT][Src::WORDS];
+  uint32_t mode = 0;                                         // 2 bits per item: 0 slow, 1 raw words, 2 constant 255
+  auto prefetch = [&](int blk) {
+    mode = 0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * THREADS;
+      if (i < ITEMS) {
         const int r = i / NQ, q = i - r * NQ;
-        const int y = min(RB * b + r, IH - 1);
+        const int y = min(RB * blk + r, IH - 1);
         const int xq = x0 - 28 + 4 * q;
+        if (xq >= 0 && xq + 3 < IW) mode |= (uint32_t)src.load4(img, y, xq, raw[it]) << (2 * it);
+      }
+    }
+  };
+  auto commit = [&](int blk) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = threadIdx.x + it * THREADS;
+      if (i < ITEMS) {
+        const int r = i / NQ, q = i - r * NQ;
+        const int xq = x0 - 28 + 4 * q;
+        const uint32_t m = (mode >> (2 * it)) & 3u;
         float v[4];
-        if (!(xq >= 0 && xq + 3 < IW && src.gray4(img, y, xq, v))) {
+        if (m == 1u) {
+          src.conv4(raw[it], v);
+        } else if (m == 2u) {
+          v[0] = v[1] = v[2] = v[3] = 255.f;
+        } else {
+          const int y = min(RB * blk + r, IH - 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = src.gray(img, y, min(max(xq + j, 0), IW - 1));
         }
@@ -172,11 +200,18 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         for (int j = 0; j < 4; ++j)
           if (4 * q - 3 + j >= 0 && 4 * q - 3 + j < GW) gr[j] = v[j];
         if (q >= 7 && q < 7 + SW / 4)
-          *reinterpret_cast<uint32_t*>(gc + ((RB * b + r) & (RING - 1)) * SW + 4 * (q - 7)) =
+          *reinterpret_cast<uint32_t*>(gc + ((RB * blk + r) & (RING - 1)) * SW + 4 * (q - 7)) =
               (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
       }
     }
+  };
+  if (n_blocks > 0) prefetch(0);
+
+  for (int b = 0; b < n_blocks + 2; ++b) {
+    // ---- stage gray rows [RB*b, RB*b + RB) x columns [x0 - KR, x0 + SW + KR), clamped to the image ----
+    if (b < n_blocks) commit(b);
     __syncthreads();
+    if (b + 1 < n_blocks) prefetch(b + 1);
 
     // ---- row pass of block b: ring[row][c] = sum_k g[row][c + k] * w[k], k ascending, FMA ----
     if (b < n_blocks) {
