@@ -43,6 +43,19 @@ def test_trained_recogniser_identical_decoded_lines(engine):
     print(f"identical decoded lines GPU vs oracle: {same}/48; equal to the ground-truth transcription: {right}/48; "
           f"oracle top-2 margin / logit std: median {np.median(margin) / ref_logits.std():.2f}")
     assert same >= 46, f"only {same}/48 decoded lines identical to the CPU oracle"
+    # every per-step argmax difference sits on a near-tie of the oracle: top-2 margin inside the bf16 tolerance
+    dev, hw, off = engine.pack_crops(crops)
+    lines, _ = engine.ocr_prepare_lines(dev, hw, off, 48, 80, 2000, False)
+    g = engine.ocr_forward(ocr.ocr_session, lines).cpu().numpy()                  # [48, T, V]
+    r = ref_logits.transpose(0, 2, 1)
+    diff = g.argmax(-1) != r.argmax(-1)
+    top = np.sort(r, axis=-1)
+    tol = 0.08 * r.std() + 0.05 * np.abs(top[..., -1])
+    outside = diff & ((top[..., -1] - top[..., -2]) > tol)
+    print(f"per-step argmax differences: {int(diff.sum())} of {diff.size}, outside the tolerance: {int(outside.sum())}; "
+          f"largest oracle margin among them {float((top[..., -1] - top[..., -2])[diff].max()) if diff.any() else 0.0:.4f} "
+          f"(logit std {r.std():.3f})")
+    assert not outside.any()
     texts = ocr.run_batch(crops[:4], pre_pad=False)     # index -> character map (inference.py:108-112)
     assert texts == ["".join(synth.CHARSET_76[i - 1] for i in g) for g in got[:4]]
 
