@@ -169,6 +169,43 @@ def cpu_reference_pages_per_sec(n_pages: int, steps: int = 1, warmup: int = 0):
     return n_pages * steps / dt, dt / steps, cores
 
 
+def cpu_reference_page_to_text(page, gpu_result):
+    """The oracle's whole page -> text pipeline (tile/binarise, torch-CPU fp32 DeepLabV3+ with the fitted head,
+    mask, the reference's cv2/numpy line extraction, line prep, torch-CPU Easter2, greedy CTC) on ONE page, on all
+    host cores, beside the GPU pipeline's result for the same page."""
+    import cv2
+    import torch
+
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.data import OpStatus
+    from ocr_inference_b200.synthetic_weights import easter2_weights_fitted, seg_weights_fitted
+    from oracle import geometry as og
+    from oracle import hostops as ho
+    from oracle import nets
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cv2.setNumThreads(-1)
+    ws, we = seg_weights_fitted(11), easter2_weights_fitted()
+    t0 = time.perf_counter()
+    tiles, meta = ho.seg_preprocess(page, closed_form=False)
+    x = np.repeat(tiles[:, None].astype(np.float32), 3, axis=1)
+    logits = np.concatenate([nets.seg_forward(ws, x[i:i + 8]) for i in range(0, len(x), 8)])
+    mask = ho.line_postprocess(logits, meta, 0.9, closed_form=False)
+    r = og.page_to_lines(page, mask, 2.0, 2.5)
+    texts = [] if isinstance(r, str) else og.recognise(r[2], we, synthetic.CHARSET_76)[0]
+    dt = time.perf_counter() - t0
+    out = {"value": 1.0 / dt, "unit": "pages/s", "lines_per_sec": len(texts) / dt, "cores": cores, "kind": "port",
+           "sample": "1 of the pages: oracle/ page -> text (cv2/numpy host code of the reference restated, torch-CPU fp32 "
+                     "networks), all host threads", "seconds_per_page": dt, "lines": len(texts)}
+    if gpu_result[0] == OpStatus.SUCCESS:
+        got = [l.text for l in gpu_result[1][2]]
+        want = [t.strip().replace("\u00a7", " ") for t in texts]
+        out["gpu_lines"] = len(got)
+        out["gpu_lines_identical_to_cpu_oracle"] = sum(a == b for a, b in zip(got, want)) if len(got) == len(want) else None
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -336,7 +373,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     return out
 
 
-def bench_c3(eng, steps: int, pages_per_step: int = 32, workers: int = 2):
+def bench_c3(eng, steps: int, pages_per_step: int = 32, workers: int = 2, with_cpu: bool = False):
     """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (host numpy in, OCRLine text out)."""
     from ocr_inference_b200 import synthetic
     from ocr_inference_b200.data import LineDetectionConfig, OpStatus
@@ -360,7 +397,11 @@ def bench_c3(eng, steps: int, pages_per_step: int = 32, workers: int = 2):
     want = [{"".join(synthetic.CHARSET_76[i] for i in t).strip().replace("§", " ") for t in base[i % 4][2]}
             for i in range(pages_per_step)]
     n_right = sum(sum(l.text in want[i] for l in r[1][2]) for i, r in enumerate(res) if r[0] == OpStatus.SUCCESS)
+    cpu = None
+    if with_cpu:
+        cpu = cpu_reference_page_to_text(base[0][0], res[0])
     return {
+        **({"cpu_baseline": cpu} if cpu else {}),
         "workload": f"C3: {pages_per_step} synthetic 2048x3072 text pages per step through OCRPipeline.run_ocr_batch "
                     "(staged: pages grouped 6 at a time through tile/binarise + DeepLabV3+ with fitted head + mask, cv2 "
                     "contours + reading order on host threads, GPU line crops, all lines of the batch through line prep + "
@@ -617,7 +658,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and args.extras:
         try:
             extras["c1"] = bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline)
-            extras["c3"] = bench_c3(eng, 2)
+            extras["c3"] = bench_c3(eng, 2, with_cpu=args.cpu_baseline)
             extras["c4"] = bench_c4(eng)
             nproc = max(2, min(8, len(os.sched_getaffinity(0)) // 2))
             extras["c3"]["multi_process"] = bench_c3_procs(local_rank, nproc, threads=1)
