@@ -373,7 +373,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     return out
 
 
-def bench_c3(eng, steps: int, pages_per_step: int = 32, workers: int = 2, with_cpu: bool = False):
+def bench_c3(eng, steps: int, pages_per_step: int = 48, workers: int | None = None, with_cpu: bool = False):
     """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (host numpy in, OCRLine text out)."""
     from ocr_inference_b200 import synthetic
     from ocr_inference_b200.data import LineDetectionConfig, OpStatus
@@ -400,14 +400,16 @@ def bench_c3(eng, steps: int, pages_per_step: int = 32, workers: int = 2, with_c
     cpu = None
     if with_cpu:
         cpu = cpu_reference_page_to_text(base[0][0], res[0])
+    n_geo = len(getattr(pipe, "_gpool", None) or [])
+    pipe.close()
     return {
         **({"cpu_baseline": cpu} if cpu else {}),
         "workload": f"C3: {pages_per_step} synthetic 2048x3072 text pages per step through OCRPipeline.run_ocr_batch "
                     "(staged: pages grouped 6 at a time through tile/binarise + DeepLabV3+ with fitted head + mask, cv2 "
-                    "contours + reading order on host threads, GPU line crops, all lines of the batch through line prep + "
-                    "Easter2 + greedy CTC in one call)",
+                    "contours + reading order in geometry worker processes (no CUDA in them), GPU line crops, all lines of "
+                    "the batch through line prep + Easter2 + greedy CTC in one call; ONE CUDA context)",
         "e2e_pages_per_sec": pages_per_step / dt, "e2e_lines_per_sec": n_lines / dt, "ms_per_page": dt * 1e3 / pages_per_step,
-        "host_threads": workers, "pages_ok": len(ok), "lines_found": n_lines, "lines_on_pages": n_truth,
+        "host_threads": workers, "geometry_processes": n_geo, "pages_ok": len(ok), "lines_found": n_lines, "lines_on_pages": n_truth,
         "lines_equal_to_truth": n_right,
         "note": "host-bound: cv2.findContours + reading-order Python (SURVEY 8(a)-10) take ~15-20 ms/page/core on the noisy "
                 "masks of the fitted head (~750 contours per page); GPU stages ~3 ms/page",
@@ -473,13 +475,13 @@ def _c3_worker(rank, n_workers, device, pages_per_worker, steps, threads, barrie
         base = [synthetic.text_page(3003 + (rank * 2 + i) % 4) for i in range(2)]
         pages = [base[i % 2][0] for i in range(pages_per_worker)]
         kw = dict(k_factor=2.0, bbox_tolerance=2.5)
-        pipe.run_ocr_batch(pages[:max(2, threads)], workers=threads, **kw)
+        pipe.run_ocr_batch(pages[:max(2, threads)], workers=threads, geometry_procs=0, **kw)
         torch.cuda.synchronize()
         barrier.wait()
         t0 = time.perf_counter()
         n_lines = n_ok = 0
         for _ in range(steps):
-            for st, res in pipe.run_ocr_batch(pages, workers=threads, **kw):
+            for st, res in pipe.run_ocr_batch(pages, workers=threads, geometry_procs=0, **kw):
                 if st == OpStatus.SUCCESS:
                     n_ok += 1
                     n_lines += len(res[2])

@@ -482,7 +482,7 @@ class OCRPipeline:
             return OpStatus.FAILED, f"OCR pipeline failed: {str(e)}"
 
     def run_ocr_batch(self, images: Sequence[np.ndarray], workers: int | None = None, staged: bool = True,
-                      chunk_pages: int = 48, **kw):
+                      chunk_pages: int = 48, geometry_procs: int | None = None, **kw):
         """Pages are independent units: same results as [run_ocr(i, **kw) for i in images].
 
         staged=True (default) runs the stages of run_ocr across pages instead of page by page:
@@ -491,7 +491,14 @@ class OCRPipeline:
         extraction of one page each on their own CUDA stream while the next group is in the network, and
         the recogniser reads the crops of ALL pages of a chunk as one batch.  Batching is exact (per-tile
         and per-line reductions only), so the result equals the page-by-page one.  staged=False keeps the
-        page-per-thread schedule."""
+        page-per-thread schedule.
+
+        `geometry_procs` > 0 moves the cv2 geometry of the staged schedule (contours, reading order, ROI masks:
+        line_detection.page_geometry) into that many worker PROCESSES (geometry_pool.GeometryPool; no CUDA in
+        them, masks through shared memory), which is what lets one GPU-owning process go past ~120 pages/s;
+        None = 8 (half the cores at most) once a call brings at least 16 pages, 0 = threads only.  Like any
+        `spawn`-based pool it needs the caller's script to be import-safe (`if __name__ == "__main__":`)."""
+        workers_given = workers
         if workers is None:
             # measured on a 16-core B200 host: 2 geometry threads beside the launching and the upload thread are
             # the best staged schedule (120 pages/s; 4: 71), 4 page threads the best page-by-page one (113)
@@ -499,9 +506,12 @@ class OCRPipeline:
         if len(images) <= 1 or kw.get("eval_mode") or not self.ready:
             return [self.run_ocr(img, **kw) for img in images]
         if staged:
+            gpool = self._geometry_pool(geometry_procs, len(images)) if not kw.get("use_tps") else None
+            if gpool is not None and workers_given is None:
+                workers = len(gpool)            # these threads mostly wait for their page's geometry
             out = []
             for c0 in range(0, len(images), chunk_pages):
-                out.extend(self._run_ocr_staged(images[c0:c0 + chunk_pages], workers, **kw))
+                out.extend(self._run_ocr_staged(images[c0:c0 + chunk_pages], workers, gpool, **kw))
             return out
         if workers <= 1:
             return [self.run_ocr(img, **kw) for img in images]
@@ -517,13 +527,49 @@ class OCRPipeline:
 
         return list(self._thread_pool(workers).map(one, images))
 
+    def _geometry_pool(self, procs: int | None, n_images: int):
+        """The GeometryPool of this pipeline (started on first use, kept for later calls), or None."""
+        have = getattr(self, "_gpool", None)
+        if procs == 0 or have is False:
+            return None
+        if procs is None:
+            if have is not None:
+                return have
+            if n_images < 16:
+                return None
+            procs = max(2, min(8, len(os.sched_getaffinity(0)) // 2))
+        if have is not None and len(have) == procs:
+            return have
+        from .geometry_pool import GeometryPool
+
+        if have is not None:
+            have.close()
+        try:
+            self._gpool = GeometryPool(procs)
+        except Exception as e:  # noqa: BLE001  (e.g. a caller script that is not import-safe under `spawn`)
+            print(f"geometry worker processes unavailable ({e}); using threads")
+            self._gpool = False
+            return None
+        return self._gpool
+
+    def close(self):
+        """Stops the geometry worker processes and the page threads of run_ocr_batch."""
+        g = getattr(self, "_gpool", None)
+        if g:
+            g.close()
+        self._gpool = None
+        p = getattr(self, "_pool", None)
+        if p is not None:
+            p.shutdown(wait=False)
+            self._pool = None
+
     def _thread_pool(self, workers: int) -> ThreadPoolExecutor:
         pool = getattr(self, "_pool", None)
         if pool is None or pool._max_workers != workers:
             pool = self._pool = ThreadPoolExecutor(workers, thread_name_prefix="bdrc-page")
         return pool
 
-    def _run_ocr_staged(self, images, workers: int, k_factor: float = 2.5, bbox_tolerance: float = 4.0,
+    def _run_ocr_staged(self, images, workers: int, gpool=None, k_factor: float = 2.5, bbox_tolerance: float = 4.0,
                         merge_lines: bool = True, use_tps: bool = False, tps_threshold: float = 0.25,
                         target_encoding: Encoding = Encoding.UNICODE, eval_mode: bool = False):
         """One chunk of pages through the staged schedule (see run_ocr_batch).  A page on which any
@@ -576,7 +622,9 @@ class OCRPipeline:
         def page_stage(i: int, mask_host: np.ndarray, mask_ev: torch.cuda.Event):
             if not hasattr(tls, "stream"):
                 torch.cuda.set_device(dev)
-                tls.stream = torch.cuda.Stream(dev)
+                # high priority: the small extraction kernels of a page go ahead of the next conv launch of the
+                # segmentation group that is in flight, instead of queueing behind the whole forward
+                tls.stream = torch.cuda.Stream(dev, priority=-1)
             tls.fast = True
             try:
                 with torch.cuda.stream(tls.stream):
@@ -584,20 +632,39 @@ class OCRPipeline:
                     image = images[i]
                     line_mask = mask_host if layout_ch is None else mask_host[:, :, layout_ch]
                     det._tls.last = (image, pages_dev[i])
-                    status, res = self.build_lines(image, line_mask)
-                    if status == OpStatus.FAILED:
-                        return status, res
-                    rot_img, rot_mask, _, filtered, page_angle = res
-                    status, dew = self.apply_dewarping(rot_img, rot_mask, filtered, page_angle, use_tps=use_tps,
-                                                       tps_threshold=tps_threshold)
-                    if status == OpStatus.FAILED:
-                        return status, dew
-                    status, res = self.extract_lines(dew.work_img, rot_mask, dew.filtered_contours,
-                                                     merge_lines=merge_lines, k_factor=k_factor,
-                                                     bbox_tolerance=bbox_tolerance)
-                    if status == OpStatus.FAILED:
-                        return status, res
-                    sorted_lines, line_images = res
+                    geo = gpool.submit(line_mask, merge_lines).result() if gpool is not None else None
+                    if geo is not None and geo[0] == "failed":
+                        return OpStatus.FAILED, geo[1]
+                    if geo is not None and geo[0] == "ok":
+                        # stages 2-4 with the geometry done by a worker process (no rotation, no dewarping)
+                        import cv2
+
+                        from .data import BBox
+                        from .line_detection import extract_line_images
+
+                        _, page_angle, lines, rois, masks, hs = geo
+                        rot_mask = cv2.cvtColor(np.ascontiguousarray(line_mask), cv2.COLOR_GRAY2RGB)
+                        sorted_lines = [Line(g, c, BBox(*bb), ctr) for g, c, bb, ctr in lines]
+                        line_images = extract_line_images(image, sorted_lines, k_factor, bbox_tolerance,
+                                                          page_dev=pages_dev[i], download=False,
+                                                          _rois=(rois, masks, hs))
+                        if not line_images:
+                            return OpStatus.FAILED, "No valid line images extracted"
+                    else:       # threads only, or a page that has to be rotated first (GPU work)
+                        status, res = self.build_lines(image, line_mask)
+                        if status == OpStatus.FAILED:
+                            return status, res
+                        rot_img, rot_mask, _, filtered, page_angle = res
+                        status, dew = self.apply_dewarping(rot_img, rot_mask, filtered, page_angle, use_tps=use_tps,
+                                                           tps_threshold=tps_threshold)
+                        if status == OpStatus.FAILED:
+                            return status, dew
+                        status, res = self.extract_lines(dew.work_img, rot_mask, dew.filtered_contours,
+                                                         merge_lines=merge_lines, k_factor=k_factor,
+                                                         bbox_tolerance=bbox_tolerance)
+                        if status == OpStatus.FAILED:
+                            return status, res
+                        sorted_lines, line_images = res
                     keep_idx = [j for j, im in enumerate(line_images) if im.shape[0] != 0 and im.shape[1] != 0]
                     pack = getattr(line_images, "device_pack", None)
                     if pack is None or list(pack[3]) != keep_idx or len(line_images) != len(sorted_lines):

@@ -175,6 +175,37 @@ def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold:
     return out_img, mask3, contours, angle
 
 
+def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold: float = 0.5):
+    """Everything between the line mask and the GPU line extraction that needs no pixels of the page and no GPU
+    (build_raw_line_data without rotation, filter_line_contours, build_line_data, sort_lines_by_threshold2 and
+    the filled-contour ROI masks of extract_line_images), as ONE picklable call for a geometry worker process
+    (geometry_pool.py).  Returns
+      ("rotate",)                      the page needs rotating (angle > rot_threshold): GPU work, caller's job
+      ("failed", message)              the reference's stage-2 failure messages (inference.py:521-528)
+      ("ok", angle, lines, rois, masks, hs)   lines = [(guid, contour, (x, y, w, h), center)] in reading order
+    """
+    rows = RowCompaction(line_mask)
+    found = get_contours_compact(line_mask, rows)
+    areas = [cv2.contourArea(c) for c in found]
+    angle = get_rotation_angle_from_lines(line_mask, _contours=found, _areas=areas)
+    if angle > rot_threshold:
+        return ("rotate",)
+    contours = [c for c, a in zip(found, areas) if a > 10]
+    if len(contours) == 0:
+        return ("failed", "No lines detected")
+    filtered = filter_line_contours(line_mask, contours)
+    if len(filtered) == 0:
+        return ("failed", "No valid lines after filtering")
+    line_data = [build_line_data(c) for c in filtered]
+    linked = line_mask.view(Mask3)          # lets get_line_threshold reuse the row compaction
+    linked.gray, linked.rows = line_mask, rows
+    sorted_lines, _ = sort_lines_by_threshold2(linked, line_data, group_lines=merge_lines)
+    H, W = line_mask.shape[:2]
+    rois, masks, hs = line_rois(sorted_lines, H, W)
+    lines = [(ln.guid, ln.contour, (ln.bbox.x, ln.bbox.y, ln.bbox.w, ln.bbox.h), ln.center) for ln in sorted_lines]
+    return ("ok", angle, lines, rois, masks, hs)
+
+
 def filter_line_contours(image: np.ndarray, line_contours, threshold: float = 0.01) -> list:
     """:247-264: keep contours wider than `threshold` of the page and taller than 10 px."""
     keep = []
@@ -415,23 +446,30 @@ def _extract_on_device(page_dev: torch.Tensor, rois, masks, bbox_hs, default_k: 
     return chosen, real, crops_dev, hw, off, C
 
 
-def extract_line_images(image: np.ndarray, line_data: list[Line], default_k: float = 1.7,
-                        bbox_tolerance: float = 3, page_dev: torch.Tensor | None = None,
-                        download: bool = True) -> LineImages:
-    """:330-359.  `page_dev` (optional) is the same image already resident on the GPU; with
-    download=False the crops stay on the device (DeviceCrop placeholders) for the recogniser."""
-    eng = _engine()
-    if image.ndim == 2:
-        image = image[..., None]
-    if page_dev is None:
-        page_dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
-    H, W = image.shape[:2]
+def line_rois(line_data: list[Line], H: int, W: int):
+    """Filled-contour ROI masks of the lines (the host half of extract_line_images): (rois, masks, bbox heights)."""
     rois, masks, hs = [], [], []
     for ln in line_data:
         roi, m, h = _roi_mask(ln.contour, H, W)
         rois.append(roi)
         masks.append(m)
         hs.append(h)
+    return rois, masks, hs
+
+
+def extract_line_images(image: np.ndarray, line_data: list[Line], default_k: float = 1.7,
+                        bbox_tolerance: float = 3, page_dev: torch.Tensor | None = None,
+                        download: bool = True, _rois=None) -> LineImages:
+    """:330-359.  `page_dev` (optional) is the same image already resident on the GPU; with
+    download=False the crops stay on the device (DeviceCrop placeholders) for the recogniser.
+    `_rois` (internal): line_rois(line_data, H, W) when a geometry worker already rasterised them."""
+    eng = _engine()
+    if image.ndim == 2:
+        image = image[..., None]
+    if page_dev is None:
+        page_dev = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(eng.device)
+    H, W = image.shape[:2]
+    rois, masks, hs = _rois if _rois is not None else line_rois(line_data, H, W)
     chosen, real, crops_dev, hw, off, C = _extract_on_device(page_dev, rois, masks, hs, default_k, bbox_tolerance)
     out = LineImages()
     host = {}

@@ -166,11 +166,13 @@ def test_run_ocr_batch_staged_equals_page_by_page(engine):
     kw = dict(k_factor=2.0, bbox_tolerance=2.5)
     want = [pipe.run_ocr(p, **kw) for p in pages]
     assert sum(w[0] == OpStatus.SUCCESS for w in want) >= 7
-    for workers, chunk in ((4, 48), (2, 4), (1, 3)):
-        got = pipe.run_ocr_batch(pages, workers=workers, chunk_pages=chunk, **kw)
+    for workers, chunk, gprocs in ((4, 48, 0), (2, 4, 0), (1, 3, 0), (None, 48, 2), (3, 5, 2)):
+        got = pipe.run_ocr_batch(pages, workers=workers, chunk_pages=chunk, geometry_procs=gprocs, **kw)
         assert len(got) == len(want)
         for g, w in zip(got, want):
             _same_page_result(g, w)
+    assert len(pipe._gpool) == 2
+    pipe.close()
     print("angles:", [w[1][3] if w[0] == OpStatus.SUCCESS else w[1] for w in want])
     torch.cuda.synchronize()
 

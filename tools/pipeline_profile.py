@@ -62,14 +62,16 @@ def main():
         delattr(pipe, name)   # drop the timing wrappers (they synchronise the device)
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     batch = [pages[i % n] for i in range(nb)]
-    for staged, ws in ((False, (1, 4, 6)), (True, (1, 2, 3, 4, 6, 8))):
+    for staged, gp, ws in ((False, 0, (1, 4)), (True, 0, (1, 2, 4)), (True, 4, (4, 8)), (True, 8, (8, 12)), (True, 12, (12,))):
         for workers in ws:
-            pipe.run_ocr_batch(batch, workers=workers, staged=staged)
+            pipe.run_ocr_batch(batch, workers=workers, staged=staged, geometry_procs=gp)
             t0 = time.perf_counter()
-            out = pipe.run_ocr_batch(batch, workers=workers, staged=staged)
+            out = pipe.run_ocr_batch(batch, workers=workers, staged=staged, geometry_procs=gp)
             dt = time.perf_counter() - t0
             nl = sum(len(r[1][2]) for r in out if r[0] == OpStatus.SUCCESS)
-            print(f"run_ocr_batch staged={staged} workers={workers}: {nb / dt:.1f} pages/s, {nl / dt:.0f} lines/s")
+            print(f"run_ocr_batch staged={staged} geometry_procs={gp} workers={workers}: {nb / dt:.1f} pages/s, "
+                  f"{nl / dt:.0f} lines/s", flush=True)
+    pipe.close()
 
 
 if __name__ == "__main__":
