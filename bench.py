@@ -203,7 +203,29 @@ def cpu_reference_page_to_text(page, gpu_result):
         want = [t.strip().replace("\u00a7", " ") for t in texts]
         out["gpu_lines"] = len(got)
         out["gpu_lines_identical_to_cpu_oracle"] = sum(a == b for a, b in zip(got, want)) if len(got) == len(want) else None
+        # whole-page identity is decided by the few mask pixels whose logit sits inside the bf16 tolerance of the
+        # threshold (a different contour polygon -> a crop shifted by a pixel -> another resize phase); report how far
+        # apart the two pipelines actually are: line boxes and character-level agreement
+        if not isinstance(r, str):
+            gb = [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h) for l in gpu_result[1][1]]
+            ob = [tuple(l.bbox) for l in r[1]]
+            out["gpu_line_boxes_identical"] = sum(a == b for a, b in zip(gb, ob)) if len(gb) == len(ob) else None
+            out["gpu_line_boxes_max_abs_diff_px"] = (max(max(abs(p - q) for p, q in zip(a, b)) for a, b in zip(gb, ob))
+                                                     if len(gb) == len(ob) and gb else None)
+        if len(got) == len(want) and got:
+            dist = sum(_edit_distance(a, b) for a, b in zip(got, want))
+            out["gpu_vs_cpu_character_agreement"] = 1.0 - dist / max(1, sum(max(len(a), len(b)) for a, b in zip(got, want)))
     return out
+
+
+def _edit_distance(a: str, b: str) -> int:
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
 
 
 def run_reference(args, rank, world):
@@ -373,7 +395,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     return out
 
 
-def bench_c3(eng, steps: int, pages_per_step: int = 48, workers: int | None = None, with_cpu: bool = False):
+def bench_c3(eng, steps: int, pages_per_step: int = 96, workers: int | None = None, with_cpu: bool = False):
     """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (host numpy in, OCRLine text out)."""
     from ocr_inference_b200 import synthetic
     from ocr_inference_b200.data import LineDetectionConfig, OpStatus

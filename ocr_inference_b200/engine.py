@@ -373,15 +373,17 @@ class Engine:
         return crops, hw, coff
 
     # ---- a-7 -----------------------------------------------------------------------------
-    def pack_crops(self, crops: list[np.ndarray]):
-        """Host list of ragged HWC u8 crops -> (device buffer, hw int32 [L,2], off int64 [L])."""
+    def pack_crops(self, crops: list[np.ndarray], key: str = "crops"):
+        """Host list of ragged HWC u8 crops -> (device buffer, hw int32 [L,2], off int64 [L]).  `key` names the
+        pinned staging buffer: callers that pack several groups per call give each its own, so that packing group
+        k + 1 overlaps the upload of group k."""
         hw = np.array([[c.shape[0], c.shape[1]] for c in crops], dtype=np.int32).reshape(-1, 2)
         sizes = [int(c.shape[0]) * int(c.shape[1]) * 3 for c in crops]
         off = np.zeros(len(crops), dtype=np.int64)
         if len(crops) > 1:
             off[1:] = np.cumsum([(s + 15) // 16 * 16 for s in sizes[:-1]])
         total = int(off[-1] + sizes[-1]) if crops else 0
-        host = self._pinned("crops", total)
+        host = self._pinned(key, total)
         hv = host.numpy()
         # contiguous 3-channel crops go through the native gather (a few threads, GIL released once)
         native = [j for j, c in enumerate(crops) if sizes[j] and c.ndim == 3 and c.shape[2] == 3
@@ -398,8 +400,15 @@ class Engine:
         for j in rest:
             if sizes[j]:
                 hv[off[j]:off[j] + sizes[j]] = np.ascontiguousarray(crops[j][..., :3]).reshape(-1)
-        dev = self._upload("crops", host)
-        return dev, torch.from_numpy(hw).to(self.device), torch.from_numpy(off).to(self.device)
+        dev = self._upload(key, host)
+        # crop geometry rides in its own small pinned buffer: a pageable .to() would synchronise the stream
+        n = len(crops)
+        meta = self._pinned(key + ".meta", 16 * n + 16)
+        mv = meta.numpy()
+        mv[:8 * n].view(np.int32)[:] = hw.reshape(-1)
+        mv[8 * n:16 * n].view(np.int64)[:] = off
+        meta_dev = self._upload(key + ".meta", meta)
+        return dev, meta_dev[:8 * n].view(torch.int32).view(n, 2), meta_dev[8 * n:16 * n].view(torch.int64)
 
     def ocr_prepare_lines(self, crops_dev, hw_dev, off_dev, L: int, Ht: int, Wt: int, pre_pad: bool,
                           want_f32: bool = False, out: torch.Tensor | None = None):
