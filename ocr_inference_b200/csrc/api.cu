@@ -1,5 +1,8 @@
 // Context management and the small C-ABI entry points that are not tied to one stage.
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -87,6 +90,62 @@ int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double*
   return BDRC_OK;
 }
 
+// A few persistent host threads for bdrc_host_gather: starting std::threads per call costs 50-100 us each inside
+// a CUDA process (measured: it ate the whole gain of the parallel copy).  Jobs are index ranges [0, T); the
+// caller runs index 0 itself.  One job at a time (calls from several Python threads queue on `call_`).
+namespace {
+class HostPool {
+ public:
+  static constexpr int kMax = 7;
+  static HostPool& get() {
+    static HostPool* p = new HostPool();   // never destroyed: the workers are detached and die with the process
+    return *p;
+  }
+  void run(int T, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> call(call_);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      total_ = T;
+      next_ = 1;
+      pending_ = T - 1;
+      ++generation_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    for (int i = 0; i < kMax; ++i) std::thread([this] { loop(); }).detach();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      cv_.wait(lk, [&] { return generation_ != seen; });
+      seen = generation_;
+      while (fn_ && next_ < total_) {
+        const int idx = next_++;
+        const std::function<void(int)>* f = fn_;
+        lk.unlock();
+        (*f)(idx);
+        lk.lock();
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::mutex m_, call_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int total_ = 0, next_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+};
+}  // namespace
+
 // Host-side staging: n ragged byte ranges -> one (pinned) buffer, copied by a few native threads.
 // One Python thread packing 64 line crops (19 MB) with numpy runs at memcpy speed of one core (~2 ms);
 // this call releases the GIL once and splits the bytes evenly, so OCRInference.run_batch's upload
@@ -100,7 +159,7 @@ int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_
     total += nbytes[i];
   }
   if (total == 0) return BDRC_OK;
-  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, 16), total / (1 << 20)));
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, HostPool::kMax + 1), total / (1 << 20)));
   auto work = [&](int t) {
     // thread t copies bytes [lo, hi) of the concatenated stream
     const int64_t lo = total * t / T, hi = total * (t + 1) / T;
@@ -117,11 +176,7 @@ int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_
     work(0);
     return BDRC_OK;
   }
-  std::vector<std::thread> pool;
-  pool.reserve(T - 1);
-  for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
-  work(0);
-  for (auto& th : pool) th.join();
+  HostPool::get().run(T, work);
   return BDRC_OK;
 }
 

@@ -76,9 +76,9 @@ class Engine:
         # worker thread, each on its own CUDA stream
         self._ws: dict[tuple, torch.Tensor] = {}
         self._pin: dict[tuple, list] = {}
-        # measured on the B200 host (tools/pack_bench.py, 19 MB of crops): numpy 1.74 ms, 2-4 native threads 1.3 ms,
-        # 8 threads 1.8 ms (thread start-up outweighs the copy)
-        self._gather_threads = max(1, min(3, len(os.sched_getaffinity(0)) // 2))
+        # bdrc_host_gather runs on persistent native threads; tools/pack_bench.py on the B200 host, 19 MB of crops:
+        # numpy 1.53 ms, 2 threads 1.21, 4 threads 1.29, 8 threads 1.80 (host copy bandwidth, not thread count)
+        self._gather_threads = max(1, min(2, len(os.sched_getaffinity(0)) // 2))
 
     # ---- plumbing ------------------------------------------------------------------------
     @property

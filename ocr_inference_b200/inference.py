@@ -249,26 +249,11 @@ class OCRInference:
         for img in line_images:
             self._check_fit(img, pre_pad)
         eng = self.engine
-        L = len(line_images)
-        sizes = [int(im.shape[0]) * int(im.shape[1]) * 3 for im in line_images]
-        if L >= 8 and sum(sizes) >= (4 << 20):
-            # groups of ~equal bytes: packing group k + 1 on the host overlaps the upload + a-7 of group k
-            from .engine import OCR_CPAD
-
-            lines = torch.empty((L, self._input_width, OCR_CPAD), dtype=torch.bfloat16, device=eng.device)
-            bounds, acc, per = [0], 0, sum(sizes) / 4
-            for j, sz in enumerate(sizes):
-                acc += sz
-                if acc >= per * len(bounds) and j + 1 < L and len(bounds) < 4:
-                    bounds.append(j + 1)
-            bounds.append(L)
-            for g, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
-                dev, hw, off = eng.pack_crops(list(line_images[a:b]), key=f"crops{g}")
-                eng.ocr_prepare_lines(dev, hw, off, b - a, self._input_height, self._input_width, pre_pad,
-                                      out=lines[a:b])                                      # a-7
-        else:
-            dev, hw, off = eng.pack_crops(list(line_images))
-            lines, _ = eng.ocr_prepare_lines(dev, hw, off, L, self._input_height, self._input_width, pre_pad)
+        # (packing in four groups so that the host copy of group k + 1 overlaps the upload of group k was measured:
+        #  no gain -- the call is bound by ~16 GB/s of host copy into pinned memory, tools/pack_bench.py)
+        dev, hw, off = eng.pack_crops(list(line_images))
+        lines, _ = eng.ocr_prepare_lines(dev, hw, off, len(line_images), self._input_height, self._input_width,
+                                         pre_pad)                                          # a-7
         logits = eng.ocr_forward(self.ocr_session, lines)                                  # a-8
         ids, lens = eng.ctc_greedy(logits, layout=LAYOUT_TV, blank=self.ctc_decoder.blank_index)   # a-9
         ids, lens = ids.cpu().numpy(), lens.cpu().numpy()

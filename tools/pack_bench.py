@@ -25,3 +25,17 @@ for th in (0, 1, 2, 4, 8):
         eng.pack_crops(crops_t)
     torch.cuda.synchronize()
     print("numpy path" if th == 0 else f"gather x{th}", f"{(time.perf_counter() - t0) / 20 * 1e3:.3f} ms per pack_crops (incl. H2D)")
+
+# the whole call: pack -> upload -> a-7 -> Easter2 -> greedy CTC -> text
+from tools.pipeline_profile import build_pipeline  # noqa: E402
+
+ocr = build_pipeline(eng).ocr_inference
+for th in (0, 2, 4, 8):
+    eng._gather_threads = th
+    for _ in range(3):
+        ocr.run_batch(crops, pre_pad=False)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        texts = ocr.run_batch(crops, pre_pad=False)
+    dt = (time.perf_counter() - t0) / 20
+    print(f"run_batch, gather threads {th}: {dt * 1e3:.3f} ms per 64 lines = {64 / dt:.0f} lines/s")
