@@ -463,15 +463,15 @@ def bench_c4(eng, steps: int = 2):
             m = det.predict_masks(p, 0.8)
     dt1 = (time.perf_counter() - t0) / steps
     batch = pages * 2                                   # 12 pages, 92 tiles: tiles of several pages per forward call
-    det.predict_masks_batch(batch, 0.8)
+    det.predict_masks_batch(batch, 0.8, copy=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        ms = det.predict_masks_batch(batch, 0.8)
+        ms = det.predict_masks_batch(batch, 0.8, copy=False)
     dt = (time.perf_counter() - t0) / steps
     same = all(a.shape == b.shape for a, b in zip(ms[:len(pages)], ms[len(pages):])) and bool((ms[len(pages) - 1] == m).all())
     return {"workload": "C4: ModernBookFormatLayoutDetection.predict_masks_batch on 6 page sizes "
-                        f"{sizes} x 2 (5 classes, random-init, torch-path semantics), host pages in -> host [5,H,W] masks out",
+                        f"{sizes} x 2 (5 classes, random-init, torch-path semantics), host pages in -> host [5,H,W] masks in pinned staging buffers (copy=False)",
             "e2e_pages_per_sec": len(batch) / dt, "ms_per_page": dt * 1e3 / len(batch),
             "megapixels_per_sec": 2 * sum(h * w for h, w in sizes) / dt / 1e6,
             "per_image_calls_pages_per_sec": len(pages) / dt1, "batch_equals_per_image": same,

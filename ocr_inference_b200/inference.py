@@ -805,11 +805,12 @@ class ModernBookFormatLayoutDetection:
         return eng.seg_postprocess_torch(logits, meta, class_threshold).cpu().numpy()
 
     def predict_masks_batch(self, images: Sequence[np.ndarray], class_threshold: float = 0.8,
-                            max_tiles: int = 148) -> list[np.ndarray]:
+                            max_tiles: int = 148, copy: bool = True) -> list[np.ndarray]:
         """[predict_masks(i) for i in images] with the tiles of several images sharing one forward call -- what
         the reference's DataLoader + multi_image_collate_fn (utils.py:1142-1172, batch_size images per step) does.
         Uploads run ahead on a copy stream and masks return through pinned buffers on a third one; images are
-        grouped while their tiles fit `max_tiles` (one 148-tile chunk of the network)."""
+        grouped while their tiles fit `max_tiles` (one 148-tile chunk of the network).  copy=False returns views of
+        this object's pinned staging buffers (valid until the next call) instead of fresh arrays."""
         from .engine import clamp_size_torch
 
         eng, dev = self.engine, self.engine.device
@@ -868,7 +869,7 @@ class ModernBookFormatLayoutDetection:
             i = j
         copy_out.synchronize()
         compute.synchronize()
-        return [o.numpy().copy() for o in outs]
+        return [o.numpy().copy() if copy else o.numpy() for o in outs]
 
     def post_process_sample(self, prediction: np.ndarray, class_index: int):
         import cv2
@@ -909,5 +910,5 @@ class ModernBookFormatLayoutDetection:
         for b0 in range(0, len(paths), step):
             chunk = paths[b0:b0 + step]
             imgs = [cv2.cvtColor(cv2.imread(p, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for p in chunk]
-            for p, masks in zip(chunk, self.predict_masks_batch(imgs, class_threshold)):
+            for p, masks in zip(chunk, self.predict_masks_batch(imgs, class_threshold, copy=False)):
                 self.extract_json_data({"image_name": os.path.basename(p)}, masks, filter_classes, output_dir)
