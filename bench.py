@@ -568,7 +568,18 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None   # before the CUDA context exists
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator comes up; stdout carries the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = get_engine(local_rank)
     dev = eng.device
 
