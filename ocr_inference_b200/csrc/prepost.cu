@@ -448,27 +448,50 @@ ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, in
   if (layout == BDRC_LAYOUT_TV) {
     // [T][V] rows are short (V = 77 -> 308 B) and unaligned: stream the line through shared memory in
     // chunks of CTC_ROWS time steps with fully coalesced loads (every thread keeps several in flight),
-    // then one thread per time step scans its row (row pitch V|1 is odd: conflict-free).
+    // then FOUR threads per time step scan a quarter of its row each and combine by shuffle.
     float* buf = reinterpret_cast<float*>(sm + 2 * T);
     const int pitch = V | 1;
+    const int per = (V + 3) >> 2;                       // four threads share a row: V / 4 logits each
+    const int step_r = 512 / V, step_c = 512 - step_r * V;   // blockDim.x == 512 (launch below)
+    const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
     for (int t0 = 0; t0 < T; t0 += CTC_ROWS) {
       const int rows = min(CTC_ROWS, T - t0);
       const float* src = base + (size_t)t0 * V;
-      const int n = rows * V;
+      // fully coalesced flat copy, eight loads in flight per thread; (row, column) of element i advance
+      // incrementally (one division per kernel instead of one per element)
+      {
+        const int n = rows * V;
+        int rr = threadIdx.x / V, cc = threadIdx.x - rr * V;
 #pragma unroll 8
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = i / V, c = i - r * V;
-        buf[r * pitch + c] = __ldg(src + i);
+        for (int i = threadIdx.x; i < n; i += 512) {
+          buf[rr * pitch + cc] = __ldg(src + i);
+          rr += step_r;
+          cc += step_c;
+          if (cc >= V) { cc -= V; ++rr; }
+        }
       }
       __syncthreads();
-      if (threadIdx.x < rows) {
-        const float* row = buf + threadIdx.x * pitch;
-        float bv = row[0]; int bi = 0;
-        for (int v = 1; v < V; ++v) {
-          const float x = row[v];
-          if (better(x, v, bv, bi)) { bv = x; bi = v; }
+      {
+        float bv = 0.f;
+        int bi = -1;                                    // -1: this thread holds no candidate
+        const int v0 = part * per, v1 = min(V, v0 + per);
+        if (r < rows && v0 < v1) {
+          const float* row = buf + r * pitch;
+          bv = row[v0];
+          bi = v0;
+          for (int v = v0 + 1; v < v1; ++v) {
+            const float x = row[v];
+            if (better(x, v, bv, bi)) { bv = x; bi = v; }
+          }
         }
-        am[t0 + threadIdx.x] = bi;
+        // combine the four partial results of a row (lanes 4k .. 4k+3): first max wins, as in the serial scan
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi >= 0 && (bi < 0 || better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+        }
+        if (part == 0 && r < rows) am[t0 + r] = bi;
       }
       __syncthreads();
     }
