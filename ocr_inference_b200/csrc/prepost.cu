@@ -355,20 +355,26 @@ float sigmoid_logit_threshold(float thr) {
 // a-7 OCR line preparation, stage 1: (pre-pad) + aspect-preserving cv2 resize + black padding
 // + gray, written as a u8 gray canvas [L][Ht][Wt]
 // ------------------------------------------------------------------------------------------
-__global__ void ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__ hw,
-                                  const int64_t* __restrict__ off, int Ht, int Wt, int pre_pad,
-                                  uint8_t* __restrict__ canvas, int* __restrict__ status) {
-  // per (line, canvas row) constants -- the double-precision geometry of _pad_ocr_line and the vertical resize
-  // coefficients -- are computed once per block (fp64 divisions per pixel dominated the first version)
-  __shared__ int g_i[6];          // rh, rw, top, left, cy.i0, cy.i1
-  __shared__ float g_f[2];        // cy.w0, cy.w1
+constexpr int CANVAS_ROWS = 8;   // canvas rows per block
+__global__ void __launch_bounds__(128)
+ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__ hw,
+                  const int64_t* __restrict__ off, int Ht, int Wt, int pre_pad,
+                  uint8_t* __restrict__ canvas, int* __restrict__ status) {
+  // Per-line constants -- the double-precision geometry of _pad_ocr_line -- and the vertical resize coefficients
+  // of this block's CANVAS_ROWS rows are computed once per block, one row per thread (fp64 divisions per pixel
+  // dominated the first version, a serial per-block preamble for ONE row the second: 82 k tiny blocks); the
+  // horizontal coefficients of a column are computed once per thread and reused for all rows of the block.
+  __shared__ int g_i[4];                       // rh, rw, top, left
+  __shared__ int r_i0[CANVAS_ROWS], r_i1[CANVAS_ROWS];
+  __shared__ float r_w0[CANVAS_ROWS], r_w1[CANVAS_ROWS];
   __shared__ double g_scale_x;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
+  const int y0 = blockIdx.y * CANVAS_ROWS;
   const int l = blockIdx.z;
   const int h = hw[2 * l], w0 = hw[2 * l + 1];
   const int w = pre_pad ? w0 + 2 * h : w0;     // _pre_pad hstacks an h x h white patch each side
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < CANVAS_ROWS) {
+    const int y = y0 + threadIdx.x;
     int rh = 0, rw = 0, top = 0, left = 0;
     LinCoef cy = {0, 0, 1.f, 0.f};
     double scale_x = 1.0;
@@ -382,46 +388,62 @@ __global__ void ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32
         if (y >= top && y < top + rh) cy = lin_coef(y - top, h, rh, true);
       }
     }
-    g_i[0] = rh; g_i[1] = rw; g_i[2] = top; g_i[3] = left; g_i[4] = cy.i0; g_i[5] = cy.i1;
-    g_f[0] = cy.w0; g_f[1] = cy.w1;
-    g_scale_x = scale_x;
+    r_i0[threadIdx.x] = cy.i0; r_i1[threadIdx.x] = cy.i1;
+    r_w0[threadIdx.x] = cy.w0; r_w1[threadIdx.x] = cy.w1;
+    if (threadIdx.x == 0) {
+      g_i[0] = rh; g_i[1] = rw; g_i[2] = top; g_i[3] = left;
+      g_scale_x = scale_x;
+    }
   }
   __syncthreads();
   if (x >= Wt) return;
-  uint8_t g = 0;
-  if (h > 0 && w0 > 0) {
-    const int rh = g_i[0], rw = g_i[1], top = g_i[2], left = g_i[3];
-    if (rh <= 0 || rw <= 0) {
-      if (x == 0 && y == 0) status[l] = 1;   // cv2.resize would raise on an empty target
-    } else if (y >= top && y < top + rh && x >= left && x < left + rw) {
-      const int dy = y - top, dx = x - left;
-      const uint8_t* base = crops + off[l];
+  const int rh = g_i[0], rw = g_i[1], top = g_i[2], left = g_i[3];
+  const bool live = h > 0 && w0 > 0;
+  if (live && (rh <= 0 || rw <= 0)) {
+    if (x == 0 && y0 == 0) status[l] = 1;     // cv2.resize would raise on an empty target
+  }
+  const bool in_x = live && rh > 0 && rw > 0 && x >= left && x < left + rw;
+  const int dx = x - left;
+  const uint8_t* base = crops + off[l];
+  auto fetch = [&](int sy, int sx, int* out3) {
+    if (pre_pad && (sx < h || sx >= h + w0)) { out3[0] = out3[1] = out3[2] = 255; return; }
+    const uint8_t* p = base + ((size_t)sy * w0 + (pre_pad ? sx - h : sx)) * 3;
+    out3[0] = p[0]; out3[1] = p[1]; out3[2] = p[2];
+  };
+  const int mode = !in_x ? 0 : (rh == h && rw == w) ? 1 : (w == 2 * rw && h == 2 * rh) ? 2 : 3;
+  LinCoef cx = {0, 0, 1.f, 0.f};
+  int a0 = 0, a1 = 0;
+  if (mode == 3) {
+    cx = lin_coef_scaled(dx, w, g_scale_x, false);
+    a0 = fix11(cx.w0);
+    a1 = fix11(cx.w1);
+  }
+#pragma unroll 4
+  for (int r = 0; r < CANVAS_ROWS; ++r) {
+    const int y = y0 + r;
+    if (y >= Ht) break;
+    uint8_t g = 0;
+    if (mode != 0 && y >= top && y < top + rh) {
+      const int dy = y - top;
       int px[3];
-      auto fetch = [&](int sy, int sx, int* out3) {
-        if (pre_pad && (sx < h || sx >= h + w0)) { out3[0] = out3[1] = out3[2] = 255; return; }
-        const uint8_t* p = base + ((size_t)sy * w0 + (pre_pad ? sx - h : sx)) * 3;
-        out3[0] = p[0]; out3[1] = p[1]; out3[2] = p[2];
-      };
-      if (rh == h && rw == w) {
+      if (mode == 1) {
         fetch(dy, dx, px);
-      } else if (w == 2 * rw && h == 2 * rh) {
+      } else if (mode == 2) {
         int a[3], b[3], c[3], d[3];
         fetch(2 * dy, 2 * dx, a); fetch(2 * dy, 2 * dx + 1, b);
         fetch(2 * dy + 1, 2 * dx, c); fetch(2 * dy + 1, 2 * dx + 1, d);
         for (int k = 0; k < 3; ++k) px[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
       } else {
-        const LinCoef cx = lin_coef_scaled(dx, w, g_scale_x, false);
-        const LinCoef cy = {g_i[4], g_i[5], g_f[0], g_f[1]};
-        const int a0 = fix11(cx.w0), a1 = fix11(cx.w1), b0 = fix11(cy.w0), b1 = fix11(cy.w1);
+        const int b0 = fix11(r_w0[r]), b1 = fix11(r_w1[r]);
         int s00[3], s01[3], s10[3], s11[3];
-        fetch(cy.i0, cx.i0, s00); fetch(cy.i0, cx.i1, s01);
-        fetch(cy.i1, cx.i0, s10); fetch(cy.i1, cx.i1, s11);
+        fetch(r_i0[r], cx.i0, s00); fetch(r_i0[r], cx.i1, s01);
+        fetch(r_i1[r], cx.i0, s10); fetch(r_i1[r], cx.i1, s11);
         for (int k = 0; k < 3; ++k) px[k] = resize_fix_sample(s00[k], s01[k], s10[k], s11[k], a0, a1, b0, b1);
       }
       g = (uint8_t)((px[0] * 9798 + px[1] * 19235 + px[2] * 3735 + 16384) >> 15);
     }
+    canvas[((size_t)l * Ht + y) * Wt + x] = g;
   }
-  canvas[((size_t)l * Ht + y) * Wt + x] = g;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -656,7 +678,7 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
   uint8_t* canvas = reinterpret_cast<uint8_t*>(workspace);
   int* status = reinterpret_cast<int*>(canvas + align_up((size_t)L * Ht * Wt, 256));
   BDRC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)L * sizeof(int), s));
-  dim3 grid(ceil_div(Wt, 128), Ht, L);
+  dim3 grid(ceil_div(Wt, 128), ceil_div(Ht, CANVAS_ROWS), L);
   bdrc_prof_begin(ctx, "a-7.canvas", 0, s);
   ocr_canvas_kernel<<<grid, 128, 0, s>>>(crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status);
   bdrc_prof_end(ctx, s);
