@@ -582,7 +582,7 @@ class OCRPipeline:
         tls = self._tls
         results: list = [None] * n
         bad = [i for i, img in enumerate(images)
-               if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] < 3 or img.dtype != np.uint8
+               if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8
                or img.shape[0] == 0 or img.shape[1] == 0]
         good = [i for i in range(n) if i not in bad]
         for i in bad:
