@@ -24,7 +24,9 @@ constexpr int KS = 51, KR = 25;
 constexpr int SW = 32;                 // strip width (output columns per CTA)
 constexpr int RB = 32;                 // rows per block
 constexpr int GW = SW + 2 * KR;        // 82 staged columns
-constexpr int GSTRIDE = 84;            // padded row stride of the staged gray block (float4-aligned)
+constexpr int GSTRIDE = 92;            // padded row stride of the staged gray block (float4-aligned)
+constexpr int GOFF = 4;                // staged column c lives at g[row * GSTRIDE + GOFF + c]: a quad store that hangs over the
+                                       // 82 columns by up to 3 on either side lands in padding, no predicates
 constexpr int RING = 128;              // row-pass ring (rows), power of two
 constexpr int THREADS = 256;
 constexpr size_t SMEM_BYTES = (size_t)(RB * GSTRIDE + RING * SW) * sizeof(float) + RING * SW + RB * SW;
@@ -61,13 +63,19 @@ struct SrcPageTiles {
     raw[0] = __ldg(q); raw[1] = __ldg(q + 1); raw[2] = __ldg(q + 2);
     return 1;
   }
-  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v) const {
+  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v, uint32_t& packed) const {
     const uint32_t w0 = raw[0], w1 = raw[1], w2 = raw[2];
-    // bytes: w0 = r0 g0 b0 r1, w1 = g1 b1 r2 g2, w2 = b2 r3 g3 b3 (little endian)
-    v[0] = (float)(int)(((w0 & 255u) * 9798u + ((w0 >> 8) & 255u) * 19235u + ((w0 >> 16) & 255u) * 3735u + 16384u) >> 15);
-    v[1] = (float)(int)(((w0 >> 24) * 9798u + (w1 & 255u) * 19235u + ((w1 >> 8) & 255u) * 3735u + 16384u) >> 15);
-    v[2] = (float)(int)((((w1 >> 16) & 255u) * 9798u + (w1 >> 24) * 19235u + (w2 & 255u) * 3735u + 16384u) >> 15);
-    v[3] = (float)(int)((((w2 >> 8) & 255u) * 9798u + ((w2 >> 16) & 255u) * 19235u + (w2 >> 24) * 3735u + 16384u) >> 15);
+    // bytes: w0 = r0 g0 b0 r1, w1 = g1 b1 r2 g2, w2 = b2 r3 g3 b3 (little endian).  One register per pixel with
+    // (r, g, b, x) in its bytes, then the 15-bit gray as two byte dot products: 9798 = 38*256 + 70,
+    // 19235 = 75*256 + 35, 3735 = 14*256 + 151 (the fourth byte meets a zero coefficient)
+    const uint32_t p0 = w0, p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
+    constexpr uint32_t CH = 38u | (75u << 8) | (14u << 16), CL = 70u | (35u << 8) | (151u << 16);
+    const uint32_t g0 = ((__dp4a(p0, CH, 0u) << 8) + __dp4a(p0, CL, 16384u)) >> 15;
+    const uint32_t g1 = ((__dp4a(p1, CH, 0u) << 8) + __dp4a(p1, CL, 16384u)) >> 15;
+    const uint32_t g2 = ((__dp4a(p2, CH, 0u) << 8) + __dp4a(p2, CL, 16384u)) >> 15;
+    const uint32_t g3 = ((__dp4a(p3, CH, 0u) << 8) + __dp4a(p3, CL, 16384u)) >> 15;
+    v[0] = (float)g0; v[1] = (float)g1; v[2] = (float)g2; v[3] = (float)g3;
+    packed = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
   }
 };
 
@@ -87,9 +95,10 @@ struct SrcGrayBatch {
     raw[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
     return 1;
   }
-  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v) const {
+  __device__ __forceinline__ void conv4(const uint32_t* raw, float* v, uint32_t& packed) const {
     const uint32_t w = raw[0];
     v[0] = (float)(w & 255u); v[1] = (float)((w >> 8) & 255u); v[2] = (float)((w >> 16) & 255u); v[3] = (float)(w >> 24);
+    packed = w;
   }
 };
 
@@ -186,22 +195,23 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         const int xq = x0 - 28 + 4 * q;
         const uint32_t m = (mode >> (2 * it)) & 3u;
         float v[4];
+        uint32_t packed;
         if (m == 1u) {
-          src.conv4(raw[it], v);
+          src.conv4(raw[it], v, packed);
         } else if (m == 2u) {
           v[0] = v[1] = v[2] = v[3] = 255.f;
+          packed = 0xFFFFFFFFu;
         } else {
           const int y = min(RB * blk + r, IH - 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) v[j] = src.gray(img, y, min(max(xq + j, 0), IW - 1));
+          packed = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
         }
-        float* gr = g + r * GSTRIDE + 4 * q - 3;
+        float* gr = g + r * GSTRIDE + GOFF + 4 * q - 3;      // 4q + 1 .. 4q + 4 of a 92-float row: always inside
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (4 * q - 3 + j >= 0 && 4 * q - 3 + j < GW) gr[j] = v[j];
+        for (int j = 0; j < 4; ++j) gr[j] = v[j];
         if (q >= 7 && q < 7 + SW / 4)
-          *reinterpret_cast<uint32_t*>(gc + ((RB * blk + r) & (RING - 1)) * SW + 4 * (q - 7)) =
-              (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+          *reinterpret_cast<uint32_t*>(gc + ((RB * blk + r) & (RING - 1)) * SW + 4 * (q - 7)) = packed;
       }
     }
   };
@@ -216,7 +226,7 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
     // ---- row pass of block b: ring[row][c] = sum_k g[row][c + k] * w[k], k ascending, FMA ----
     if (b < n_blocks) {
       const int r = threadIdx.x / (SW / 4), c = (threadIdx.x % (SW / 4)) * 4;
-      const float* gp = g + r * GSTRIDE + c;
+      const float* gp = g + r * GSTRIDE + GOFF + c;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       float4 v = *reinterpret_cast<const float4*>(gp);
       float w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;   // sliding window g[c+k .. c+k+3]

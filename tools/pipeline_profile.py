@@ -71,6 +71,14 @@ def main():
             nl = sum(len(r[1][2]) for r in out if r[0] == OpStatus.SUCCESS)
             print(f"run_ocr_batch staged={staged} geometry_procs={gp} workers={workers}: {nb / dt:.1f} pages/s, "
                   f"{nl / dt:.0f} lines/s", flush=True)
+    # chunk size of the staged schedule (pages resident on the GPU / pinned mask buffers per chunk)
+    big = [pages[i % n] for i in range(max(nb, 192))]
+    for chunk in (48, 96, 192):
+        pipe.run_ocr_batch(big, staged=True, geometry_procs=8, chunk_pages=chunk)
+        t0 = time.perf_counter()
+        out = pipe.run_ocr_batch(big, staged=True, geometry_procs=8, chunk_pages=chunk)
+        dt = time.perf_counter() - t0
+        print(f"run_ocr_batch {len(big)} pages, geometry_procs=8, chunk_pages={chunk}: {len(big) / dt:.1f} pages/s", flush=True)
     pipe.close()
 
 
