@@ -116,6 +116,35 @@ class Engine:
         self._pin[(key, threading.get_ident())][1] = ev
         return dev
 
+    def upload_page(self, img: np.ndarray, ring: list, k: int):
+        """Asynchronous H2D of a pageable u8 array on the current stream through slot k of a ring of pinned
+        buffers (`ring` = [[tensor | None, event | None], ...], owned by the caller): a few native threads copy
+        the array into the slot (bdrc_host_gather, GIL released), the DMA out of it does not block the host, so
+        the copy of the next page overlaps it.  A plain pageable .to() moves ~7 GB/s from one thread (2.7 ms per
+        19 MB page).  Returns (device tensor, event recorded after the copy)."""
+        img = np.ascontiguousarray(img)
+        nbytes = int(img.nbytes)
+        slot = ring[k % len(ring)]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        if nbytes >= (1 << 20):
+            ptr = np.array([img.ctypes.data], dtype=np.uint64)
+            nb = np.array([nbytes], dtype=np.int64)
+            zero = np.zeros(1, dtype=np.int64)
+            self._check(self.lib.bdrc_host_gather(ptr.ctypes.data, nb.ctypes.data, zero.ctypes.data, 1,
+                                                  slot[0].data_ptr(), 4), "host_gather")
+        elif nbytes:
+            np.copyto(slot[0][:nbytes].numpy().reshape(img.shape), img)
+        d = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
+        if nbytes:
+            d.copy_(slot[0][:nbytes].view(img.shape), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        slot[1] = ev
+        return d, ev
+
     def launch_count(self) -> int:
         return self.ctx.launch_count()
 

@@ -146,12 +146,16 @@ class Detection:
         ups, evs = [], []
         copy_in.wait_stream(compute)
         with torch.cuda.stream(copy_in):
+            ring = getattr(self, "_up_slots", None)
+            if ring is None:
+                ring = self._up_slots = [[None, None] for _ in range(4)]
             for i, img in enumerate(images):
-                src = pinned[i] if pinned is not None else torch.from_numpy(
-                    np.ascontiguousarray(img[..., :3], dtype=np.uint8))
-                d = src.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_in)
+                if pinned is not None:
+                    d = pinned[i].to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_in)
+                else:       # pageable page: through the pinned slot ring
+                    d, ev = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, i)
                 ups.append(d)
                 evs.append(ev)
         outs = []
@@ -605,15 +609,16 @@ class OCRPipeline:
         copy_in.wait_stream(compute)
 
         def uploader():
+            # pageable pages go through a ring of pinned slots (Engine.upload_page): a plain pageable .to() capped
+            # the whole pipeline at ~270 pages/s (tools/c3_limits.py)
             torch.cuda.set_device(dev)
+            ring = getattr(det, "_up_slots", None)
+            if ring is None:
+                ring = det._up_slots = [[None, None] for _ in range(4)]
             with torch.cuda.stream(copy_in):
-                for i in good:
+                for k, i in enumerate(good):
                     try:
-                        src = torch.from_numpy(np.ascontiguousarray(images[i][..., :3]))
-                        pages_dev[i] = src.to(dev, non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(copy_in)
-                        up_ev[i] = ev
+                        pages_dev[i], up_ev[i] = eng.upload_page(images[i], ring, k)
                     finally:
                         up_ready[i].set()
 
@@ -826,11 +831,12 @@ class ModernBookFormatLayoutDetection:
             n_tiles.append((-(-Hc // 512)) * (-(-Wc // 512)))
         ups, evs = [], []
         copy_in.wait_stream(compute)
+        ring = getattr(self, "_up_slots", None)
+        if ring is None:
+            ring = self._up_slots = [[None, None] for _ in range(4)]
         with torch.cuda.stream(copy_in):
-            for img in images:
-                d = torch.from_numpy(np.ascontiguousarray(img[..., :3], dtype=np.uint8)).to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_in)
+            for k, img in enumerate(images):
+                d, ev = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, k)
                 ups.append(d)
                 evs.append(ev)
         outs: list = [None] * len(images)
