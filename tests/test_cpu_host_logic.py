@@ -168,6 +168,23 @@ def test_page_geometry_and_geometry_pool_match_stage_functions(monkeypatch):
             pool.submit(np.zeros((4, 4, 3), np.uint8))
 
 
+def test_line_threshold_census_on_wide_pages_matches_oracle():
+    """get_line_threshold counts the contours of all vertical slices in ONE findContours call on a strip image; on
+    page-wide masks the reference's slice origins x + x_steps * step run past the right edge (empty slices), and a
+    column of foreground switches the row compaction off: same threshold as the oracle's slice-by-slice census."""
+    rng = np.random.default_rng(7)
+    for t in range(6):
+        H, W = int(rng.integers(500, 1200)), int(rng.integers(2300, 3400))
+        _, boxes = synthetic.page(900 + t, H, W)
+        m = synthetic.band_mask(boxes, H, W, thin=float(rng.uniform(0.3, 1.0)))
+        for _ in range(150):
+            m[int(rng.integers(0, H)), int(rng.integers(0, W))] = 255
+        if t % 3 == 0:
+            m[:, :5] = 255
+        assert ld.get_line_threshold(m) == og.line_threshold(m)
+        assert ld.get_line_threshold(cv2.cvtColor(m, cv2.COLOR_GRAY2RGB)) == og.line_threshold(m)
+
+
 def test_mask3_link_is_the_identity_conversion():
     """BGR2GRAY of a channel-replicated image is the channel (all 256 values), so get_line_threshold may read the
     1-channel mask build_raw_line_data remembers; views and copies drop the link."""
