@@ -196,10 +196,13 @@ def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold
     filtered = filter_line_contours(line_mask, contours)
     if len(filtered) == 0:
         return ("failed", "No valid lines after filtering")
-    line_data = [build_line_data(c) for c in filtered]
+    line_data = [build_line_data(c, _guid=False) for c in filtered]
     linked = line_mask.view(Mask3)          # lets get_line_threshold reuse the row compaction
     linked.gray, linked.rows = line_mask, rows
     sorted_lines, _ = sort_lines_by_threshold2(linked, line_data, group_lines=merge_lines)
+    for ln in sorted_lines:                 # single-chunk rows keep their chunk line: it gets its guid now
+        if ln.guid is None:
+            ln.guid = generate_guid(clock_seq=23)
     H, W = line_mask.shape[:2]
     rois, masks, hs = line_rois(sorted_lines, H, W)
     lines = [(ln.guid, ln.contour, (ln.bbox.x, ln.bbox.y, ln.bbox.w, ln.bbox.h), ln.center) for ln in sorted_lines]
@@ -216,12 +219,13 @@ def filter_line_contours(image: np.ndarray, line_contours, threshold: float = 0.
     return keep
 
 
-def build_line_data(contour: np.ndarray, optimize: bool = True) -> Line:
-    """:188-209."""
+def build_line_data(contour: np.ndarray, optimize: bool = True, _guid: bool = True) -> Line:
+    """:188-209.  `_guid=False` (internal) leaves the guid to the caller: most chunk lines of a page end up merged
+    into a row hull, which gets its own guid, and uuid1 costs as much as the polygon approximation."""
     if optimize:
         contour = optimize_countour(contour)
     x, y, w, h = cv2.boundingRect(contour)
-    return Line(generate_guid(clock_seq=23), contour, BBox(x, y, w, h), (x + (w // 2), y + (h // 2)))
+    return Line(generate_guid(clock_seq=23) if _guid else None, contour, BBox(x, y, w, h), (x + (w // 2), y + (h // 2)))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -144,6 +144,7 @@ def test_page_geometry_and_geometry_pool_match_stage_functions(monkeypatch):
 
     def check(res):
         assert res[0] == "ok" and res[1] == angle and len(res[2]) == len(want)
+        assert all(g is not None for g, _, _, _ in res[2]) and len({g for g, _, _, _ in res[2]}) == len(res[2])
         for (guid, contour, bb, ctr), w in zip(res[2], want):
             assert np.array_equal(contour, w.contour) and bb == (w.bbox.x, w.bbox.y, w.bbox.w, w.bbox.h) and ctr == w.center
         assert res[3] == rois_w and res[5] == hs_w and all(np.array_equal(a, b) for a, b in zip(res[4], masks_w))
