@@ -127,7 +127,11 @@ class Detection:
 
     def predict(self, image: np.ndarray, class_threshold: float | None = None) -> np.ndarray:
         thr = self._default_threshold if class_threshold is None else class_threshold
-        page = torch.from_numpy(np.ascontiguousarray(image[..., :3], dtype=np.uint8)).to(self.engine.device)
+        ring = getattr(self._tls, "ring", None)          # per calling thread: predict() may run on several
+        if ring is None:
+            ring = self._tls.ring = [[None, None], [None, None]]
+        self._tls.ring_k = getattr(self._tls, "ring_k", 0) + 1
+        page, _ = self.engine.upload_page(np.ascontiguousarray(image[..., :3], dtype=np.uint8), ring, self._tls.ring_k)
         self._tls.last = (image, page)
         return self._predict_device(page, thr).cpu().numpy()
 
