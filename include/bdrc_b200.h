@@ -52,6 +52,13 @@ const char* bdrc_last_error(bdrc_ctx* ctx);
 const char* bdrc_version(void);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t bdrc_launch_count(bdrc_ctx* ctx);
+/* Convolutions that ran on the SIMT engine instead of tcgen05.  A shape without a tcgen05 tiling is an
+ * error (BDRC_ERR_UNSUPPORTED) unless BDRC_ALLOW_SIMT=1 was set when the ctx was created or the SIMT engine
+ * was selected explicitly; bench.py prints this counter (0 on every measured path). */
+uint64_t bdrc_simt_launch_count(bdrc_ctx* ctx);
+/* tensor-map / tiling plans built so far: a steady-state forward re-uses cached plans (no host-side
+ * cuTensorMapEncodeTiled per launch), so this stops growing once the buffers of a workload repeat */
+uint64_t bdrc_conv_plans_built(bdrc_ctx* ctx);
 /* conv engine: 0 = tcgen05/TMEM implicit GEMM (product path), 1 = SIMT (debug cross-check) */
 int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine);
 /* per-launch CUDA-event profile of the network kernels (bench.py roofline numbers) */

@@ -23,6 +23,8 @@ _SIGS = {
     "bdrc_last_error": (C.c_char_p, [c_void_p]),
     "bdrc_version": (C.c_char_p, []),
     "bdrc_launch_count": (c_u64, [c_void_p]),
+    "bdrc_simt_launch_count": (c_u64, [c_void_p]),
+    "bdrc_conv_plans_built": (c_u64, [c_void_p]),
     "bdrc_set_conv_engine": (c_int, [c_void_p, c_int]),
     "bdrc_profile_enable": (c_int, [c_void_p, c_int]),
     "bdrc_profile_reset": (c_int, [c_void_p]),
@@ -145,6 +147,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.bdrc_launch_count(self.h))
+
+    def simt_launch_count(self) -> int:
+        return int(self.lib.bdrc_simt_launch_count(self.h))
+
+    def conv_plans_built(self) -> int:
+        return int(self.lib.bdrc_conv_plans_built(self.h))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

@@ -1,5 +1,6 @@
 // Context management and the small C-ABI entry points that are not tied to one stage.
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -40,6 +41,7 @@ int bdrc_create(int device, bdrc_ctx** out) {
     return BDRC_ERR_CUDA;
   }
   cudaMemset(ctx->d_errflag, 0, sizeof(int));
+  if (const char* e = getenv("BDRC_ALLOW_SIMT")) ctx->allow_simt = e[0] == '1';
   *out = ctx;
   return BDRC_OK;
 }
@@ -48,12 +50,17 @@ void bdrc_destroy(bdrc_ctx* ctx) {
   if (!ctx) return;
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   if (ctx->d_errflag) cudaFree(ctx->d_errflag);
+  conv_tc_cache_free(ctx);
   delete ctx;
 }
 
 const char* bdrc_last_error(bdrc_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 
 uint64_t bdrc_launch_count(bdrc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t bdrc_simt_launch_count(bdrc_ctx* ctx) { return ctx ? ctx->simt_launches : 0; }
+
+uint64_t bdrc_conv_plans_built(bdrc_ctx* ctx) { return ctx ? ctx->tc_plans_built : 0; }
 
 int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine) {
   if (!ctx || engine < 0 || engine > 1) return BDRC_ERR_ARG;

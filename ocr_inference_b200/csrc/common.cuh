@@ -24,7 +24,11 @@ struct bdrc_ctx {
   std::vector<double> prof_flops;
   size_t prof_used = 0;
   uint64_t launches = 0;                   // kernels launched through this ctx
-  int conv_engine = 0;                     // 0 = tcgen05 implicit GEMM, 1 = SIMT (debug)
+  int conv_engine = 0;                     // 0 = tcgen05 implicit GEMM, 1 = SIMT (debug cross-check, explicit)
+  bool allow_simt = false;                 // BDRC_ALLOW_SIMT=1: shapes the tcgen05 engine cannot tile may run SIMT
+  uint64_t simt_launches = 0;              // convolutions that ran on the SIMT engine (bdrc_simt_launch_count)
+  uint64_t tc_plans_built = 0;             // tensor-map / tiling plans built (cache misses of conv_tc_launch)
+  void* tc_cache = nullptr;                // TcCache* (conv_tc.cu)
   int* d_errflag = nullptr;                // device-side watchdog flag
 };
 
@@ -88,17 +92,15 @@ struct ConvArgs {
   int out_ld = 0, out_coff = 0;
   int out_fp32 = 0;
   int relu = 0;
-  // optional fused 1x1 head (tcgen05 engine only): out is not written, head_out [N,Hout,Wout,head_C] fp32 is
-  const float* head_w = nullptr;          // [head_C][Cout_pad] fp32
-  const float* head_b = nullptr;
-  float* head_out = nullptr;
-  int head_C = 0;
+  int pdl = 0;                            // programmatic dependent launch (short chains only, see conv_tc.cu)
 };
 
 int conv_tc_supported(const ConvWeights& w, const ConvArgs& a);
 int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s);
 int conv_simt_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s);
-// dispatch: tcgen05 when supported (and ctx->conv_engine == 0), else SIMT
+void conv_tc_cache_free(bdrc_ctx* ctx);
+// dispatch: tcgen05 (ctx->conv_engine == 0).  A shape the tcgen05 engine cannot tile is an ERROR unless the
+// context allows the SIMT engine (BDRC_ALLOW_SIMT=1 or bdrc_set_conv_engine(ctx, 1)); SIMT launches are counted.
 int conv_launch(bdrc_ctx* ctx, const char* name, const ConvWeights& w, const ConvArgs& a,
                 cudaStream_t s);
 

@@ -1,4 +1,4 @@
-// SIMT convolution (debug cross-check engine and catch-all for shapes the tcgen05 engine does
+// SIMT convolution (debug cross-check engine; opt-in catch-all for shapes the tcgen05 engine does
 // not tile), weight packing, conv dispatch and the per-launch profiling hooks.
 #include <cstdarg>
 
@@ -142,6 +142,13 @@ int conv_launch(bdrc_ctx* ctx, const char* name, const ConvWeights& w, const Con
     bdrc_prof_begin(ctx, name, flops, s);
     rc = conv_tc_launch(ctx, w, a, s);
   } else {
+    // never silently: a model configuration that falls off the tcgen05 tiling would run ~50x slower
+    if (ctx->conv_engine == 0 && !ctx->allow_simt)
+      return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED,
+                       "conv '%s' %d->%d k%dx%d s%dx%d on %dx%d (ld %d, off %d) has no tcgen05 tiling; "
+                       "BDRC_ALLOW_SIMT=1 runs it on the (slow) SIMT engine",
+                       name, w.Cin, w.Cout, w.R, w.S, a.stride_h, a.stride_w, a.Hout, a.Wout, a.in_ld, a.in_coff);
+    ctx->simt_launches++;
     bdrc_prof_begin(ctx, name, flops, s);
     rc = conv_simt_launch(ctx, w, a, s);
   }

@@ -17,6 +17,8 @@
 //                allocator, warps 4..11 = epilogue (TMEM -> registers -> bias/residual/ReLU ->
 //                bf16 NHWC; lane quarter x column half per warp).  Persistent grid, one CTA per SM, static round-robin tile schedule.
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -47,30 +49,26 @@ struct TcParams {
   int res_ld;
   void* out;
   int out_ld, out_coff, out_fp32, relu, out_tma;
-  // optional fused 1x1 "head" over the (ReLU'd, bf16-rounded) outputs of this layer: head_out[pix][c] =
-  // head_b[c] + sum_n out[pix][n] * head_w[c][n]; the layer's own output is then not stored at all
-  const float* head_w;
-  const float* head_b;
-  float* head_out;
-  int head_C, head_ld;
   int* errflag;
-  int dbg_skip;   // timing experiments only -- bit 0: skip A loads, 1: skip B loads, 2: skip epilogue math + I/O,
+  int dbg_skip;   // -DBDRC_EXPERIMENTS builds only -- bit 0: skip A loads, 1: skip B loads, 2: skip epilogue math + I/O,
                   // 3: skip the TMA stores, 4: skip the residual loads
 };
 
 using namespace tcptx;
 
-// BDRC_PDL=1 launches the conv kernels with programmatic dependent launch (the next kernel's barrier init / TMEM
-// allocation overlaps the tail of this one).  Measured on B200 and left OFF: C1 at 64 lines gains 3 % (69.5 k ->
-// 71.8 k lines/s), but 8 queued C2 steps (1456 back-to-back launches) drop from 515 to 199 pages/s -- with deep
-// queues of cluster launches the early-resident CTAs of kernel N+1 appear to hold back kernel N's tail.
-static bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("BDRC_PDL");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
+// Timing experiments (skip loads / epilogue, alternative variants) exist only in -DBDRC_EXPERIMENTS builds; the
+// product build compiles every one of these branches out.
+#ifdef BDRC_EXPERIMENTS
+#define DBG(p, bits) ((p).dbg_skip & (bits))
+#else
+#define DBG(p, bits) 0
+#endif
+
+// ConvArgs.pdl launches a conv kernel with programmatic dependent launch (its barrier init / TMEM allocation
+// overlaps the tail of the previous kernel).  Measured on B200: the short Easter2 chain gains 3 % at 64 lines
+// (69.5 k -> 71.8 k lines/s) and asks for it; the segmentation forward does NOT -- 8 queued C2 steps (1456
+// back-to-back launches) drop from 515 to 199 pages/s, with deep queues of cluster launches the early-resident
+// CTAs of kernel N+1 hold back kernel N's tail.
 
 __device__ __forceinline__ int floordiv(int a, int b) {
   int q = a / b;
@@ -157,7 +155,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
       }
       uint4 rres[16];
-      if (res_vec && !(p.dbg_skip & (4 | 16))) {
+      if (res_vec && !DBG(p, 4 | 16)) {
 #pragma unroll
         for (int ul = 0; ul < 2; ++ul) {
           if (egrp + 2 * ul < units && valid[ul]) {
@@ -169,10 +167,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
           }
         }
       }
-
-      float hacc[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) hacc[c] = 0.f;
 
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
       tc_fence_after();
@@ -199,7 +193,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
           uint32_t v[16];
           tc_ld16(tbase + (uint32_t)(g * p.BN + c0), v);
           tc_wait_ld();
-          if (p.dbg_skip & 4) continue;
+          if (DBG(p, 4)) continue;
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -233,25 +227,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          if (p.head_w) {
-            // the head consumes this layer's output as the unfused path stores it: rounded to bf16
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __bfloat162float(__float2bfloat16(f[j]));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (c < p.head_C) {
-                const float* hw = p.head_w + (size_t)c * p.BN + c0;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(hw + j));
-                  hacc[c] = fmaf(f[j + 0], w4.x, hacc[c]);
-                  hacc[c] = fmaf(f[j + 1], w4.y, hacc[c]);
-                  hacc[c] = fmaf(f[j + 2], w4.z, hacc[c]);
-                  hacc[c] = fmaf(f[j + 3], w4.w, hacc[c]);
-                }
-              }
-            }
-          } else if (p.out_tma) {
+          if (p.out_tma) {
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -262,7 +238,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
             uint8_t* rowp = sbuf + (size_t)m * 128;
             *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else if (valid[ul] && n0 + c0 < p.Cout) {   // (never reached with a fused head: handled above)
+          } else if (valid[ul] && n0 + c0 < p.Cout) {
             const bool full16 = (n0 + c0 + 16 <= p.Cout);
             if (p.out_fp32) {
               float* op = reinterpret_cast<float*>(p.out) + pix[ul] * p.out_ld + p.out_coff + n0 + c0;
@@ -286,7 +262,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         if (p.out_tma) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(1 + egrp) : "memory");
-          if (issuer && !(p.dbg_skip & (4 | 8))) {
+          if (issuer && !DBG(p, 4 | 8)) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&tmapO)), "r"(smem_u32(sbuf)), "r"(n0 + cg0[ul]), "r"(oxs[ul]),
@@ -303,21 +279,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         if (CTAS == 2) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u); else mbar_arrive(tempty0 + (uint32_t)acc * 8u);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (p.head_w) {
-        // the two epilogue groups hold the partial dot products of their column groups: combine through
-        // shared memory (two buffers alternate, so one 256-thread barrier per tile is enough)
-        float* hbuf = reinterpret_cast<float*>(stage_out_base) + (size_t)(use & 1) * (2 * 128 * 8);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) hbuf[((size_t)egrp * 128 + m) * 8 + c] = hacc[c];
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (egrp == 0 && valid[0]) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < p.head_C)
-              p.head_out[pix[0] * p.head_ld + c] = hbuf[(size_t)m * 8 + c] + hbuf[((size_t)128 + m) * 8 + c] + __ldg(p.head_b + c);
-        }
-        ++use;
-      }
     }
     if (p.out_tma && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -429,17 +390,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                   tma_load_2d_2sm(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
                 }
               } else {
-                const uint32_t bytes = ((p.dbg_skip & 1) ? 0u : a_bytes) + ((p.dbg_skip & 2) ? 0u : b_stage_bytes);
+                const uint32_t bytes = (DBG(p, 1) ? 0u : a_bytes) + (DBG(p, 2) ? 0u : b_stage_bytes);
                 if (elect_one()) {
                   if (bytes) mbar_arrive_expect_tx(fb, bytes); else mbar_arrive(fb);
-                  if (!(p.dbg_skip & 1)) {
+                  if (!DBG(p, 1)) {
 #pragma unroll
                     for (int g = 0; g < MAX_G; ++g)
                       if (g < G)
                         tma_load_5d(a_dst + (uint32_t)g * A_STAGE_BYTES, &tmapA, fb, par_w * p.par_c + kc * BK,
                                     ox0[g] + off_w, par_h, oy0[g] + off_h, img[g]);
                   }
-                  if (!(p.dbg_skip & 2))
+                  if (!DBG(p, 2))
                     tma_load_2d(a_dst + a_bytes, &tmapB, fb, ((r * p.S + s) * p.kchunks + kc) * BK, n0);
                 }
               }
@@ -525,29 +486,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 // base offset = s the results are wrong), so a window that starts at any 128-byte row reads what TMA wrote.  All 9 weight tiles stay resident (72 KB).  A CTA owns a contiguous range
 // of "super rows" (4 output rows = 4 interleaved accumulators); consecutive super rows reuse 2 of their 6
 // input rows, slots are released tap-row by tap-row with tcgen05.commit so the ring (7 slots) never stalls.
-// SLAB<1>: one CTA, 7 slots, whole weight tiles resident, consecutive super rows reuse 2 of their 6 rows.
-// SLAB<2>: CTA pair (cta_group::2, M = 256): CTA r of the pair owns output rows 8t + 4r .. + 3 of pair tile t,
-//          loads its own 6 input rows and HALF of every weight tile (36 KB), which frees room for 9 slots.
+// One CTA per SM, 7 slots, whole weight tiles resident.  (A CTA-pair variant was built and measured SLOWER, 608
+// against 674 TFLOP/s at 148 tiles: at N = 64 the operand path is bound by the 4 KB of A per MMA, which pairing
+// does not reduce, and the pair adds a coupled accumulator hand-off.  It is not in the tree any more.)
 constexpr uint32_t SLAB_ROW_BYTES = 17 * 1024;        // 130 px x 128 B = 16640, padded to 1024
 constexpr uint32_t SLAB_ROW_TX = 130 * 128;
-template <int CTAS> struct SlabCfg {
-  static constexpr int SLOTS = CTAS == 2 ? 9 : 7;
-  static constexpr uint32_t B_TAP_BYTES = 64 / CTAS * 128;       // 8 KB (4 KB per CTA of a pair) per filter tap
-  static constexpr uint32_t B_BYTES = 9 * B_TAP_BYTES;
-  static constexpr size_t SMEM = 1024 + (size_t)SLOTS * SLAB_ROW_BYTES + B_BYTES + 1024 + 2 * OUT_STAGE_BYTES;
-};
+constexpr int SLAB_SLOTS = 7;
+constexpr uint32_t SLAB_B_TAP_BYTES = 64 * 128;       // 8 KB per filter tap
+constexpr uint32_t SLAB_B_BYTES = 9 * SLAB_B_TAP_BYTES;
+constexpr size_t SLAB_SMEM = 1024 + (size_t)SLAB_SLOTS * SLAB_ROW_BYTES + SLAB_B_BYTES + 1024 + 2 * OUT_STAGE_BYTES;
 
-template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapO, const TcParams p) {
-  using Cfg = SlabCfg<CTAS>;
-  constexpr int SLOTS = Cfg::SLOTS;
+  constexpr int SLOTS = SLAB_SLOTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* rows = smem;
   uint8_t* bmat = rows + (size_t)SLOTS * SLAB_ROW_BYTES;
-  uint8_t* bar_base = bmat + Cfg::B_BYTES;
+  uint8_t* bar_base = bmat + SLAB_B_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + SLOTS;
   uint64_t* bfull_bar = empty_bar + SLOTS;
@@ -558,12 +515,10 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
-  const int unit_id = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int rows_per_tile = 4 * CTAS;
-  const int tiles_per_img = p.Hout / rows_per_tile;
-  // contiguous range of (pair) super rows for this CTA (pair)
+  const int unit_id = (int)blockIdx.x;
+  const int n_units = (int)gridDim.x;
+  const int tiles_per_img = p.Hout / 4;
+  // contiguous range of super rows (4 output rows) for this CTA
   const int st_begin = (int)(((long long)p.total_tiles * unit_id) / n_units);
   const int st_end = (int)(((long long)p.total_tiles * (unit_id + 1)) / n_units);
 
@@ -579,23 +534,17 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     mbar_init(smem_u32(bfull_bar), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 8 * CTAS);
+      mbar_init(smem_u32(&tempty_bar[i]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    if (CTAS == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only parameters, shared memory and TMEM; the activations are the previous kernel's
@@ -604,36 +553,26 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    const uint32_t full0 = CTAS == 2 ? mapa_u32(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-    const uint32_t bfull = CTAS == 2 ? mapa_u32(smem_u32(bfull_bar), 0) : smem_u32(bfull_bar);
+    const uint32_t full0 = smem_u32(&full_bar[0]);
+    const uint32_t bfull = smem_u32(bfull_bar);
     if (elect_one()) {
-      if (cta_rank == 0) mbar_arrive_expect_tx(bfull, (uint32_t)CTAS * Cfg::B_BYTES);
-      for (int t = 0; t < 9; ++t) {
-        if (CTAS == 2)
-          tma_load_2d_2sm(smem_u32(bmat) + (uint32_t)t * Cfg::B_TAP_BYTES, &tmapB, bfull, t * BK, (int)cta_rank * 32);
-        else
-          tma_load_2d(smem_u32(bmat) + (uint32_t)t * Cfg::B_TAP_BYTES, &tmapB, bfull, t * BK, 0);
-      }
+      mbar_arrive_expect_tx(bfull, SLAB_B_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(bmat) + (uint32_t)t * SLAB_B_TAP_BYTES, &tmapB, bfull, t * BK, 0);
     }
     __syncwarp();
     uint32_t L = 0;   // row-load counter: load L goes to slot L % SLOTS, use (L / SLOTS)
     for (int st = st_begin; st < st_end; ++st) {
       const int img = st / tiles_per_img;
-      const int y0 = (st - img * tiles_per_img) * rows_per_tile + 4 * (int)cta_rank;
-      // single CTA: rows y0-1, y0 are the previous super row's last two (pairs skip 4 rows: nothing to reuse)
-      const bool carry = CTAS == 1 && (st > st_begin) && (y0 != 0);
+      const int y0 = (st - img * tiles_per_img) * 4;
+      // rows y0-1, y0 are the previous super row's last two
+      const bool carry = (st > st_begin) && (y0 != 0);
       for (int q = carry ? 2 : 0; q < 6; ++q) {
         const uint32_t slot = L % SLOTS, use = L / SLOTS;
         mbar_wait(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
         if (elect_one()) {
           const uint32_t fb = full0 + slot * 8u;
-          if (CTAS == 2) {
-            if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2u * SLAB_ROW_TX);
-            tma_load_4d_2sm(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
-          } else {
-            mbar_arrive_expect_tx(fb, SLAB_ROW_TX);
-            tma_load_4d(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
-          }
+          mbar_arrive_expect_tx(fb, SLAB_ROW_TX);
+          tma_load_4d(smem_u32(rows) + slot * SLAB_ROW_BYTES, &tmapA, fb, 0, -1, y0 - 1 + q, img);
         }
         __syncwarp();
         ++L;
@@ -641,79 +580,66 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (cta_rank == 0) {
-      mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
-      uint32_t base = 0, waited = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int st = st_begin; st < st_end; ++st) {
-        const int y0 = (st % tiles_per_img) * rows_per_tile;
-        const bool next_carry = CTAS == 1 && (st + 1 < st_end) && (y0 + 4 < p.Hout);
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 4 * 64);
-        for (int r = 0; r < 3; ++r) {
-          while (waited <= base + (uint32_t)r + 3u) {
-            mbar_wait(smem_u32(&full_bar[waited % SLOTS]), (waited / SLOTS) & 1, p.errflag, 3);
-            ++waited;
-          }
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3 + s) * Cfg::B_TAP_BYTES);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const uint32_t slot = (base + (uint32_t)(r + g)) % SLOTS;
-                  const uint32_t a_addr = smem_u32(rows) + slot * SLAB_ROW_BYTES + (uint32_t)s * 128u;
-                  if (CTAS == 2)
-                    tc_mma_bf16_2sm(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
-                                    bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
-                  else
-                    tc_mma_bf16(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
-                                bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
-                }
-              }
-            }
-            // release the rows whose last use was this tap row (in both CTAs of a pair)
-            auto release = [&](uint32_t ln) {
-              if (CTAS == 2) tc_commit_2sm(smem_u32(&empty_bar[ln % SLOTS])); else tc_commit(smem_u32(&empty_bar[ln % SLOTS]));
-            };
-            if (r < 2) {
-              release(base + (uint32_t)r);
-            } else {
-              release(base + 2u);
-              release(base + 3u);
-              if (!next_carry) {
-                release(base + 4u);
-                release(base + 5u);
-              }
-            }
-          }
-          __syncwarp();
+    mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
+    uint32_t base = 0, waited = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int st = st_begin; st < st_end; ++st) {
+      const int y0 = (st % tiles_per_img) * 4;
+      const bool next_carry = (st + 1 < st_end) && (y0 + 4 < p.Hout);
+      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.errflag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 4 * 64);
+      for (int r = 0; r < 3; ++r) {
+        while (waited <= base + (uint32_t)r + 3u) {
+          mbar_wait(smem_u32(&full_bar[waited % SLOTS]), (waited / SLOTS) & 1, p.errflag, 3);
+          ++waited;
         }
+        tc_fence_after();
         if (elect_one()) {
-          if (CTAS == 2) tc_commit_2sm(smem_u32(&tfull_bar[acc])); else tc_commit(smem_u32(&tfull_bar[acc]));
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3 + s) * SLAB_B_TAP_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t slot = (base + (uint32_t)(r + g)) % SLOTS;
+                const uint32_t a_addr = smem_u32(rows) + slot * SLAB_ROW_BYTES + (uint32_t)s * 128u;
+                tc_mma_bf16(d_tmem + (uint32_t)(g * 64), make_sdesc(a_addr) + (uint64_t)(2 * k),
+                            bdesc + (uint64_t)(2 * k), p.idesc, (r | s | k) ? 1u : 0u);
+              }
+            }
+          }
+          // release the rows whose last use was this tap row
+          auto release = [&](uint32_t ln) { tc_commit(smem_u32(&empty_bar[ln % SLOTS])); };
+          if (r < 2) {
+            release(base + (uint32_t)r);
+          } else {
+            release(base + 2u);
+            release(base + 3u);
+            if (!next_carry) {
+              release(base + 4u);
+              release(base + 5u);
+            }
+          }
         }
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        base += next_carry ? 4u : 6u;
       }
+      if (elect_one()) tc_commit(smem_u32(&tfull_bar[acc]));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      base += next_carry ? 4u : 6u;
     }
   } else if (warp >= 4) {
-    epilogue_loop<CTAS, 1>(p, &tmapO, stage_out, tfull_bar, tempty_bar, tmem_base, cta_rank, st_begin, st_end, 1);
+    epilogue_loop<1, 1>(p, &tmapO, stage_out, tfull_bar, tempty_bar, tmem_base, 0u, st_begin, st_end, 1);
   }
 
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    if (CTAS == 2)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -761,19 +687,12 @@ bool make_plan(const ConvWeights& w, const ConvArgs& a, TcPlan* pl) {
   int G = 1;
   for (int g = MAX_G; g >= 1; g >>= 1)
     if (2 * g * pl->BN <= 512 && g * ((pl->BN + 63) / 64) <= 4 && m_tiles % g == 0) { G = g; break; }
-  if (const char* e = getenv("BDRC_TC_G")) {
-    const int want = atoi(e);
-    if (want >= 1 && want <= G && m_tiles % want == 0) G = want;
-  }
   pl->G = G;
   // CTA pairs (cta_group::2) whenever the pixel tiles split evenly over the two CTAs
   // and the K loop is long enough to amortise the pair's coupled accumulator hand-off (measured: pairs win
   // on the 3x3 / k-tap layers with N >= 128, lose on 1x1 layers whose tiles are epilogue-bound)
   const int k_iters = w.R * w.S * (w.Cin_pad / BK);
   pl->ctas = (pl->BN >= 128 && pl->BN % 16 == 0 && k_iters >= 16 && m_tiles % (2 * G) == 0) ? 2 : 1;
-  if (const char* e = getenv("BDRC_TC_CTAS"))
-    if (atoi(e) == 1) pl->ctas = 1;
-    else if (atoi(e) == 2 && pl->BN >= 64 && pl->BN % 16 == 0 && m_tiles % (2 * G) == 0) pl->ctas = 2;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * G * pl->BN)) cols <<= 1;
   pl->tmem_cols = cols;
@@ -809,132 +728,120 @@ int conv_tc_supported(const ConvWeights& w, const ConvArgs& a) {
 namespace {
 
 bool slab_eligible(const ConvWeights& w, const ConvArgs& a) {
-  if (a.head_w) return false;
-  if (const char* e = getenv("BDRC_TC_SLAB"))
-    if (atoi(e) == 0) return false;
   return w.R == 3 && w.S == 3 && a.stride_h == 1 && a.stride_w == 1 && a.dil_h == 1 && a.dil_w == 1 && a.pad_h == 1 &&
          a.pad_w == 1 && w.Cin == 64 && w.Cin_pad == 64 && w.Cout_pad == 64 && a.Win == 128 && a.Wout == 128 &&
          a.Hin == a.Hout && a.Hout % 4 == 0 && !a.out_fp32 && a.out_ld % 8 == 0 && a.out_coff % 8 == 0 &&
          a.in_ld % 8 == 0 && a.in_coff % 8 == 0 && a.N >= 1;
 }
 
-int conv_tc_slab_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-  // The pair variant (BDRC_TC_SLAB=2) is correct but measured SLOWER than the single-CTA one (608 against 674
-  // TFLOP/s at 148 tiles): at N = 64 the operand path is bound by the 4 KB of A per MMA, which pairing does not
-  // reduce, and the pair adds a coupled accumulator hand-off.  Default: single CTA.
-  int ctas = 1;
-  if (const char* e = getenv("BDRC_TC_SLAB"))
-    if (atoi(e) == 2 && a.Hout % 8 == 0) ctas = 2;
+// Everything one launch needs.  Built once per distinct (weights, ConvArgs) and kept in the context
+// (TcCache): a forward re-uses the same few dozen entries call after call, so the steady state encodes no
+// tensor maps and derives no tiling on the host.
+enum { TC_GENERIC1 = 0, TC_GENERIC2 = 1, TC_SLAB = 2 };
+struct TcLaunch {
   CUtensorMap mapA, mapB, mapO;
+  TcParams p;
+  int kind = TC_GENERIC1;
+  unsigned grid = 0;
+  size_t smem = 0;
+};
+
+// POD key: every field of the problem that reaches a tensor map or TcParams (padding bytes zeroed by memset)
+struct TcKey {
+  const void *w, *b, *in, *out, *residual, *bias_override;
+  int Cout, Cout_pad, Cin, Cin_pad, R, S;
+  int N, Hin, Win, in_ld, in_coff, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, Hout, Wout;
+  int bias_img_stride, res_ld, out_ld, out_coff, out_fp32, relu, sm_count;
+};
+
+}  // namespace
+
+struct TcCache {
+  std::mutex mu;
+  std::unordered_map<std::string, TcLaunch> map;
+};
+
+void conv_tc_cache_free(bdrc_ctx* ctx) {
+  delete reinterpret_cast<TcCache*>(ctx->tc_cache);
+  ctx->tc_cache = nullptr;
+}
+
+namespace {
+
+int encode(bdrc_ctx* ctx, EncodeTiledFn enc, CUtensorMap* m, int rank, void* base, const cuuint64_t* dims,
+           const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapL2promotion l2, const char* what) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+  return 0;
+}
+
+int encode_weights(bdrc_ctx* ctx, EncodeTiledFn enc, CUtensorMap* m, const ConvWeights& w, int box_n) {
+  const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
+  cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
+  cuuint64_t strides[1] = {K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_n};
+  return encode(ctx, enc, m, 2, w.w, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "weights");
+}
+
+int encode_out(bdrc_ctx* ctx, EncodeTiledFn enc, CUtensorMap* m, const ConvWeights& w, const ConvArgs& a, int BW, int BH) {
+  const cuuint64_t ld = (cuuint64_t)a.out_ld;
+  cuuint64_t dims[4] = {(cuuint64_t)w.Cout, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
+  cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  return encode(ctx, enc, m, 4, reinterpret_cast<bf16*>(a.out) + a.out_coff, dims, strides, box,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, "out");
+}
+
+void common_params(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, TcParams* p) {
+  p->n_img = a.N;
+  p->par_c = a.in_ld;
+  p->Hout = a.Hout; p->Wout = a.Wout; p->Cout = w.Cout;
+  p->bias = a.bias_override ? a.bias_override : w.b;
+  p->bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
+  p->residual = a.residual; p->res_ld = a.res_ld;
+  p->out = a.out; p->out_ld = a.out_ld; p->out_coff = a.out_coff; p->out_fp32 = a.out_fp32;
+  p->relu = a.relu;
+  p->errflag = ctx->d_errflag;
+  p->dbg_skip = 0;
+#ifdef BDRC_EXPERIMENTS
+  if (const char* e = getenv("BDRC_DBG_SKIP")) p->dbg_skip = atoi(e);
+#endif
+}
+
+int build_slab(bdrc_ctx* ctx, EncodeTiledFn enc, const ConvWeights& w, const ConvArgs& a, TcLaunch* L) {
   {
     const cuuint64_t ld = (cuuint64_t)a.in_ld;
     cuuint64_t dims[4] = {(cuuint64_t)w.Cin, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.N};
     cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Win * ld * 2, (cuuint64_t)a.Hin * a.Win * ld * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, 130, 1, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(a.in) + a.in_coff, dims, strides, box,
-                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab A) failed: %d", (int)r);
+    BDRC_TRY(encode(ctx, enc, &L->mapA, 4, const_cast<bf16*>(a.in) + a.in_coff, dims, strides, box,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "slab A"));
   }
-  {
-    const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
-    cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
-    cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(64 / ctas)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab B) failed: %d", (int)r);
-  }
-  {
-    const cuuint64_t ld = (cuuint64_t)a.out_ld;
-    cuuint64_t dims[4] = {(cuuint64_t)w.Cout, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
-    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
-    cuuint32_t box[4] = {64, 128, 1, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, reinterpret_cast<bf16*>(a.out) + a.out_coff, dims,
-                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(slab out) failed: %d", (int)r);
-  }
-  TcParams p;
-  p.tiles_n = 1; p.tiles_w = 1; p.tiles_h = a.Hout; p.n_img = a.N;
-  p.total_tiles = a.N * (a.Hout / (4 * ctas));
+  BDRC_TRY(encode_weights(ctx, enc, &L->mapB, w, 64));
+  BDRC_TRY(encode_out(ctx, enc, &L->mapO, w, a, 128, 1));
+  TcParams& p = L->p;
+  common_params(ctx, w, a, &p);
+  p.tiles_n = 1; p.tiles_w = 1; p.tiles_h = a.Hout;
+  p.total_tiles = a.N * (a.Hout / 4);
   p.BW = 128; p.BH = 1; p.BN = 64; p.stages = 0; p.G = 4;
   p.R = 3; p.S = 3; p.kchunks = 1;
   p.stride_h = p.stride_w = 1; p.pad_h = p.pad_w = 1; p.dil_h = p.dil_w = 1;
-  p.par_c = a.in_ld;
-  p.Hout = a.Hout; p.Wout = a.Wout; p.Cout = w.Cout;
-  p.idesc = make_idesc_bf16(BM * ctas, 64);
+  p.idesc = make_idesc_bf16(BM, 64);
   p.tmem_cols = 512;
-  p.bias = a.bias_override ? a.bias_override : w.b;
-  p.bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
-  p.residual = a.residual; p.res_ld = a.res_ld;
-  p.out = a.out; p.out_ld = a.out_ld; p.out_coff = a.out_coff; p.out_fp32 = 0;
-  p.relu = a.relu;
+  p.out_fp32 = 0;
   p.out_tma = 1;
-  p.errflag = ctx->d_errflag;
-  p.dbg_skip = 0;
-  p.head_w = nullptr; p.head_b = nullptr; p.head_out = nullptr; p.head_C = 0; p.head_ld = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)SlabCfg<1>::SMEM));
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)SlabCfg<2>::SMEM));
-    attr_set = true;
-  }
-  if (ctas == 2) {
-    const int pairs = ctx->sm_count / 2;
-    const int units = p.total_tiles < pairs ? p.total_tiles : pairs;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SlabCfg<2>::SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<2>, mapA, mapB, mapO, p));
-  } else {
-    const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SlabCfg<1>::SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel<1>, mapA, mapB, mapO, p));
-  }
-  BDRC_CHECK_LAUNCH(ctx);
+  L->kind = TC_SLAB;
+  L->grid = (unsigned)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
+  L->smem = SLAB_SMEM;
   return 0;
 }
 
-}  // namespace
-
-int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
-  if (slab_eligible(w, a)) return conv_tc_slab_launch(ctx, w, a, s);
+int build_generic(bdrc_ctx* ctx, EncodeTiledFn enc, const ConvWeights& w, const ConvArgs& a, TcLaunch* L) {
   TcPlan pl;
   if (!make_plan(w, a, &pl)) return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED, "conv_tc: unsupported shape");
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-
   const int sw = a.stride_w, sh = a.stride_h;
-  CUtensorMap mapA, mapB;
   {
     const cuuint64_t ld = (cuuint64_t)a.in_ld;
     cuuint64_t dims[5] = {sw == 2 ? 2 * ld : (cuuint64_t)w.Cin, (cuuint64_t)(a.Win / sw),
@@ -942,111 +849,112 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     cuuint64_t strides[4] = {(cuuint64_t)sw * ld * 2, (cuuint64_t)a.Win * ld * 2,
                              (cuuint64_t)sh * a.Win * ld * 2, (cuuint64_t)a.Hin * a.Win * ld * 2};
     cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)pl.BW, 1, (cuuint32_t)pl.BH, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    void* base = const_cast<bf16*>(a.in) + a.in_coff;
-    CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-      return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    BDRC_TRY(encode(ctx, enc, &L->mapA, 5, const_cast<bf16*>(a.in) + a.in_coff, dims, strides, box,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A"));
   }
-  {
-    const cuuint64_t K = (cuuint64_t)w.R * w.S * w.Cin_pad;
-    cuuint64_t dims[2] = {K, (cuuint64_t)w.Cout_pad};
-    cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(pl.BN / pl.ctas)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.w, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-      return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-  }
-
-  CUtensorMap mapO = mapB;
+  BDRC_TRY(encode_weights(ctx, enc, &L->mapB, w, pl.BN / pl.ctas));
   const int out_tma = (!a.out_fp32 && a.out_ld % 8 == 0 && a.out_coff % 8 == 0) ? 1 : 0;
-  if (out_tma) {
-    const cuuint64_t ld = (cuuint64_t)a.out_ld;
-    cuuint64_t dims[4] = {(cuuint64_t)w.Cout, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
-    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)pl.BW, (cuuint32_t)pl.BH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    void* base = reinterpret_cast<bf16*>(a.out) + a.out_coff;
-    CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-      return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
-  }
+  L->mapO = L->mapB;
+  if (out_tma) BDRC_TRY(encode_out(ctx, enc, &L->mapO, w, a, pl.BW, pl.BH));
 
-  TcParams p;
-  p.tiles_n = pl.tiles_n; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_img = a.N;
+  TcParams& p = L->p;
+  common_params(ctx, w, a, &p);
+  p.tiles_n = pl.tiles_n; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.total_tiles = pl.tiles_n * ((pl.tiles_w * pl.tiles_h * a.N) / (pl.G * pl.ctas));   // super tiles (per CTA / pair)
   p.BW = pl.BW; p.BH = pl.BH; p.BN = pl.BN; p.stages = pl.stages; p.G = pl.G;
   p.R = w.R; p.S = w.S; p.kchunks = w.Cin_pad / BK;
   p.stride_h = sh; p.stride_w = sw; p.pad_h = a.pad_h; p.pad_w = a.pad_w;
   p.dil_h = a.dil_h; p.dil_w = a.dil_w;
-  p.par_c = a.in_ld;
-  p.Hout = a.Hout; p.Wout = a.Wout; p.Cout = w.Cout;
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128 (256 for a CTA pair)
   p.idesc = make_idesc_bf16(BM * pl.ctas, pl.BN);
   p.tmem_cols = pl.tmem_cols;
-  p.bias = a.bias_override ? a.bias_override : w.b;
-  p.bias_img_stride = a.bias_override ? a.bias_img_stride : 0;
-  p.residual = a.residual; p.res_ld = a.res_ld;
-  p.out = a.out; p.out_ld = a.out_ld; p.out_coff = a.out_coff; p.out_fp32 = a.out_fp32;
-  p.relu = a.relu;
   p.out_tma = out_tma;
-  p.errflag = ctx->d_errflag;
-  {
-    const char* e = getenv("BDRC_DBG_SKIP");
-    p.dbg_skip = e ? atoi(e) : 0;
-  }
-  p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = a.head_out; p.head_C = a.head_C; p.head_ld = a.head_C;
-  if (a.head_w) {
-    if (pl.tiles_n != 1 || pl.G != 1 || pl.ctas != 1 || a.head_C < 1 || a.head_C > 8 || pl.BN % 64 != 0)
-      return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED, "conv_tc: fused head needs one column tile, G = 1 and <= 8 classes");
-    p.out_tma = 0;
-  }
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    BDRC_CUDA(ctx, cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
-  }
+  L->smem = pl.smem_bytes;
   if (pl.ctas == 2) {
     const int pairs = ctx->sm_count / 2;
-    const int units = p.total_tiles < pairs ? p.total_tiles : pairs;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = pl.smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, mapA, mapB, mapO, p));
+    L->kind = TC_GENERIC2;
+    L->grid = 2u * (unsigned)(p.total_tiles < pairs ? p.total_tiles : pairs);
   } else {
-    int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = pl.smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, mapA, mapB, mapO, p));
+    L->kind = TC_GENERIC1;
+    L->grid = (unsigned)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
   }
+  return 0;
+}
+
+}  // namespace
+
+int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaStream_t s) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return bdrc_fail(ctx, BDRC_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  static std::once_flag attr_once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+    attr_rc = e;
+  });
+  if (attr_rc != cudaSuccess)
+    return bdrc_fail(ctx, BDRC_ERR_CUDA, "cudaFuncSetAttribute(conv_tc) -> %s", cudaGetErrorString(attr_rc));
+
+  TcKey key;
+  memset(&key, 0, sizeof(key));
+  key.w = w.w; key.b = w.b; key.in = a.in; key.out = a.out; key.residual = a.residual; key.bias_override = a.bias_override;
+  key.Cout = w.Cout; key.Cout_pad = w.Cout_pad; key.Cin = w.Cin; key.Cin_pad = w.Cin_pad; key.R = w.R; key.S = w.S;
+  key.N = a.N; key.Hin = a.Hin; key.Win = a.Win; key.in_ld = a.in_ld; key.in_coff = a.in_coff;
+  key.stride_h = a.stride_h; key.stride_w = a.stride_w; key.pad_h = a.pad_h; key.pad_w = a.pad_w;
+  key.dil_h = a.dil_h; key.dil_w = a.dil_w; key.Hout = a.Hout; key.Wout = a.Wout;
+  key.bias_img_stride = a.bias_img_stride; key.res_ld = a.res_ld; key.out_ld = a.out_ld; key.out_coff = a.out_coff;
+  key.out_fp32 = a.out_fp32; key.relu = a.relu; key.sm_count = ctx->sm_count;
+  const std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
+
+  TcLaunch L;
+  {
+    if (!ctx->tc_cache) {
+      static std::mutex create_mu;
+      std::lock_guard<std::mutex> g(create_mu);
+      if (!ctx->tc_cache) ctx->tc_cache = new TcCache();
+    }
+    TcCache* cache = reinterpret_cast<TcCache*>(ctx->tc_cache);
+    std::lock_guard<std::mutex> g(cache->mu);
+    auto it = cache->map.find(k);
+    if (it == cache->map.end()) {
+      TcLaunch fresh;
+      BDRC_TRY(slab_eligible(w, a) ? build_slab(ctx, enc, w, a, &fresh) : build_generic(ctx, enc, w, a, &fresh));
+      if (cache->map.size() >= 8192) cache->map.clear();   // callers that never repeat a buffer address
+      it = cache->map.emplace(k, fresh).first;
+      ctx->tc_plans_built++;
+    }
+    L = it->second;
+  }
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (L.kind == TC_GENERIC2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (a.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (L.kind == TC_GENERIC2)
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, L.mapA, L.mapB, L.mapO, L.p));
+  else if (L.kind == TC_GENERIC1)
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, L.mapA, L.mapB, L.mapO, L.p));
+  else
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel, L.mapA, L.mapB, L.mapO, L.p));
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

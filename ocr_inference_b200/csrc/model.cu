@@ -72,8 +72,6 @@ struct bdrc_model {
   float* pool_w = nullptr;        // [256][512]
   float* pool_b = nullptr;
   float* proj_b = nullptr;
-  float* head_wf = nullptr;       // [C][256] fp32 holding the bf16-rounded head weights (fused-head epilogue)
-  float* head_bf = nullptr;       // [C]
   int ocr_in_h = 0;
 };
 
@@ -214,15 +212,6 @@ int load_seg(Loader& L, int n_classes) {
   BDRC_TRY(L.depthwise("decoder.block2.0.0", 304));
   BDRC_TRY(L.conv("decoder.block2.0.1", 256, 304, 1, 1));
   BDRC_TRY(L.conv("segmentation_head.0", n_classes, 256, 1, 1));
-  {
-    const BlobTensor* hw = L.get("segmentation_head.0.weight", {n_classes, 256, 1, 1});
-    const BlobTensor* hb = L.get("segmentation_head.0.bias", {n_classes});
-    if (!hw || !hb) return BDRC_ERR_WEIGHTS;
-    std::vector<float> wf(hw->numel);
-    for (size_t i = 0; i < hw->numel; ++i) wf[i] = __bfloat162float(__float2bfloat16(hw->data[i]));   // as conv_pack_weights stores them
-    BDRC_TRY(dev_copy(ctx, m, wf, &m->head_wf));
-    BDRC_TRY(dev_copy(ctx, m, std::vector<float>(hb->data, hb->data + n_classes), &m->head_bf));
-  }
   return 0;
 }
 
@@ -350,7 +339,7 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   if (!A.ok) return bdrc_fail(ctx, BDRC_ERR_ARG, "seg_forward: workspace too small");
 
   // stem + maxpool (ipynb:L233-L238)
-  if (cin == 1 && ctx->conv_engine == 0 && !getenv("BDRC_NO_STEM_TC")) {
+  if (cin == 1 && ctx->conv_engine == 0) {
     // binarised tiles: tcgen05 stem fused with the max-pool, the 256x256x64 activation stays on chip
     bdrc_prof_begin(ctx, "stem7x7+maxpool", 2.0 * n * 256 * 256 * 64 * 49 * 3, s);
     BDRC_TRY(stem_tc_pool_launch(ctx, reinterpret_cast<const uint8_t*>(tiles), n, m->stem_wb, m->stem_b, buf[0], s));
@@ -417,13 +406,7 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
       dwo[i] = dws + i * br;
     }
     bdrc_prof_begin(ctx, "aspp.dw3x3", 2.0 * n * 32 * 32 * 512 * 9 * 3, s);
-    if (getenv("BDRC_NO_ASPP_FUSED")) {
-      for (int i = 0; i < 3; ++i)
-        BDRC_TRY(depthwise3x3_launch(ctx, x, 512, 0, n, 32, 32, 512, rates[i], dww[i], dwo[i], 512, 0, s));
-      gmean = nullptr;
-    } else {
-      BDRC_TRY(aspp_dw3_launch(ctx, x, n, 512, rates, dww, dwo, gmean, s));
-    }
+    BDRC_TRY(aspp_dw3_launch(ctx, x, n, 512, rates, dww, dwo, gmean, s));
     bdrc_prof_end(ctx, s);
     for (int i = 0; i < 3; ++i)
       BDRC_TRY(conv_launch(ctx, "aspp.1x1", m->conv["decoder.aspp.0.convs." + std::to_string(i + 1) + ".0.1"],
@@ -453,20 +436,11 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   BDRC_TRY(depthwise3x3_launch(ctx, dcat, 304, 0, n, 128, 128, 304, 1, m->dw["decoder.block2.0.0"].w9c, d2dw, 304, 0, s));
   bdrc_prof_end(ctx, s);
   // 1x1 304 -> 256 + ReLU, then the head 1x1 256 -> C (ipynb:L455-L466); fp32 NHWC low-res logits.
-  // BDRC_HEAD_FUSE=1 folds the head (<= 8 classes) into the first conv's epilogue as a per-pixel dot product,
-  // so the 256-channel activation (403 MB per 48 tiles) is never stored.  Correct and deterministic, but
-  // MEASURED SLOWER (0.322 ms against 0.184 + 0.083 ms): this layer has only 5 K steps per tile and is already
-  // epilogue-bound, the SIMT dot product doubles the epilogue.  Kept off; the way to win is to feed the staged
-  // bf16 tile back to the tensor cores as the A operand of a second, 16-column MMA.
-  const char* hf = getenv("BDRC_HEAD_FUSE");
-  const bool fuse_head = ctx->conv_engine == 0 && C <= 8 && hf && atoi(hf) == 1;
-  if (fuse_head) {
-    ConvArgs a = mk(d2dw, n, 128, 128, 304, 0, 1, 1, 1, d2pw, 256, 0, 1);
-    a.head_w = m->head_wf; a.head_b = m->head_bf; a.head_out = low; a.head_C = C;
-    BDRC_TRY(conv_launch(ctx, "dec.1x1+head", m->conv["decoder.block2.0.1"], a, s));
-  } else {
-    BDRC_TRY(conv_launch(ctx, "dec.1x1", m->conv["decoder.block2.0.1"],
-                         mk(d2dw, n, 128, 128, 304, 0, 1, 1, 1, d2pw, 256, 0, 1), s));
+  // (A SIMT per-pixel dot product for the head inside the first conv's epilogue was built in round 1 and
+  // measured slower, 0.322 ms against 0.184 + 0.083 ms per 48 tiles: the layer is epilogue-bound.  Removed.)
+  BDRC_TRY(conv_launch(ctx, "dec.1x1", m->conv["decoder.block2.0.1"],
+                       mk(d2dw, n, 128, 128, 304, 0, 1, 1, 1, d2pw, 256, 0, 1), s));
+  {
     ConvArgs a = mk(d2pw, n, 128, 128, 256, 0, 1, 1, 1, low, low_ld, 0, 0);
     a.out_fp32 = 1;
     BDRC_TRY(conv_launch(ctx, "head1x1", m->conv["segmentation_head.0"], a, s));
@@ -512,6 +486,7 @@ ConvArgs mk1d(const bf16* in, int L, int T, int ld, int k, int stride, int dil, 
   a.pad_h = 0; a.pad_w = (k / 2) * dil;
   a.Hout = 1; a.Wout = (T + 2 * a.pad_w - dil * (k - 1) - 1) / stride + 1;
   a.out = out; a.out_ld = out_ld; a.out_coff = 0; a.relu = relu;
+  a.pdl = 1;   // the Easter2 chain is short (26 launches): PDL gains 3 % at 64 lines (conv_tc.cu)
   return a;
 }
 

@@ -675,7 +675,7 @@ int depthwise3x3_launch(bdrc_ctx* ctx, const bf16* in, int in_ld, int in_coff, i
                         cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
                "depthwise: channel counts must be multiples of 8");
-  if (dil == 1 && W % DWR_PX == 0 && bdrc_tma_encode_fn() != nullptr && !getenv("BDRC_NO_DW_RING")) {
+  if (dil == 1 && W % DWR_PX == 0 && bdrc_tma_encode_fn() != nullptr) {
     CUtensorMap map;
     const cuuint64_t ld = (cuuint64_t)in_ld;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};

@@ -145,6 +145,12 @@ class Engine:
         slot[1] = ev
         return d, ev
 
+    def simt_launch_count(self) -> int:
+        return self.ctx.simt_launch_count()
+
+    def conv_plans_built(self) -> int:
+        return self.ctx.conv_plans_built()
+
     def launch_count(self) -> int:
         return self.ctx.launch_count()
 

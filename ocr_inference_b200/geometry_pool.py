@@ -67,6 +67,7 @@ class GeometryPool:
         self._pending: dict[int, tuple[Future, shared_memory.SharedMemory]] = {}
         self._ticket = 0
         self._closed = False
+        self._broken = False
         import queue
         import time
 
@@ -102,11 +103,13 @@ class GeometryPool:
                     s = shared_memory.SharedMemory(create=True, size=max(nbytes, self._slot_bytes))
                     self._all.append(s)
                     return s
-                self._cv.wait()
+                if self._closed or self._broken:
+                    raise RuntimeError("GeometryPool: closed or a worker process died")
+                self._cv.wait(timeout=1.0)
 
     def submit(self, mask: np.ndarray, merge_lines: bool = True) -> Future:
-        if self._closed:
-            raise RuntimeError("GeometryPool is closed")
+        if self._closed or self._broken:
+            raise RuntimeError("GeometryPool is closed or a worker process died")
         if mask.ndim != 2 or mask.dtype != np.uint8:
             raise ValueError("GeometryPool.submit: the line mask must be a 2-D u8 array")
         slot = self._slot(mask.nbytes)
@@ -127,9 +130,13 @@ class GeometryPool:
                 msg = self._results.get(timeout=1.0)
             except queue.Empty:
                 if any(p.exitcode not in (None, 0) for p in self._procs):
+                    # fail everything in flight AND hand the slots back: callers blocked in _slot() must wake up
                     with self._cv:
+                        self._broken = True
                         pend = list(self._pending.values())
                         self._pending.clear()
+                        self._free.extend(slot for _, slot in pend)
+                        self._cv.notify_all()
                     for fut, _ in pend:
                         fut.set_exception(RuntimeError("GeometryPool: a worker process died"))
                 continue

@@ -77,16 +77,25 @@ def run_tps(image: np.ndarray, input_pts, output_pts, add_corners: bool = True, 
     return remap(src, tps.control_points, tps.parameters).cpu().numpy()
 
 
-def _slice_center(mask_roi: np.ndarray, x0: int, x1: int, gx: int, gy: int):
-    """get_global_center (:77-115) on a column slice [x0, x1) of a line's ROI mask."""
-    sl = np.ascontiguousarray(mask_roi[:, max(x0, 0):max(x1, 0)])
+def _slice_center(mask_roi: np.ndarray, s0: int, s1: int, x: int, y: int, page_w: int):
+    """get_global_center (:77-115) on the page columns [x + s0, x + s1) of a line whose filled contour is
+    `mask_roi` at page offset (x, y).  The reference slices a page-sized canvas, so a slice may reach beyond the
+    line's bounding box (lines narrower than 4 slice widths: zeros there) and follows Python's slice rules at
+    the page border; the x offset it adds back is the unclamped slice start."""
+    a, b, _ = slice(x + s0, x + s1).indices(page_w)
+    sl = np.zeros((mask_roi.shape[0], max(0, b - a)), np.uint8)
+    lo, hi = max(a, x), min(b, x + mask_roi.shape[1])
+    if hi > lo:
+        sl[:, lo - a:hi - a] = mask_roi[:, lo - x:hi - x]
+    gx = x + s0
     found, _ = cv2.findContours(sl, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE) if sl.size else ((), None)
     if not found:
-        return gx + sl.shape[1] // 2, gy + sl.shape[0] // 2, sl.shape[0]
-    big = max(found, key=cv2.contourArea)
+        return gx + sl.shape[1] // 2, y + sl.shape[0] // 2, sl.shape[0]
+    areas = [cv2.contourArea(c) for c in found]
+    big = found[areas.index(max(areas))]
     _, _, _, bh = cv2.boundingRect(big)
     (cx, cy), _, _ = cv2.minAreaRect(big)
-    return gx + int(cx), gy + int(cy), bh
+    return gx + int(cx), y + int(cy), bh
 
 
 def check_line_tps(image: np.ndarray, contour: np.ndarray, slice_width: int = 40):
@@ -96,7 +105,7 @@ def check_line_tps(image: np.ndarray, contour: np.ndarray, slice_width: int = 40
     roi = np.zeros((h, w), np.uint8)
     cv2.drawContours(roi, [contour], 0, 255, -1, offset=(-x, -y))
     starts = [0, w // 4 - slice_width, w // 2, w // 2 + w // 4, w - slice_width]
-    cs = [_slice_center(roi, s, s + slice_width, x + s, y) for s in starts]
+    cs = [_slice_center(roi, s, s + slice_width, x, y, image.shape[1]) for s in starts]
     ys = [c[1] for c in cs]
     spread = max(ys) - min(ys)
     if spread > np.mean([c[2] for c in cs]):

@@ -19,6 +19,7 @@ import torch
 from .data import (CharsetEncoder, DewarpingResult, Encoding, KenLMConfig, LayoutDetectionConfig,  # noqa: F401
                    Line, LineDetectionConfig, OCRLine, OCRModelConfig, OpStatus)
 from .engine import LAYOUT_TV, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
+from .weights import MAGIC, load_reference_checkpoint
 
 _ENGINES: dict[int, Engine] = {}
 
@@ -33,10 +34,17 @@ def get_engine(device: int | None = None) -> Engine:
 
 
 def _read_weights(src):
+    """dict of tensors / BDRCW1 bytes / path of a BDRCW1 container / path of a torch checkpoint of the
+    reference's torch path (an un-folded state dict: BatchNorm is folded here, weights.load_reference_checkpoint)."""
     if isinstance(src, dict) or isinstance(src, (bytes, bytearray)):
         return src
     with open(src, "rb") as f:
-        return f.read()
+        head = f.read(8)
+        if head == MAGIC:
+            return head + f.read()
+    if str(src).endswith((".pth", ".pt", ".ckpt")):
+        return load_reference_checkpoint(src)
+    raise ValueError(f"{src}: not a BDRCW1 weight container (convert the ONNX / checkpoint first, INTEGRATION.md)")
 
 
 class CTCDecoder:
@@ -619,12 +627,21 @@ class OCRPipeline:
             ring = getattr(det, "_up_slots", None)
             if ring is None:
                 ring = det._up_slots = [[None, None] for _ in range(4)]
-            with torch.cuda.stream(copy_in):
-                for k, i in enumerate(good):
-                    try:
-                        pages_dev[i], up_ev[i] = eng.upload_page(images[i], ring, k)
-                    finally:
-                        up_ready[i].set()
+            try:
+                with torch.cuda.stream(copy_in):
+                    for k, i in enumerate(good):
+                        # a page whose upload fails (pinned-alloc OOM, CUDA error) is left without an entry in
+                        # up_ev: its group fails, the page is retried through run_ocr, later pages still upload
+                        try:
+                            pages_dev[i], up_ev[i] = eng.upload_page(images[i], ring, k)
+                        except Exception:  # noqa: BLE001
+                            pages_dev.pop(i, None)
+                            up_ev.pop(i, None)
+                        finally:
+                            up_ready[i].set()
+            finally:
+                for ev in up_ready.values():      # whatever happened above, nobody waits forever
+                    ev.set()
 
         up_thread = threading.Thread(target=uploader, name="bdrc-upload", daemon=True)
         up_thread.start()
@@ -708,7 +725,10 @@ class OCRPipeline:
             g0 += group
             try:
                 for i in idx:
-                    up_ready[i].wait()
+                    if not up_ready[i].wait(timeout=300.0):
+                        raise TimeoutError("page upload did not finish")
+                    if i not in up_ev:
+                        raise RuntimeError("page upload failed")
                     compute.wait_event(up_ev[i])
                 masks = det._predict_device_batch([pages_dev[i] for i in idx], thr)
                 seg_done = torch.cuda.Event()
@@ -802,8 +822,29 @@ class ModernBookFormatLayoutDetection:
         self.classes = config.classes
         self.engine = engine or get_engine()
         self.device = "cuda"
-        src = config.checkpoint if config.checkpoint else config.onnx_file
-        self.model = self.engine.load_model(SEG, _read_weights(src), len(self.classes))
+        self.model = self.engine.load_model(SEG, _read_weights(self._weights_source(config)), len(self.classes))
+
+    @staticmethod
+    def _weights_source(config: LayoutDetectionConfig):
+        """The reference's torch path loads config.checkpoint (BDRC/inference.py:864).  Here: the BDRCW1 container
+        named by onnx_file (after utils._weights_path's `.bdrcw` substitution) when there is one, else the
+        checkpoint -- a BDRCW1 container, or the reference's own `.pth` (BatchNorm folded at load)."""
+        def is_blob(x):
+            if isinstance(x, (dict, bytes, bytearray)):
+                return True
+            try:
+                with open(x, "rb") as f:
+                    return f.read(8) == MAGIC
+            except (OSError, TypeError):
+                return False
+
+        for cand in (config.onnx_file, config.checkpoint):
+            if cand is not None and not (isinstance(cand, str) and cand == "") and is_blob(cand):
+                return cand
+        for cand in (config.checkpoint, config.onnx_file):
+            if isinstance(cand, str) and cand and os.path.exists(cand):
+                return cand
+        raise FileNotFoundError(f"no weights found: checkpoint={config.checkpoint!r}, onnx_file={config.onnx_file!r}")
 
     def predict_masks(self, image: np.ndarray, class_threshold: float = 0.8) -> np.ndarray:
         """RGB HWC u8 page -> u8 {0,255} masks [C, H, W] (what run() thresholds, :949-956)."""

@@ -58,7 +58,7 @@ def _worker(device, factory, factory_args, tasks, results, keep_mask):
         job = tasks.get()
         if job is None:
             return
-        idx, name, shape, kw = job
+        call, idx, name, shape, kw = job
         shm = None
         try:
             shm = shared_memory.SharedMemory(name=name)
@@ -68,9 +68,9 @@ def _worker(device, factory, factory_args, tasks, results, keep_mask):
                 payload = [None] + list(payload[1:])     # rot_mask is page-sized: only sent back on request
             elif isinstance(payload, list):
                 payload = [np.array(payload[0])] + list(payload[1:])
-            results.put(("done", idx, status, payload))
+            results.put(("done", call, idx, status, payload))
         except Exception:  # noqa: BLE001
-            results.put(("error", idx, traceback.format_exc()))
+            results.put(("error", call, idx, traceback.format_exc()))
         finally:
             if shm is not None:
                 shm.close()
@@ -111,6 +111,12 @@ class PipelinePool:
     def run_ocr_many(self, images: Sequence[np.ndarray], **run_ocr_kwargs):
         """[(OpStatus, payload)] like [OCRPipeline.run_ocr(i, **kw) for i in images] (payload[0], the rotated
         mask, is None unless the pool was built with return_masks=True)."""
+        from .data import OpStatus
+
+        # every call tags its jobs: results of an earlier call that was abandoned half-way (a dead worker)
+        # can never be mistaken for this call's pages
+        self._call = getattr(self, "_call", 0) + 1
+        call = self._call
         shms = []
         try:
             for idx, img in enumerate(images):
@@ -118,22 +124,34 @@ class PipelinePool:
                 shm = shared_memory.SharedMemory(create=True, size=max(1, img.nbytes))
                 np.ndarray(img.shape, dtype=np.uint8, buffer=shm.buf)[...] = img
                 shms.append(shm)
-                self._tasks.put((idx, shm.name, img.shape, run_ocr_kwargs))
+                self._tasks.put((call, idx, shm.name, img.shape, run_ocr_kwargs))
             out: list = [None] * len(images)
-            for _ in range(len(images)):
-                while True:
-                    try:
-                        msg = self._results.get(timeout=5)
-                        break
-                    except queue.Empty:
-                        if any(p.exitcode not in (None, 0) for p in self._procs):
-                            raise RuntimeError("PipelinePool: a worker process died") from None
+            got = 0
+            while got < len(images):
+                try:
+                    msg = self._results.get(timeout=5)
+                except queue.Empty:
+                    if any(p.exitcode not in (None, 0) for p in self._procs):
+                        # pages still in flight are lost with the worker; report them, keep the finished ones
+                        for i in range(len(images)):
+                            if out[i] is None:
+                                out[i] = (OpStatus.FAILED, "OCR pipeline failed: a PipelinePool worker process died")
+                        self._broken = True
+                        return out
+                    continue
+                if msg[1] != call:
+                    continue                      # stale result of an abandoned call
                 if msg[0] == "error":
-                    raise RuntimeError(f"PipelinePool: page {msg[1]} failed in a worker:\n{msg[2]}")
-                _, idx, status, payload = msg
-                out[idx] = (status, payload)
+                    _, _, idx, tb = msg
+                    out[idx] = (OpStatus.FAILED, f"OCR pipeline failed: {tb.strip().splitlines()[-1]}")
+                else:
+                    _, _, idx, status, payload = msg
+                    out[idx] = (status, payload)
+                got += 1
             return out
         finally:
+            if getattr(self, "_broken", False):
+                self.close()                      # workers may still read the shared pages: stop them first
             for shm in shms:
                 shm.close()
                 shm.unlink()

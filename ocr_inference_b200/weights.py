@@ -66,3 +66,55 @@ def read_blob(blob: bytes) -> dict[str, np.ndarray]:
 def from_torch_state_dict(sd) -> dict[str, np.ndarray]:
     """Convenience for users holding a BN-folded torch state dict (keys already in ONNX naming)."""
     return {k: v.detach().cpu().float().numpy() for k, v in sd.items()}
+
+
+def fold_batchnorm_state_dict(sd, eps: float = 1e-5) -> dict[str, np.ndarray]:
+    """An UN-folded torch state dict (what the reference's torch path loads: BDRC/utils.py:1175-1180,
+    `sm.DeepLabV3Plus(...).load_state_dict(checkpoint["state_dict"])`) -> the BN-folded tensors the B200 loader
+    expects, named like the exported ONNX initializers (PyTorch-LineInference.ipynb:L131-L230).
+
+    A state dict lists tensors in module-registration order, so the convolution a BatchNorm normalises is the
+    last 4-D `.weight` seen before the BatchNorm's `running_mean`: w' = w * g / sqrt(var + eps) per output
+    channel, b' = beta + (b - mean) * g / sqrt(var + eps).  Depthwise convs of the separable blocks keep their
+    names and no bias (the BatchNorm that follows the pointwise conv folds into the pointwise conv)."""
+    keys = list(sd.keys())
+    prefixes = [k[: -len(".running_mean")] for k in keys if k.endswith(".running_mean")]
+    bn_keys = {p + sfx for p in prefixes for sfx in (".weight", ".bias", ".running_mean", ".running_var",
+                                                     ".num_batches_tracked")}
+    get = lambda k: np.asarray(sd[k].detach().cpu().float().numpy() if hasattr(sd[k], "detach") else sd[k],  # noqa: E731
+                               dtype=np.float32)
+    out: dict[str, np.ndarray] = {}
+    last_conv = None
+    for k in keys:
+        if k in bn_keys:
+            if k.endswith(".running_mean"):
+                p = k[: -len(".running_mean")]
+                if last_conv is None:
+                    raise ValueError(f"BatchNorm '{p}' has no convolution before it")
+                g, beta = get(p + ".weight"), get(p + ".bias")
+                mean, var = get(p + ".running_mean"), get(p + ".running_var")
+                scale = g / np.sqrt(var + eps)
+                w = out[last_conv + ".weight"]
+                b = out.get(last_conv + ".bias", np.zeros(w.shape[0], np.float32))
+                out[last_conv + ".weight"] = (w * scale.reshape(-1, *([1] * (w.ndim - 1)))).astype(np.float32)
+                out[last_conv + ".bias"] = (beta + (b - mean) * scale).astype(np.float32)
+                last_conv = None
+            continue
+        v = get(k)
+        out[k] = v
+        if k.endswith(".weight") and v.ndim >= 3:
+            last_conv = k[: -len(".weight")]
+    return out
+
+
+def load_reference_checkpoint(path: str) -> dict[str, np.ndarray]:
+    """A `.pth` written by the reference's training code -> folded tensors.  Accepts a bare state dict or the
+    {"state_dict": ...} wrapper of BDRC/utils.py:1176-1179, with an optional "model." / "module." key prefix."""
+    import torch
+
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    sd = ck["state_dict"] if isinstance(ck, dict) and "state_dict" in ck else ck
+    for pre in ("model.", "module."):
+        if sd and all(k.startswith(pre) for k in sd):
+            sd = {k[len(pre):]: v for k, v in sd.items()}
+    return fold_batchnorm_state_dict(sd)

@@ -306,3 +306,71 @@ def test_model_config_readers_match_reference_layout(tmp_path):
     assert (lc.onnx_file, lc.patch_size, lc.classes) == (f"{d}/lines.onnx", 512, ["line"])
     lay = utils.read_layout_model_config(str(d / "line.json"))
     assert lay.architecture == f"{d}/deeplabv3" and lay.patch_size == 512
+
+
+def test_fold_batchnorm_state_dict_equals_eval_mode_modules():
+    """weights.fold_batchnorm_state_dict: conv+BN (plain, separable, with and without conv bias, downsample
+    naming) folded into conv weights/bias named like the exported ONNX initializers."""
+    import torch
+    from torch import nn
+
+    from ocr_inference_b200.weights import fold_batchnorm_state_dict
+
+    torch.manual_seed(0)
+
+    class Sep(nn.Sequential):
+        def __init__(self, cin, cout):
+            super().__init__(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), nn.Conv2d(cin, cout, 1, bias=False))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, 8, 3, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(8)
+            self.block = nn.Sequential(Sep(8, 16), nn.BatchNorm2d(16), nn.ReLU())
+            self.downsample = nn.Sequential(nn.Conv2d(16, 16, 1, bias=True), nn.BatchNorm2d(16))
+            self.head = nn.Conv2d(16, 2, 1)
+
+        def forward(self, x):
+            return self.head(self.downsample(self.block(torch.relu(self.bn1(self.conv1(x))))))
+
+    net = Net()
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_()
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.normal_(1.0, 0.3)
+            m.bias.data.normal_()
+    net.eval()
+    x = torch.randn(2, 3, 12, 12)
+    want = net(x)
+    w = {k: torch.from_numpy(v) for k, v in fold_batchnorm_state_dict(net.state_dict()).items()}
+    assert set(w) == {"conv1.weight", "conv1.bias", "block.0.0.weight", "block.0.1.weight", "block.0.1.bias",
+                      "downsample.0.weight", "downsample.0.bias", "head.weight", "head.bias"}
+    F = torch.nn.functional
+    y = torch.relu(F.conv2d(x, w["conv1.weight"], w["conv1.bias"], padding=1))
+    y = F.conv2d(y, w["block.0.0.weight"], None, padding=1, groups=8)
+    y = torch.relu(F.conv2d(y, w["block.0.1.weight"], w["block.0.1.bias"]))
+    y = F.conv2d(y, w["downsample.0.weight"], w["downsample.0.bias"])
+    y = F.conv2d(y, w["head.weight"], w["head.bias"])
+    assert torch.allclose(y, want, atol=1e-5)
+
+
+def test_modern_layout_weight_source_prefers_a_container_over_the_reference_pth(tmp_path):
+    """A model directory laid out like the reference's (checkpoint = torch .pth, onnx-model next to a .bdrcw):
+    the container wins; with only the .pth present the checkpoint is named (and folded at load)."""
+    from ocr_inference_b200.data import LayoutDetectionConfig
+    from ocr_inference_b200.inference import ModernBookFormatLayoutDetection as M
+    from ocr_inference_b200.weights import write_blob
+
+    pth, blob = tmp_path / "model.pth", tmp_path / "model.bdrcw"
+    pth.write_bytes(b"PK\x03\x04 not a container")
+    blob.write_bytes(write_blob({"a": np.zeros((1,), np.float32)}))
+    classes = ["background", "line"]
+    assert M._weights_source(LayoutDetectionConfig(str(pth), str(blob), "x", 512, classes)) == str(blob)
+    assert M._weights_source(LayoutDetectionConfig(str(pth), str(tmp_path / "missing.onnx"), "x", 512, classes)) == str(pth)
+    assert M._weights_source(LayoutDetectionConfig(str(blob), "", "x", 512, classes)) == str(blob)
+    w = {"k": np.zeros(1, np.float32)}
+    assert M._weights_source(LayoutDetectionConfig(w, "", "x", 512, classes)) is w
+    with pytest.raises(FileNotFoundError):
+        M._weights_source(LayoutDetectionConfig(str(tmp_path / "no.pth"), str(tmp_path / "no.onnx"), "x", 512, classes))

@@ -74,3 +74,37 @@ def test_torch_path_collate_matches_oracle(ref):
         assert np.array_equal(all_tiles.numpy(), x)
         assert (metas[0]["pad_x"], metas[0]["pad_y"], metas[0]["x_steps"], metas[0]["y_steps"]) == \
                (meta["pad_x"], meta["pad_y"], meta["x_steps"], meta["y_steps"])
+
+
+def test_check_line_tps_matches_reference_on_narrow_and_wide_lines(ref):
+    """image_dewarping.check_line_tps works on the line's ROI; the reference slices a page-sized canvas.  Lines
+    narrower than 4 slice widths put slices 2 and 5 partly outside the bounding box (negative ROI starts): the
+    control points must still be the reference's (BDRC/image_dewarping.py:118-193)."""
+    import cv2
+
+    from ocr_inference_b200 import image_dewarping as idw
+
+    ref_idw = __import__("BDRC.image_dewarping", fromlist=["check_line_tps"])
+    rng = np.random.default_rng(5)
+    checked, narrow = 0, 0
+    for w in (30, 60, 100, 150, 159, 160, 400, 1200):
+        for x0 in (3, 50, 700):
+            H, W = 400, 2000
+            canvas = np.zeros((H, W), np.uint8)
+            # a steep slanted band (plus a ripple): the slices' centres spread by more than a slice height
+            xs = np.arange(x0, x0 + w)
+            yc = 120 + (170.0 * (xs - x0) / w + 6 * np.sin(xs / 9.0)).astype(int)
+            cv2.polylines(canvas, [np.stack([xs, yc], axis=1).astype(np.int32)], False, 255, int(rng.integers(9, 15)))
+            cnts, _ = cv2.findContours(canvas, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+            cnt = max(cnts, key=cv2.contourArea)
+            image = np.zeros((H, W, 3), np.uint8)
+            want = ref_idw.check_line_tps(image, cnt)
+            got = idw.check_line_tps(image, cnt)
+            assert got[0] == want[0], (w, x0)
+            if want[0]:
+                assert np.array_equal(np.asarray(got[1]), np.asarray(want[1])), (w, x0, got[1], want[1])
+                assert np.array_equal(np.asarray(got[2]), np.asarray(want[2])), (w, x0)
+                assert got[3] == want[3]
+                checked += 1
+                narrow += int(w < 160)
+    assert checked >= 8 and narrow >= 2, (checked, narrow)
