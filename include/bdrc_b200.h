@@ -91,6 +91,12 @@ void bdrc_free_model(bdrc_model* m);
  * identical, so one is stored).  nty = ceil(H/patch), ntx = ceil(W/patch). */
 int bdrc_seg_preprocess(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int patch,
                         uint8_t* tiles, void* stream);
+/* a-1 for several pages in ONE launch (Detection._preprocess_image per page, BDRC/inference.py:132-139, as
+ * OCRPipeline runs it page after page).  pages / H / W are HOST arrays of n_pages device pointers and (already
+ * clamp-resized) sizes; tiles receives the tiles of all pages back to back, page after page. */
+int bdrc_seg_preprocess_batch(bdrc_ctx* ctx, const uint8_t* const* pages, const int* H, const int* W, int n_pages,
+                              int patch, uint8_t* tiles, void* stream);
+
 /* torch-path collate  utils.multi_image_collate_fn :1142-1172 (no binarise): resize_clamp
  * (F.interpolate bilinear, align_corners=False, to Hc x Wc; identity when equal) -> pad with 255
  * to a multiple of `patch` -> row-major tiles fp32 [nty*ntx][patch][patch][3] with values in
@@ -125,6 +131,12 @@ int bdrc_seg_postprocess(bdrc_ctx* ctx, const float* logits, int nty, int ntx, i
 int bdrc_seg_postprocess_lowres(bdrc_ctx* ctx, const float* logits_lowres, int nty, int ntx,
                                 int C, int patch, int Hc, int Wc, int mode, float thr,
                                 uint8_t* mask, void* stream);
+/* a-3 for several pages in ONE launch (LineDetection.predict per page, BDRC/inference.py:170-183): host arrays of
+ * per-page low-res logits pointers, tile counts, sizes (no page resize: Hc x Wc is the mask size) and mask pointers. */
+int bdrc_seg_postprocess_lowres_batch(bdrc_ctx* ctx, const float* const* logits_lowres, const int* nty,
+                                      const int* ntx, const int* Hc, const int* Wc, int n_pages, int C, int patch,
+                                      int mode, float thr, uint8_t* const* masks, void* stream);
+
 /* torch-path post  inference.py:947-956: softmax -> stitch -> crop -> float bilinear
  * (align_corners=False) to H0 x W0 -> > thr -> u8*255, planar [C][H0][W0]. */
 int bdrc_seg_postprocess_torch(bdrc_ctx* ctx, const float* logits, int nty, int ntx, int C,

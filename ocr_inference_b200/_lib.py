@@ -35,6 +35,7 @@ _SIGS = {
     "bdrc_load_weights": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, C.POINTER(c_void_p)]),
     "bdrc_free_model": (None, [c_void_p]),
     "bdrc_seg_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "bdrc_seg_preprocess_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "bdrc_seg_tile_rgb": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
     "bdrc_seg_workspace_bytes": (c_size_t, [c_void_p, c_int]),
@@ -46,6 +47,8 @@ _SIGS = {
                                      c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "bdrc_seg_postprocess_lowres": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_int, c_float, c_void_p, c_void_p]),
+    "bdrc_seg_postprocess_lowres_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                  c_int, c_int, c_float, c_void_p, c_void_p]),
     "bdrc_seg_postprocess_torch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "bdrc_resize_bilinear_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,

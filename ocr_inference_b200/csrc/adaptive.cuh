@@ -34,15 +34,15 @@ constexpr size_t SMEM_BYTES = (size_t)(RB * GSTRIDE + RING * SW) * sizeof(float)
 __constant__ float c_gauss[KS];
 
 // Source policies ------------------------------------------------------------------------------
+// A policy hands out a per-CTA View of image `img` (one tile / one line): everything that depends on the image
+// index -- the page of a multi-page batch, the tile's origin in it -- is resolved once per CTA, not per pixel.
+//
 // RGB page viewed as row-major 512x512 tiles, padded with 255 beyond (Hc, Wc) (utils.py:775-776)
-struct SrcPageTiles {
+struct PageTileView {
   const uint8_t* page;
-  int Hc, Wc, ntx, patch;
-  int ih() const { return patch; }
-  int iw() const { return patch; }
-  __device__ __forceinline__ float gray(int img, int y, int x) const {
-    const int ty = img / ntx, tx = img - ty * ntx;
-    const int py = ty * patch + y, px = tx * patch + x;
+  int Hc, Wc, py0, px0;
+  __device__ __forceinline__ float gray(int y, int x) const {
+    const int py = py0 + y, px = px0 + x;
     if (py >= Hc || px >= Wc) return 255.f;
     const uint8_t* p = page + ((size_t)py * Wc + px) * 3;
     const int g = (p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + 16384) >> 15;
@@ -53,9 +53,8 @@ struct SrcPageTiles {
   // pixels lie in the 255 padding) or 0 where the caller must go pixel by pixel (quad straddling the page
   // edge, or a row that is not 4-byte aligned).  conv4 turns the raw words into gray values.
   static constexpr int WORDS = 3;
-  __device__ __forceinline__ int load4(int img, int y, int x, uint32_t* raw) const {
-    const int ty = img / ntx, tx = img - ty * ntx;
-    const int py = ty * patch + y, px = tx * patch + x;
+  __device__ __forceinline__ int load4(int y, int x, uint32_t* raw) const {
+    const int py = py0 + y, px = px0 + x;
     if (py >= Hc || px >= Wc) return 2;
     const uint8_t* p = page + ((size_t)py * Wc + px) * 3;
     if (px + 3 >= Wc || (reinterpret_cast<uintptr_t>(p) & 3)) return 0;
@@ -79,18 +78,45 @@ struct SrcPageTiles {
   }
 };
 
-// batch of single-channel u8 images [n][H][W]
-struct SrcGrayBatch {
-  const uint8_t* img;
-  int H, W;
-  int ih() const { return H; }
-  int iw() const { return W; }
-  __device__ __forceinline__ float gray(int i, int y, int x) const {
-    return (float)img[((size_t)i * H + y) * W + x];
+struct SrcPageTiles {
+  const uint8_t* page;
+  int Hc, Wc, ntx, patch;
+  typedef PageTileView View;
+  int ih() const { return patch; }
+  int iw() const { return patch; }
+  __device__ __forceinline__ View view(int img) const {
+    const int ty = img / ntx, tx = img - ty * ntx;
+    return View{page, Hc, Wc, ty * patch, tx * patch};
   }
+};
+
+// Several pages in ONE launch (bdrc_seg_preprocess_batch): tile `img` of the batch belongs to the page whose
+// tile range [tile0[k], tile0[k + 1]) holds it.  The table travels in the kernel parameters.
+constexpr int MAX_BATCH_PAGES = 32;
+struct SrcPageTable {
+  const uint8_t* page[MAX_BATCH_PAGES];
+  int Hc[MAX_BATCH_PAGES], Wc[MAX_BATCH_PAGES], ntx[MAX_BATCH_PAGES], tile0[MAX_BATCH_PAGES + 1];
+  int n_pages, patch;
+  typedef PageTileView View;
+  int ih() const { return patch; }
+  int iw() const { return patch; }
+  __device__ __forceinline__ View view(int img) const {
+    int k = 0;
+    while (k + 1 < n_pages && img >= tile0[k + 1]) ++k;
+    const int t = img - tile0[k];
+    const int ty = t / ntx[k], tx = t - ty * ntx[k];
+    return View{page[k], Hc[k], Wc[k], ty * patch, tx * patch};
+  }
+};
+
+// batch of single-channel u8 images [n][H][W]
+struct GrayView {
+  const uint8_t* img;
+  int W;
+  __device__ __forceinline__ float gray(int y, int x) const { return (float)img[(size_t)y * W + x]; }
   static constexpr int WORDS = 1;
-  __device__ __forceinline__ int load4(int i, int y, int x, uint32_t* raw) const {
-    const uint8_t* p = img + ((size_t)i * H + y) * W + x;
+  __device__ __forceinline__ int load4(int y, int x, uint32_t* raw) const {
+    const uint8_t* p = img + (size_t)y * W + x;
     if (reinterpret_cast<uintptr_t>(p) & 3) return 0;
     raw[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
     return 1;
@@ -100,6 +126,15 @@ struct SrcGrayBatch {
     v[0] = (float)(w & 255u); v[1] = (float)((w >> 8) & 255u); v[2] = (float)((w >> 16) & 255u); v[3] = (float)(w >> 24);
     packed = w;
   }
+};
+
+struct SrcGrayBatch {
+  const uint8_t* img;
+  int H, W;
+  typedef GrayView View;
+  int ih() const { return H; }
+  int iw() const { return W; }
+  __device__ __forceinline__ View view(int i) const { return View{img + (size_t)i * H * W, W}; }
 };
 
 // Sink policies --------------------------------------------------------------------------------
@@ -162,6 +197,7 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
   const int sx = blockIdx.x % strips_x;
   const int img = blockIdx.x / strips_x;
   const int x0 = sx * SW;
+  const typename Src::View sv = src.view(img);
   const int n_blocks = (IH + RB - 1) / RB;
 
   // Staging works on quads: tile columns x0 - 28 + 4q .. + 3 (a 4-aligned superset of the 82 staged columns),
@@ -171,7 +207,7 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
   constexpr int NQ = (GW + 3 + 3) / 4;                       // 22
   constexpr int ITEMS = RB * NQ;                             // 704
   constexpr int NIT = (ITEMS + THREADS - 1) / THREADS;       // 3
-  uint32_t raw[NIT][Src::WORDS];
+  uint32_t raw[NIT][Src::View::WORDS];
   uint32_t mode = 0;                                         // 2 bits per item: 0 slow, 1 raw words, 2 constant 255
   auto prefetch = [&](int blk) {
     mode = 0;
@@ -182,7 +218,7 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         const int r = i / NQ, q = i - r * NQ;
         const int y = min(RB * blk + r, IH - 1);
         const int xq = x0 - 28 + 4 * q;
-        if (xq >= 0 && xq + 3 < IW) mode |= (uint32_t)src.load4(img, y, xq, raw[it]) << (2 * it);
+        if (xq >= 0 && xq + 3 < IW) mode |= (uint32_t)sv.load4(y, xq, raw[it]) << (2 * it);
       }
     }
   };
@@ -197,14 +233,14 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         float v[4];
         uint32_t packed;
         if (m == 1u) {
-          src.conv4(raw[it], v, packed);
+          sv.conv4(raw[it], v, packed);
         } else if (m == 2u) {
           v[0] = v[1] = v[2] = v[3] = 255.f;
           packed = 0xFFFFFFFFu;
         } else {
           const int y = min(RB * blk + r, IH - 1);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = src.gray(img, y, min(max(xq + j, 0), IW - 1));
+          for (int j = 0; j < 4; ++j) v[j] = sv.gray(y, min(max(xq + j, 0), IW - 1));
           packed = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
         }
         float* gr = g + r * GSTRIDE + GOFF + 4 * q - 3;      // 4q + 1 .. 4q + 4 of a 92-float row: always inside

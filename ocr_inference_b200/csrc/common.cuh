@@ -63,6 +63,16 @@ int bdrc_fail(bdrc_ctx* ctx, int code, const char* fmt, ...);
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// One bilinear sample in the operation order of torch's upsample_bilinear2d (horizontal lerps, then the
+// vertical one), with the FMA contraction spelled out so that every kernel that upsamples logits -- the fused
+// mask kernels of a-3 and the full-resolution upsample -- produces the same bits for the same inputs.
+__device__ __forceinline__ float bdrc_bilerp(float a00, float a01, float a10, float a11, float lx0, float lx1,
+                                             float ly0, float ly1) {
+  const float top = __fmaf_rn(lx1, a01, __fmul_rn(lx0, a00));
+  const float bot = __fmaf_rn(lx1, a11, __fmul_rn(lx0, a10));
+  return __fmaf_rn(ly1, bot, __fmul_rn(ly0, top));
+}
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- profiling helpers (conv_tc.cu / nets) ---------------------------------------

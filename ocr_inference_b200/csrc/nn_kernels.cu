@@ -508,8 +508,8 @@ __global__ void upsample_logits_kernel(const float* __restrict__ in, int N, int 
   const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
   const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
   const float* b = in + (size_t)n * h * w * C + c;
-  out[idx] = ly0 * (lx0 * b[((size_t)y0 * w + x0) * C] + lx1 * b[((size_t)y0 * w + x1) * C]) +
-             ly1 * (lx0 * b[((size_t)y1 * w + x0) * C] + lx1 * b[((size_t)y1 * w + x1) * C]);
+  out[idx] = bdrc_bilerp(b[((size_t)y0 * w + x0) * C], b[((size_t)y0 * w + x1) * C], b[((size_t)y1 * w + x0) * C],
+                         b[((size_t)y1 * w + x1) * C], lx0, lx1, ly0, ly1);
 }
 
 // one CTA per image: mean over HW -> 1x1 conv + ReLU -> tail of the projection conv

@@ -208,6 +208,62 @@ class Engine:
         meta = dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc, pad_y=nty * patch - Hc)
         return tiles, meta
 
+    def seg_preprocess_batch(self, pages: list, patch: int = PATCH):
+        """a-1 for several device-resident pages in ONE launch -> (tiles u8 {0,1} [sum N,P,P], metas).  Pages that
+        need the clamp resize are resized first (one small kernel each, rare)."""
+        metas, srcs = [], []
+        for page in pages:
+            H0, W0 = int(page.shape[0]), int(page.shape[1])
+            Hc, Wc = clamp_size(H0, W0, patch)
+            page = page.contiguous()
+            if (Hc, Wc) != (H0, W0):
+                page = self.resize_u8(page, Hc, Wc)
+            nty, ntx = math.ceil(Hc / patch), math.ceil(Wc / patch)
+            srcs.append(page)
+            metas.append(dict(H0=H0, W0=W0, Hc=Hc, Wc=Wc, nty=nty, ntx=ntx, pad_x=ntx * patch - Wc,
+                              pad_y=nty * patch - Hc))
+        n = len(srcs)
+        tiles = torch.empty((sum(m["nty"] * m["ntx"] for m in metas), patch, patch), dtype=torch.uint8, device=self.device)
+        if n == 0:
+            return tiles, metas
+        ptrs = np.array([t.data_ptr() for t in srcs], dtype=np.uint64)
+        hs = np.array([m["Hc"] for m in metas], dtype=np.int32)
+        ws = np.array([m["Wc"] for m in metas], dtype=np.int32)
+        self._check(self.lib.bdrc_seg_preprocess_batch(self.ctx.h, ptrs.ctypes.data, hs.ctypes.data, ws.ctypes.data, n,
+                                                       patch, tiles.data_ptr(), self.stream), "seg_preprocess_batch")
+        return tiles, metas
+
+    def seg_postprocess_lowres_batch(self, logits: torch.Tensor, metas: list, mode: int, thr: float) -> list:
+        """a-3 for the pages of one forward call in ONE launch: low-res logits [sum N,128,128,C] -> one mask per page
+        (slices of one allocation)."""
+        Cn = int(logits.shape[3])
+        logits = logits.contiguous()
+        for m in metas:
+            if (m["Hc"], m["Wc"]) != (m["H0"], m["W0"]):
+                raise _lib.BdrcError("low-res post-processing does not resize; use the full-res path")
+        sizes = [m["H0"] * m["W0"] * Cn for m in metas]
+        flat = torch.empty((sum((s + 15) // 16 * 16 for s in sizes),), dtype=torch.uint8, device=self.device)
+        masks, lptr, mptr, o, t0 = [], [], [], 0, 0
+        per_tile = 128 * 128 * Cn * 4
+        for m, sz in zip(metas, sizes):
+            shape = (m["H0"], m["W0"]) if Cn == 1 else (m["H0"], m["W0"], Cn)
+            masks.append(flat[o:o + sz].view(shape))
+            mptr.append(flat.data_ptr() + o)
+            lptr.append(logits.data_ptr() + t0 * per_tile)
+            o += (sz + 15) // 16 * 16
+            t0 += m["nty"] * m["ntx"]
+        n = len(metas)
+        if n == 0:
+            return masks
+        arr = lambda v, dt: np.array(v, dtype=dt)  # noqa: E731
+        lp, mp = arr(lptr, np.uint64), arr(mptr, np.uint64)
+        nty, ntx = arr([m["nty"] for m in metas], np.int32), arr([m["ntx"] for m in metas], np.int32)
+        hc, wc = arr([m["Hc"] for m in metas], np.int32), arr([m["Wc"] for m in metas], np.int32)
+        self._check(self.lib.bdrc_seg_postprocess_lowres_batch(
+            self.ctx.h, lp.ctypes.data, nty.ctypes.data, ntx.ctypes.data, hc.ctypes.data, wc.ctypes.data, n, Cn, PATCH,
+            mode, thr, mp.ctypes.data, self.stream), "seg_postprocess_lowres_batch")
+        return masks
+
     def seg_tile_rgb(self, page: torch.Tensor, patch: int = PATCH, out: torch.Tensor | None = None):
         """torch-path collate (utils.multi_image_collate_fn): fp32 RGB tiles [N,P,P,3] in [0,255].
         `out` (optional) is a preallocated [N,P,P,3] fp32 slice of a larger tile batch (several images per

@@ -112,24 +112,15 @@ class Detection:
         """Several device-resident pages through ONE forward call (tiles of all pages share the
         batch dimension; per-tile reductions are per batch element, so this is exact)."""
         eng = self.engine
-        from .engine import clamp_size
-        P = self._patch_size
-        geo = []
-        for p in pages_dev:
-            H0, W0 = int(p.shape[0]), int(p.shape[1])
-            Hc, Wc = clamp_size(H0, W0, P)
-            geo.append((-(-Hc // P)) * (-(-Wc // P)))
-        tiles = torch.empty((sum(geo), P, P), dtype=torch.uint8, device=eng.device)
-        metas, o = [], 0
-        for p, n in zip(pages_dev, geo):
-            _, meta = eng.seg_preprocess(p, P, out=tiles[o:o + n])
-            metas.append(meta)
-            o += n
+        tiles, metas = eng.seg_preprocess_batch(list(pages_dev), self._patch_size)         # a-1, one launch
         need_full = any((m["Hc"], m["Wc"]) != (m["H0"], m["W0"]) for m in metas)
-        logits = eng.seg_forward(self._inference, tiles, lowres=not need_full)
+        logits = eng.seg_forward(self._inference, tiles, lowres=not need_full)             # a-2
+        if not need_full:
+            return eng.seg_postprocess_lowres_batch(logits, metas, self._mode, class_threshold)   # a-3, one launch
         outs, o = [], 0
-        for n, meta in zip(geo, metas):
-            outs.append(eng.seg_postprocess(logits[o:o + n], meta, self._mode, class_threshold, lowres=not need_full))
+        for meta in metas:
+            n = meta["nty"] * meta["ntx"]
+            outs.append(eng.seg_postprocess(logits[o:o + n], meta, self._mode, class_threshold))
             o += n
         return outs
 

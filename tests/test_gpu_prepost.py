@@ -125,3 +125,60 @@ def test_ctc_greedy_bit_exact(engine, layout, L, V, T):
         ref = ho.ctc_greedy_ids(logits[l], V + 1000)   # V+1000: never transpose, input is [T,V]
         assert lens[l] == len(ref)
         assert ids[l, : lens[l]].tolist() == ref
+
+
+def test_batched_seg_preprocess_bit_exact(engine):
+    """a-1 over a page table (one launch for several pages, ragged sizes incl. clamp / upsize / pad) equals the
+    cv2 oracle page by page."""
+    shapes = [(2048, 3072), (600, 700), (472, 2550), (1024, 1536), (2100, 1500), (512, 512)]
+    pages = [synth.page(40 + i, *s)[0] for i, s in enumerate(shapes)]
+    tiles, metas = engine.seg_preprocess_batch([_dev(p) for p in pages])
+    got = tiles.cpu().numpy()
+    o = 0
+    for page, meta in zip(pages, metas):
+        ref, rmeta = ho.seg_preprocess(page, closed_form=False)
+        for k in ("Hc", "Wc", "pad_x", "pad_y"):
+            assert meta[k] == rmeta[k]
+        n = ref.shape[0]
+        assert int((got[o:o + n] != ref).sum()) == 0
+        o += n
+    assert o == got.shape[0]
+
+
+def test_batched_line_postprocess_equals_oracle_upsample_decisions(engine):
+    """a-3 over a page table with the x4 upsample fused: the mask equals threshold(oracle upsample of the same
+    low-res logits) wherever the upsampled logit is not within fp32 rounding of the threshold, and equals the
+    per-page kernel bit for bit.  Covers cells that are uniformly above / below the threshold (settled from the
+    corners alone), cells that straddle it, +-inf and NaN corners, and ragged page sizes."""
+    rng = np.random.default_rng(12)
+    shapes = [(2048, 3072), (600, 700), (1024, 1536), (512, 2000)]
+    lows, metas = [], []
+    for (H, W) in shapes:
+        nty, ntx = -(-H // 512), -(-W // 512)
+        base = rng.normal(0.0, 6.0, (nty * ntx, 1, 16, 16)).astype(np.float32)
+        low = torch.nn.functional.interpolate(torch.from_numpy(base), size=(128, 128), mode="bilinear").numpy()
+        low = np.ascontiguousarray(low.transpose(0, 2, 3, 1))            # NHWC [N,128,128,1]
+        low[0, 5, 7, 0] = np.inf
+        low[0, 9, 9, 0] = -np.inf
+        low[0, 20, 20, 0] = np.nan
+        low[0, 40:44, 40:44, 0] = np.float32(2.1972246)                  # cells sitting exactly on the threshold
+        lows.append(low)
+        metas.append(dict(H0=H, W0=W, Hc=H, Wc=W, nty=nty, ntx=ntx, pad_x=ntx * 512 - W, pad_y=nty * 512 - H))
+    logits = _dev(np.concatenate(lows))
+    masks = engine.seg_postprocess_lowres_batch(logits, metas, 0, 0.9)
+    thr = float(ho.sigmoid_logit_threshold(0.9))
+    o = 0
+    for low, meta, m in zip(lows, metas, masks):
+        n = low.shape[0]
+        per_page = engine.seg_postprocess(logits[o:o + n], meta, 0, 0.9, lowres=True)
+        assert torch.equal(m, per_page)
+        o += n
+        got = m.cpu().numpy()
+        assert got.shape == (meta["H0"], meta["W0"]) and set(np.unique(got)) <= {0, 255}
+        with np.errstate(invalid="ignore"):
+            up = torch.nn.functional.interpolate(torch.from_numpy(low.transpose(0, 3, 1, 2).copy()), scale_factor=4,
+                                                 mode="bilinear", align_corners=True).numpy()[:, 0]
+        full = np.vstack([np.hstack(list(r)) for r in np.split(up, meta["nty"])])[:meta["H0"], :meta["W0"]]
+        decided = np.isfinite(full) & (np.abs(full - thr) > 1e-4 * np.maximum(1.0, np.abs(full)))
+        assert np.array_equal(got[decided] == 255, full[decided] >= thr)
+        assert 0.1 < (got == 255).mean() < 0.9
