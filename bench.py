@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 page->text hot path.
+"""bench.py -- benchmark of the B200 page->text hot path.
 
-Workload (BASELINE.json configs[1], "C2"): a batch of 16 synthetic 2048x3072 pages per GPU per
+Headline workload (BASELINE.json configs[1], "C2"): a batch of 16 synthetic 2048x3072 pages per GPU per
 step -> 384 tiles of 512x512 -> binarise/tile (a-1) -> DeepLabV3+/R34 forward (a-2) -> mask
 threshold (a-3).  Metric: pages/s (whole job, all ranks).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-`value`  : inputs (u8 pages) resident in HBM, masks left in HBM, timed with CUDA events.
-`e2e`    : LineDetection.predict_batch(host numpy pages) -> host numpy masks (pinned H2D / D2H inside
-           the timed region).
+`value`   : inputs (u8 pages) resident in HBM, masks left in HBM, timed with CUDA events.
+`e2e`     : LineDetection.predict_batch(pageable numpy pages) -> fresh numpy masks, the reference's calling
+            convention (H2D of the pages and D2H of the masks inside the timed region).
+`e2e_io_binding`: the same call with caller-pinned inputs and masks left in the object's pinned staging buffers.
 `roofline`: tcgen05 implicit-GEMM conv kernel, algorithmic FLOPs / CUDA-event time per launch,
-           recorded live during the timed steps, vs MEASURED_PEAKS.json.
+            recorded live during the timed steps, vs MEASURED_PEAKS.json.
+`roofline_stages`: the HBM-class stages (a-1, a-3, a-5, a-7, a-9) at step granularity: algorithmic bytes
+            / CUDA-event time, vs the measured HBM copy bandwidth.
 `cpu_baseline`: the oracle (reference host code restated + torch-CPU fp32 network) on the host
-           cores, rank 0, on a bounded sample.
+            cores, rank 0, on a bounded sample.
+`c1` / `c3` (N = 1) and `c5` (every N): the other BASELINE.json configurations as first-class blocks -- line
+            recognition (lines/s), page -> text (pages/s, lines/s, identity with the CPU oracle on 8 pages) and
+            the page-sharded page -> text run (sharding.run_sharded: every rank drives its share of the pages
+            through OCRPipeline.run_ocr_batch, rank 0 gathers the per-page results on the host).
 """
 from __future__ import annotations
 
@@ -59,7 +66,11 @@ try:
             pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
         except Exception:
             pw = -1.0
-        print("s", time.time(), mhz, mask, pw, flush=True)
+        try:
+            ut = float(nv.nvmlDeviceGetUtilizationRates(h).gpu)
+        except Exception:
+            ut = -1.0
+        print("s", time.time(), mhz, mask, pw, ut, flush=True)
         time.sleep(0.025)
 except Exception as e:
     print("err", repr(e), flush=True)
@@ -81,43 +92,56 @@ class ClockSampler:
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES, NVML indexes physical GPUs
         phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-        self.windows: list[tuple[float, float]] = []
+        self.windows: list[tuple[float, float, str]] = []
         try:
             self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(phys)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception as e:  # noqa: BLE001
             self.proc, self.err = None, repr(e)
 
-    def mark(self, t0: float, t1: float):
-        self.windows.append((t0, t1))
+    def mark(self, t0: float, t1: float, tag: str = "headline"):
+        self.windows.append((t0, t1, tag))
 
-    def summary(self):
+    def _finish(self):
+        if getattr(self, "_rows", None) is not None:
+            return
+        self._rows, self._max, self._err = [], None, None
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler unavailable: {self.err}"]}
+            return
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
             out, _ = self.proc.communicate()
-        max_mhz, rows, err = None, [], None
         for ln in out.splitlines():
             f = ln.split()
             if f and f[0] == "max":
-                max_mhz = float(f[1])
+                self._max = float(f[1])
             elif f and f[0] == "s" and len(f) >= 5:
-                rows.append((float(f[1]), float(f[2]), int(f[3]), float(f[4])))
+                self._rows.append((float(f[1]), float(f[2]), int(f[3]), float(f[4]), float(f[5]) if len(f) > 5 else -1.0))
             elif f and f[0] == "err":
-                err = ln
-        inside = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
+                self._err = ln
+
+    def gpu_util(self, tag: str):
+        """Median NVML GPU utilisation (% of time a kernel was running) inside the windows tagged `tag`."""
+        self._finish()
+        u = sorted(r[4] for r in self._rows if r[4] >= 0 and any(a <= r[0] <= b and t == tag for a, b, t in self.windows))
+        return u[len(u) // 2] if u else None
+
+    def summary(self, tag: str = "headline"):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler unavailable: {self.err}"]}
+        self._finish()
+        inside = [r for r in self._rows if any(a <= r[0] <= b and t == tag for a, b, t in self.windows)]
         if not inside:
-            return {"sm_mhz": None, "sm_max_mhz": max_mhz, "reasons": [f"no samples inside the timed region ({err})"],
-                    "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": self._max,
+                    "reasons": [f"no samples inside the timed region ({self._err})"], "samples": 0}
         sm = sorted(r[1] for r in inside)
         seen = 0
         for r in inside:
             seen |= r[2]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max_mhz,
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self._max,
                 "power_w_max": max(r[3] for r in inside),
                 "reasons": [n for bit, n in self.REASONS.items() if seen & bit], "samples": len(inside)}
 
@@ -169,10 +193,31 @@ def cpu_reference_pages_per_sec(n_pages: int, steps: int = 1, warmup: int = 0):
     return n_pages * steps / dt, dt / steps, cores
 
 
-def cpu_reference_page_to_text(page, gpu_result):
-    """The oracle's whole page -> text pipeline (tile/binarise, torch-CPU fp32 DeepLabV3+ with the fitted head,
-    mask, the reference's cv2/numpy line extraction, line prep, torch-CPU Easter2, greedy CTC) on ONE page, on all
-    host cores, beside the GPU pipeline's result for the same page."""
+PT_KW = dict(k_factor=2.0, bbox_tolerance=2.5)        # the reference's Demo-OCR.ipynb parameters
+
+
+def text_pages(n: int, seed0: int = 3003, n_base: int = 8):
+    """n synthetic text pages + their transcriptions: `n_base` generated pages, the rest are
+    augmentations (vertical shift by a few rows, brightness) -- the text of a page stays what it was."""
+    from ocr_inference_b200 import synthetic
+
+    base = [synthetic.text_page(seed0 + i) for i in range(min(n, n_base))]
+    pages, truth = [], []
+    for i in range(n):
+        img, _, texts = base[i % len(base)]
+        k = i // len(base)
+        if k:
+            img = np.roll(img, ((k * 7) % 41) - 20, axis=0)
+            img = np.clip(img.astype(np.int16) + ((k * 3) % 9 - 4), 0, 255).astype(np.uint8)
+        pages.append(np.ascontiguousarray(img))
+        truth.append(["".join(synthetic.CHARSET_76[j] for j in t).strip().replace("\u00a7", " ") for t in texts])
+    return pages, truth
+
+
+def cpu_reference_page_to_text(pages, gpu_results):
+    """The oracle's whole page -> text pipeline (tile/binarise, torch-CPU fp32 DeepLabV3+ with the trained decoder,
+    mask, the reference's cv2/numpy line extraction, line prep, torch-CPU Easter2, greedy CTC) on `pages`, on all
+    host cores, beside the GPU pipeline's results for the same pages."""
     import cv2
     import torch
 
@@ -187,35 +232,49 @@ def cpu_reference_page_to_text(page, gpu_result):
     torch.set_num_threads(cores)
     cv2.setNumThreads(-1)
     ws, we = seg_weights_fitted(11), easter2_weights_fitted()
+    n_lines = same = same_box = gpu_lines = pages_same_count = 0
+    max_box = 0
+    dist = chars = 0
     t0 = time.perf_counter()
-    tiles, meta = ho.seg_preprocess(page, closed_form=False)
-    x = np.repeat(tiles[:, None].astype(np.float32), 3, axis=1)
-    logits = np.concatenate([nets.seg_forward(ws, x[i:i + 8]) for i in range(0, len(x), 8)])
-    mask = ho.line_postprocess(logits, meta, 0.9, closed_form=False)
-    r = og.page_to_lines(page, mask, 2.0, 2.5)
-    texts = [] if isinstance(r, str) else og.recognise(r[2], we, synthetic.CHARSET_76)[0]
+    per_page = []
+    for page in pages:
+        tiles, meta = ho.seg_preprocess(page, closed_form=False)
+        x = np.repeat(tiles[:, None].astype(np.float32), 3, axis=1)
+        logits = np.concatenate([nets.seg_forward(ws, x[i:i + 8]) for i in range(0, len(x), 8)])
+        mask = ho.line_postprocess(logits, meta, 0.9, closed_form=False)
+        r = og.page_to_lines(page, mask, PT_KW["k_factor"], PT_KW["bbox_tolerance"])
+        texts = [] if isinstance(r, str) else og.recognise(r[2], we, synthetic.CHARSET_76)[0]
+        per_page.append((r, texts))
     dt = time.perf_counter() - t0
-    out = {"value": 1.0 / dt, "unit": "pages/s", "lines_per_sec": len(texts) / dt, "cores": cores, "kind": "port",
-           "sample": "1 of the pages: oracle/ page -> text (cv2/numpy host code of the reference restated, torch-CPU fp32 "
-                     "networks), all host threads", "seconds_per_page": dt, "lines": len(texts)}
-    if gpu_result[0] == OpStatus.SUCCESS:
-        got = [l.text for l in gpu_result[1][2]]
+    for (r, texts), g in zip(per_page, gpu_results):
         want = [t.strip().replace("\u00a7", " ") for t in texts]
-        out["gpu_lines"] = len(got)
-        out["gpu_lines_identical_to_cpu_oracle"] = sum(a == b for a, b in zip(got, want)) if len(got) == len(want) else None
-        # whole-page identity is decided by the few mask pixels whose logit sits inside the bf16 tolerance of the
-        # threshold (a different contour polygon -> a crop shifted by a pixel -> another resize phase); report how far
-        # apart the two pipelines actually are: line boxes and character-level agreement
+        n_lines += len(want)
+        if g[0] != OpStatus.SUCCESS:
+            continue
+        got = [l.text for l in g[1][2]]
+        gpu_lines += len(got)
+        if len(got) != len(want):
+            continue
+        pages_same_count += 1
+        same += sum(a == b for a, b in zip(got, want))
+        dist += sum(_edit_distance(a, b) for a, b in zip(got, want))
+        chars += sum(max(len(a), len(b)) for a, b in zip(got, want))
         if not isinstance(r, str):
-            gb = [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h) for l in gpu_result[1][1]]
+            gb = [(l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h) for l in g[1][1]]
             ob = [tuple(l.bbox) for l in r[1]]
-            out["gpu_line_boxes_identical"] = sum(a == b for a, b in zip(gb, ob)) if len(gb) == len(ob) else None
-            out["gpu_line_boxes_max_abs_diff_px"] = (max(max(abs(p - q) for p, q in zip(a, b)) for a, b in zip(gb, ob))
-                                                     if len(gb) == len(ob) and gb else None)
-        if len(got) == len(want) and got:
-            dist = sum(_edit_distance(a, b) for a, b in zip(got, want))
-            out["gpu_vs_cpu_character_agreement"] = 1.0 - dist / max(1, sum(max(len(a), len(b)) for a, b in zip(got, want)))
-    return out
+            if len(gb) == len(ob):
+                same_box += sum(a == b for a, b in zip(gb, ob))
+                max_box = max([max_box] + [max(abs(p_ - q_) for p_, q_ in zip(a, b)) for a, b in zip(gb, ob)])
+    return {"value": len(pages) / dt, "unit": "pages/s", "lines_per_sec": n_lines / dt, "cores": cores, "kind": "port",
+            "sample": f"{len(pages)} of the pages: oracle/ page -> text (cv2/numpy host code of the reference restated, "
+                      "torch-CPU fp32 networks), all host threads", "seconds_per_page": dt / len(pages), "lines": n_lines,
+            "gpu_lines": gpu_lines, "pages_with_equal_line_count": pages_same_count,
+            "gpu_lines_identical_to_cpu_oracle": same,
+            "identical_line_fraction": same / max(1, n_lines),
+            "gpu_line_boxes_identical": same_box, "gpu_line_boxes_max_abs_diff_px": max_box,
+            "gpu_vs_cpu_character_agreement": (1.0 - dist / chars) if chars else None,
+            "note": "Easter2 internals are our restatement of arXiv 2205.14879 (parity unpinned against BDRC's ONNX "
+                    "files); greedy CTC on both sides"}
 
 
 def _edit_distance(a: str, b: str) -> int:
@@ -395,47 +454,299 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     return out
 
 
-def bench_c3(eng, steps: int, pages_per_step: int = 96, workers: int | None = None, with_cpu: bool = False):
-    """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (host numpy in, OCRLine text out)."""
-    from ocr_inference_b200 import synthetic
-    from ocr_inference_b200.data import LineDetectionConfig, OpStatus
+def _pipeline(eng):
+    from ocr_inference_b200.data import LineDetectionConfig
     from ocr_inference_b200.inference import OCRPipeline
     from ocr_inference_b200.synthetic_weights import seg_weights_fitted
     from ocr_inference_b200.weights import write_blob
 
-    pipe = OCRPipeline(_ocr_config(), LineDetectionConfig("", write_blob(seg_weights_fitted(11)), "deeplabv3plus-r34",
+    return OCRPipeline(_ocr_config(), LineDetectionConfig("", write_blob(seg_weights_fitted(11)), "deeplabv3plus-r34",
                                                           512, ["line"]), None, engine=eng)
-    base = [synthetic.text_page(3003 + i) for i in range(4)]
-    pages = [base[i % 4][0] for i in range(pages_per_step)]
-    n_truth = sum(len(base[i % 4][2]) for i in range(pages_per_step))
-    kw = dict(k_factor=2.0, bbox_tolerance=2.5)        # the reference's Demo-OCR.ipynb parameters
-    pipe.run_ocr_batch(pages, workers=workers, **kw)      # warm-up: pinned mask buffers, allocator pools
+
+
+def _score(results, truth):
+    """(pages ok, lines found, lines equal to the generator's transcription)."""
+    from ocr_inference_b200.data import OpStatus
+
+    ok = n_lines = right = 0
+    for r, want in zip(results, truth):
+        if r[0] != OpStatus.SUCCESS:
+            continue
+        ok += 1
+        got = [l.text for l in r[1][2]]
+        n_lines += len(got)
+        pool = list(want)
+        for g in got:
+            if g in pool:
+                pool.remove(g)
+                right += 1
+    return ok, n_lines, right
+
+
+def bench_c3(eng, steps: int, pages_per_step: int = 96, workers: int | None = None, with_cpu: bool = False):
+    """Full page -> text: OCRPipeline.run_ocr_batch on synthetic text pages (pageable numpy in, OCRLine text out)."""
+    import torch
+
+    pipe = _pipeline(eng)
+    pages, truth = text_pages(pages_per_step)
+    n_truth = sum(len(t) for t in truth)
+    pipe.run_ocr_batch(pages, workers=workers, **PT_KW)      # warm-up: pinned mask buffers, allocator pools, workers
+    l0 = eng.launch_count()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = pipe.run_ocr_batch(pages, workers=workers, **kw)
+        res = pipe.run_ocr_batch(pages, workers=workers, **PT_KW)
     dt = (time.perf_counter() - t0) / steps
-    ok = [r for r in res if r[0] == OpStatus.SUCCESS]
-    n_lines = sum(len(r[1][2]) for r in ok)
-    want = [{"".join(synthetic.CHARSET_76[i] for i in t).strip().replace("§", " ") for t in base[i % 4][2]}
-            for i in range(pages_per_step)]
-    n_right = sum(sum(l.text in want[i] for l in r[1][2]) for i, r in enumerate(res) if r[0] == OpStatus.SUCCESS)
-    cpu = None
-    if with_cpu:
-        cpu = cpu_reference_page_to_text(base[0][0], res[0])
+    launches = (eng.launch_count() - l0) // steps
+    ok, n_lines, n_right = _score(res, truth)
+    # the conv kernels' share of the page -> text wall time and their rate, from one more (profiled) pass
+    eng.profile(True)
+    tp = time.perf_counter()
+    pipe.run_ocr_batch(pages, workers=workers, **PT_KW)
+    torch.cuda.synchronize()
+    dtp = time.perf_counter() - tp
+    prof = eng.profile_results()
+    eng.profile(False)
+    tc = [(n, t, f) for (n, t, f) in prof if f > 0 and not n.startswith(("stem", "aspp.dw", "dec.dw", "aspp.pool"))]
+    tc_ms, tc_fl = sum(x[1] for x in tc), sum(x[2] for x in tc)
+    gpu_ms = sum(x[1] for x in prof)
+    peak_tf, _, peak_src = peaks()
+    cpu = cpu_reference_page_to_text(pages[:8], res[:8]) if with_cpu else None
     n_geo = len(getattr(pipe, "_gpool", None) or [])
     pipe.close()
+    ach = tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
     return {
-        **({"cpu_baseline": cpu} if cpu else {}),
         "workload": f"C3: {pages_per_step} synthetic 2048x3072 text pages per step through OCRPipeline.run_ocr_batch "
-                    "(staged: pages grouped 6 at a time through tile/binarise + DeepLabV3+ with fitted head + mask, cv2 "
-                    "contours + reading order in geometry worker processes (no CUDA in them), GPU line crops, all lines of "
-                    "the batch through line prep + Easter2 + greedy CTC in one call; ONE CUDA context)",
-        "e2e_pages_per_sec": pages_per_step / dt, "e2e_lines_per_sec": n_lines / dt, "ms_per_page": dt * 1e3 / pages_per_step,
-        "host_threads": workers, "geometry_processes": n_geo, "pages_ok": len(ok), "lines_found": n_lines, "lines_on_pages": n_truth,
-        "lines_equal_to_truth": n_right,
-        "note": "host-bound: cv2.findContours + reading-order Python (SURVEY 8(a)-10) take ~15-20 ms/page/core on the noisy "
-                "masks of the fitted head (~750 contours per page); GPU stages ~3 ms/page",
+                    "(pageable numpy in; staged: pages grouped 6 at a time through tile/binarise + DeepLabV3+ (trained "
+                    "decoder) + mask, cv2 contours + reading order in geometry worker processes (no CUDA in them), GPU "
+                    "line crops, all lines of the batch through line prep + Easter2 + greedy CTC in one call; ONE CUDA "
+                    "context) -> OCRLine text",
+        "metric": "pages_per_sec", "value": pages_per_step / dt, "unit": "pages/s",
+        "e2e": {"value": pages_per_step / dt, "unit": "pages/s", "lines_per_sec": n_lines / dt,
+                "h2d_bytes_per_step": int(sum(p.nbytes for p in pages)), "d2h_bytes_per_step": int(sum(p.shape[0] * p.shape[1] for p in pages)),
+                "api": "OCRPipeline.run_ocr_batch(list of pageable HWC u8 pages) -> [(OpStatus, [mask, lines, OCRLine, angle])]"},
+        "ms_per_page": dt * 1e3 / pages_per_step, "gpu_launches_per_step": int(launches),
+        "host_threads": workers, "geometry_processes": n_geo, "host_cores": len(os.sched_getaffinity(0)),
+        "pages_ok": ok, "lines_found": n_lines, "lines_on_pages": n_truth, "lines_equal_to_truth": n_right,
+        "lines_equal_to_truth_fraction": n_right / max(1, n_truth),
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (both networks) inside the page -> text run",
+                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "peak_source": peak_src,
+                     "conv_ms_per_page": tc_ms / pages_per_step, "network_kernel_ms_per_page": gpu_ms / pages_per_step,
+                     "share_of_wall": tc_ms / 1e3 / dtp if dtp else None},
+        **({"cpu_baseline": cpu} if cpu else {}),
     }
+
+
+def _proc_tree_cpu_seconds():
+    """user + system CPU seconds of this process and its live children (geometry workers)."""
+    try:
+        import psutil
+
+        me = psutil.Process()
+        tot = sum(me.cpu_times()[:2])
+        for c in me.children(recursive=True):
+            try:
+                tot += sum(c.cpu_times()[:2])
+            except Exception:  # noqa: BLE001
+                pass
+        return tot
+    except Exception:  # noqa: BLE001
+        t = os.times()
+        return t.user + t.system
+
+
+def bench_c5(eng, rank: int, world: int, sampler, steps: int = 2, pages_per_rank: int = 192):
+    """Config C5, time-bounded: the page-sharded page -> text run.  `pages_per_rank` x world synthetic text pages
+    (the C3 generator) are split into contiguous per-rank ranges by sharding.run_sharded; every rank pushes its
+    range through its own OCRPipeline.run_ocr_batch (pageable numpy in) and rank 0 gathers the per-page line
+    boxes + texts on the host.  No collective on the data path.  Timed with a barrier on both sides, max over
+    ranks; CPU seconds of every rank's process tree and the H2D byte rate say what limits it."""
+    import torch
+    import torch.distributed as dist
+
+    from ocr_inference_b200 import sharding
+    from ocr_inference_b200.data import OpStatus
+
+    cores = len(os.sched_getaffinity(0))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    geo = max(1, min(8, cores // max(1, local_world) - 2))
+    pipe = _pipeline(eng)
+    n_pages = pages_per_rank * world
+    mine = sharding.shard_range(n_pages, world, rank)
+    # every rank materialises only its own shard (generated on the fly per shard, SURVEY 8d C5)
+    shard_pages, shard_truth = text_pages(len(mine), seed0=3003 + 16 * rank)
+    offset = mine.start
+
+    def load(i):
+        return shard_pages[i - offset]
+
+    local_out = []
+
+    def process(pages):
+        out = []
+        for st, res in pipe.run_ocr_batch(pages, geometry_procs=geo, **PT_KW):
+            if st == OpStatus.SUCCESS:
+                out.append(("ok", [((l.bbox.x, l.bbox.y, l.bbox.w, l.bbox.h), o.text) for l, o in zip(res[1], res[2])]))
+            else:
+                out.append(("failed", str(res)))
+        local_out.extend(out)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    sharding.run_sharded(min(n_pages, 32 * world), lambda i: shard_pages[(i - 32 * rank) % len(shard_pages)], process, chunk=32)  # warm-up
+    barrier()
+    cpu0, w0 = _proc_tree_cpu_seconds(), time.time()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        results = sharding.run_sharded(n_pages, load, process, chunk=96)
+    barrier()
+    dt = time.perf_counter() - t0
+    cpu_s = _proc_tree_cpu_seconds() - cpu0
+    if sampler:
+        sampler.mark(w0, time.time(), "c5")
+    # every rank scores its own shard of the last step against the generator's transcriptions
+    ok = n_lines = right = 0
+    for res, want in zip(local_out[-len(mine):], shard_truth):
+        if res[0] != "ok":
+            continue
+        ok += 1
+        n_lines += len(res[1])
+        pool = list(want)
+        for _, txt in res[1]:
+            if txt in pool:
+                pool.remove(txt)
+                right += 1
+    t = torch.tensor([dt, cpu_s, ok, n_lines, right, sum(len(t_) for t_ in shard_truth)], dtype=torch.float64,
+                     device=eng.device)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dt_max, cpu_total = float(tmax[0]), float(t[1])
+    local_ok, local_lines, local_right, n_truth = int(t[2]), int(t[3]), int(t[4]), int(t[5])
+    n_geo = len(getattr(pipe, "_gpool", None) or [])
+    pipe.close()
+    if rank != 0:
+        return None
+    assert results is not None and len(results) == n_pages
+    pages_done = n_pages * steps
+    busy = cpu_total / dt_max
+    h2d = pages_done * 2048 * 3072 * 3 / dt_max / 1e9
+    util = sampler.gpu_util("c5") if sampler else None
+    if busy >= 0.75 * cores:
+        limiter = f"host cores: {busy:.1f} of {cores} busy (cv2 geometry, page copies into pinned memory, Python dispatch)"
+    elif util is not None and util >= 85:
+        limiter = f"GPU: a kernel was running {util:.0f} % of the time on rank 0's device"
+    else:
+        limiter = (f"the GPU-owning Python process of each rank (stage dispatch under the GIL): {busy:.1f} of {cores} "
+                   f"cores busy, GPU kernel-active {util if util is not None else float('nan'):.0f} %")
+    return {
+        "workload": f"C5 (time-bounded): {n_pages} synthetic 2048x3072 text pages per step ({pages_per_rank} per GPU), "
+                    f"sharded over {world} rank(s) by sharding.run_sharded -> OCRPipeline.run_ocr_batch per rank, per-page "
+                    "(line boxes, texts) gathered on rank 0 by gather_object; pageable numpy pages in",
+        "pages_per_sec": pages_done / dt_max, "lines_per_sec": local_lines * steps / dt_max,
+        "n_gpus": world, "pages_per_step": n_pages, "steps": steps, "seconds": dt_max,
+        "host_cores": cores, "host_cores_busy": busy, "host_cores_busy_per_gpu": busy / world,
+        "geometry_procs_per_gpu": n_geo, "h2d_gbytes_per_sec": h2d, "gpu_kernel_active_pct_rank0": util,
+        "pages_ok": local_ok, "lines_found": local_lines, "lines_on_pages": n_truth,
+        "lines_equal_to_truth_fraction": local_right / max(1, n_truth),
+        "limiter": limiter, "scaling": "weak", "collectives_on_data_path": 0,
+    }
+
+
+def roofline_stages(eng):
+    """The HBM-class stages at step granularity (what one C2 / C1 step launches), CUDA events around each call,
+    inputs rotated through sets larger than the 126 MB L2.  bytes = SURVEY 8(d)'s algorithmic bytes."""
+    import cv2
+    import torch
+
+    from ocr_inference_b200 import line_detection as ld
+    from ocr_inference_b200 import synthetic
+    from ocr_inference_b200.engine import LAYOUT_TV, POST_SIGMOID
+
+    _, hbm, src = peaks()
+    dev = eng.device
+    H, W = PAGE_H, PAGE_W
+    out = {}
+
+    def timeit(fn, sets, reps=12, warm=3):
+        for i in range(warm):
+            fn(sets[i % len(sets)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(sets[i % len(sets)])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def add(key, what, ms, nbytes, launches):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        out[key] = {"what": what, "bytes": int(nbytes), "us": ms * 1e3, "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                    "frac": gbs / hbm, "launches": launches}
+
+    base = make_pages(4, DATA_SEED)
+    psets = [[torch.from_numpy(np.roll(base[(i + j) % 4], 31 * (i + 4 * j), axis=1).copy()).to(dev) for i in range(16)]
+             for j in range(2)]                                     # 2 x 302 MB
+    ms = timeit(lambda ps: eng.seg_preprocess_batch(ps), psets)
+    add("a-1", "gray + 51-tap Gaussian adaptive threshold + tile, 16 pages 2048x3072x3 -> 384 u8 tiles, ONE launch "
+               "(fp32-FMA bound by construction: 102 flop per pixel)", ms, 16 * 5 * H * W, 1)
+    metas = [dict(H0=H, W0=W, Hc=H, Wc=W, nty=4, ntx=6, pad_x=0, pad_y=0) for _ in range(16)]
+    # text-band-like logits: wide bands far above / below the threshold with soft edges (what a line model emits)
+    yy = torch.arange(128 * 4, device=dev, dtype=torch.float32)[:, None]
+    band = (torch.sin(yy / 9.0) * 14.0).expand(-1, 128 * 6)
+    lsets = []
+    for j in range(3):
+        page_low = band + torch.randn((512, 768), device=dev) * 0.5 + j
+        tiles = page_low.reshape(4, 128, 6, 128).permute(0, 2, 1, 3).reshape(24, 128, 128, 1)
+        lsets.append(tiles.repeat(16, 1, 1, 1).contiguous())         # [384,128,128,1]
+    ms = timeit(lambda lg: eng.seg_postprocess_lowres_batch(lg, metas, POST_SIGMOID, 0.9), lsets)
+    add("a-3", "line masks of 16 pages from low-res logits (x4 upsample + sigmoid>0.9 + stitch fused), ONE launch",
+        ms, 16 * (24 * 128 * 128 * 4 + H * W), 1)
+    page_h, boxes, _ = synthetic.text_page(3003)
+    bandm = synthetic.band_mask(boxes, H, W, grow=2, thin=0.45)
+    contours, _ = cv2.findContours(bandm, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    rois, masks, hs = [], [], []
+    for c in contours:
+        roi, m, h = ld._roi_mask(c, H, W)
+        rois.append(roi), masks.append(m), hs.append(h)
+    pack = eng.pack_masks(masks, rois)
+    ses = [ld._se_for(h, 2.0) for h in hs]
+    idx = list(range(len(rois)))
+    tp = [torch.from_numpy(np.roll(page_h, 13 * i, axis=1).copy()).to(dev) for i in range(8)]
+    crops, hw, off = eng.extract_lines(tp[0], pack, idx, ses)
+    hw_h = hw.cpu().numpy()
+    crop_px = int((hw_h[:, 0].astype(np.int64) * hw_h[:, 1]).sum())
+    l0 = eng.launch_count()
+    eng.extract_lines(tp[0], pack, idx, ses)
+    n_l = eng.launch_count() - l0
+    ms = timeit(lambda p_: eng.extract_lines(p_, pack, idx, ses), tp)
+    add("a-5", f"masked crops of the {len(idx)} lines of one page ({crop_px / 1e6:.1f} Mpx): SAT dilation, AND, empty "
+               "row/column deletion, gather", ms, 6 * crop_px, int(n_l))
+    L = C1_LINES
+    csets = []
+    for j in range(8):
+        cs, _ = synthetic.glyph_lines(1001 + j, L)
+        csets.append(eng.pack_crops(cs, key=f"rs{j}") + (sum(c.shape[0] * c.shape[1] for c in cs),))
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    eng.ocr_prepare_lines(csets[0][0], csets[0][1], csets[0][2], L, 80, 2000, False)
+    n_l = eng.launch_count() - l0
+    ms = timeit(lambda c: eng.ocr_prepare_lines(c[0], c[1], c[2], L, 80, 2000, False), csets)
+    add("a-7", "64 ragged crops -> cv2-exact resize, pad, adaptive threshold -> bf16 [64,2000,128]", ms,
+        3 * csets[0][3] + L * 2 * 80 * 2000 * 128 // 80, int(n_l))
+    lg = [torch.randn((L, 500, 77), device=dev) for _ in range(16)]
+    ms = timeit(lambda x: eng.ctc_greedy(x, layout=LAYOUT_TV), lg)
+    add("a-9", "argmax + CTC collapse, 64 lines [500,77] fp32 (C1 size)", ms, L * 500 * 77 * 4, 1)
+    big = [torch.randn((1024, 500, 77), device=dev) for _ in range(2)]
+    ms = timeit(lambda x: eng.ctc_greedy(x, layout=LAYOUT_TV), big, reps=8)
+    add("a-9@1024", "argmax + CTC collapse, 1024 lines (a page batch)", ms, 1024 * 500 * 77 * 4, 1)
+    out["peak_source"] = src
+    return out
 
 
 def bench_c4(eng, steps: int = 2):
@@ -476,82 +787,6 @@ def bench_c4(eng, steps: int = 2):
             "megapixels_per_sec": 2 * sum(h * w for h, w in sizes) / dt / 1e6,
             "per_image_calls_pages_per_sec": len(pages) / dt1, "batch_equals_per_image": same,
             "last_mask_shape": list(m.shape)}
-
-
-def _c3_worker(rank, n_workers, device, pages_per_worker, steps, threads, barrier, q):
-    """One host process of the C3 page->text run: owns a shard of the pages and its own OCRPipeline (CUDA
-    context, weights, workspaces) on `device`.  Pages are independent units: no exchange."""
-    try:
-        import torch
-
-        from ocr_inference_b200 import synthetic
-        from ocr_inference_b200.data import LineDetectionConfig, OpStatus
-        from ocr_inference_b200.inference import OCRPipeline, get_engine
-        from ocr_inference_b200.synthetic_weights import seg_weights_fitted
-        from ocr_inference_b200.weights import write_blob
-
-        torch.cuda.set_device(device)
-        eng = get_engine(device)
-        pipe = OCRPipeline(_ocr_config(), LineDetectionConfig("", write_blob(seg_weights_fitted(11)),
-                                                              "deeplabv3plus-r34", 512, ["line"]), None, engine=eng)
-        base = [synthetic.text_page(3003 + (rank * 2 + i) % 4) for i in range(2)]
-        pages = [base[i % 2][0] for i in range(pages_per_worker)]
-        kw = dict(k_factor=2.0, bbox_tolerance=2.5)
-        pipe.run_ocr_batch(pages[:max(2, threads)], workers=threads, geometry_procs=0, **kw)
-        torch.cuda.synchronize()
-        barrier.wait()
-        t0 = time.perf_counter()
-        n_lines = n_ok = 0
-        for _ in range(steps):
-            for st, res in pipe.run_ocr_batch(pages, workers=threads, geometry_procs=0, **kw):
-                if st == OpStatus.SUCCESS:
-                    n_ok += 1
-                    n_lines += len(res[2])
-        torch.cuda.synchronize()
-        q.put((rank, t0, time.perf_counter(), n_ok, n_lines, None))
-    except Exception as e:  # noqa: BLE001
-        try:
-            barrier.abort()
-        except Exception:  # noqa: BLE001
-            pass
-        q.put((rank, 0.0, 0.0, 0, 0, repr(e)))
-
-
-def bench_c3_procs(device: int, n_workers: int, pages_per_worker: int = 8, steps: int = 2, threads: int = 2):
-    """C3 with several host processes per GPU: the cv2 / Python geometry of SURVEY 8(a)-10 is the per-page
-    critical path (~25 ms per page per core, GIL-bound inside one process), the GPU stages take ~3-7 ms."""
-    import multiprocessing as mp
-
-    ctx = mp.get_context("spawn")
-    barrier, q = ctx.Barrier(n_workers), ctx.Queue()
-    procs = [ctx.Process(target=_c3_worker, args=(r, n_workers, device, pages_per_worker, steps, threads, barrier, q))
-             for r in range(n_workers)]
-    for p in procs:
-        p.start()
-    out, deadline = [], time.time() + 240
-    while len(out) < n_workers:
-        try:
-            out.append(q.get(timeout=2))
-        except Exception:  # noqa: BLE001  (queue.Empty)
-            dead = [p for p in procs if p.exitcode not in (None, 0)]
-            if dead or time.time() > deadline:
-                for p in procs:
-                    if p.is_alive():
-                        p.terminate()
-                return {"error": f"{len(dead)} worker(s) died" if dead else "timeout waiting for the workers"}
-    for p in procs:
-        p.join(timeout=30)
-        if p.is_alive():
-            p.terminate()
-    errs = [o[5] for o in out if o[5]]
-    if errs:
-        return {"error": errs[0]}
-    t0, t1 = min(o[1] for o in out), max(o[2] for o in out)
-    pages = sum(o[3] for o in out)
-    lines = sum(o[4] for o in out)
-    return {"host_processes": n_workers, "threads_per_process": threads, "pages": pages,
-            "e2e_pages_per_sec": pages / (t1 - t0), "e2e_lines_per_sec": lines / (t1 - t0),
-            "note": "perf_counter is CLOCK_MONOTONIC (system-wide): first worker start to last worker end"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -640,23 +875,42 @@ def run_ours(args, rank, world, local_rank):
     prof = eng.profile_results()
     eng.profile(False)
 
-    # ---- e2e: host numpy pages in, host numpy masks out -----------------------------------
+    # ---- e2e: the reference's calling convention -- pageable numpy pages in, fresh numpy masks out ------------
     for _ in range(max(1, args.warmup // 2)):
-        det.predict_batch(pages, pinned=pinned, copy=False)
+        det.predict_batch(pages)
     barrier()
     w0 = time.time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = det.predict_batch(pages, pinned=pinned, copy=False)
+        out = det.predict_batch(pages)                       # pinned=None (pageable route), copy=True
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if sampler:
         sampler.mark(w0, time.time())
+    assert all(isinstance(o, np.ndarray) and o.flags["OWNDATA"] for o in out)
+    # ---- the io-binding style of use: caller-pinned inputs, masks left in the object's pinned staging buffers ----
+    det.predict_batch(pages, pinned=pinned, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        det.predict_batch(pages, pinned=pinned, copy=False)
+    torch.cuda.synchronize()
+    iob_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, iob_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, iob_ms = float(t[0]), float(t[1]), float(t[2])
+
+    # ---- C5: the page-sharded page -> text run, at every N ----------------------------------------------
+    c5 = None
+    if args.extras:
+        try:
+            c5 = bench_c5(eng, rank, world, sampler)
+        except Exception as e:  # noqa: BLE001  (the headline must still print)
+            c5 = {"error": repr(e)}
+            if world > 1:
+                raise
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -689,21 +943,32 @@ def run_ours(args, rank, world, local_rank):
         "share_of_network_time": tc_ms / all_ms if all_ms else None,
         "share_of_step": tc_ms / ms_profiled if ms_profiled else None,
         "profiled_ms_per_step": ms_profiled / args.steps,
+        "whole_step_frac": (seg_flops_per_tile(1) * 24 * PAGES_PER_STEP / ((ms / args.steps) / 1e3) / 1e12) / peak_tf,
         "by_kernel": {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
                           "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 and v[1] > 0 else None)}
                       for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},
     }
     cpu_v, cpu_s, cores = cpu_reference_pages_per_sec(1) if world >= 1 and args.cpu_baseline else (None, None, None)
-    extras = {}
-    if world == 1 and args.extras:
-        try:
-            extras["c1"] = bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline)
-            extras["c3"] = bench_c3(eng, 2, with_cpu=args.cpu_baseline)
-            extras["c4"] = bench_c4(eng)
-            nproc = max(2, min(8, len(os.sched_getaffinity(0)) // 2))
-            extras["c3"]["multi_process"] = bench_c3_procs(local_rank, nproc, threads=1)
-        except Exception as e:  # noqa: BLE001  (the headline must still print)
-            extras["error"] = repr(e)
+    c1 = c3 = c4 = stages = None
+    errors = {}
+    if args.extras:
+        for name, fn in (("roofline_stages", lambda: roofline_stages(eng)),
+                         ("c1", lambda: bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline) if world == 1 else None),
+                         ("c3", lambda: bench_c3(eng, 2, with_cpu=args.cpu_baseline) if world == 1 else None),
+                         ("c4", lambda: bench_c4(eng) if world == 1 else None)):
+            try:
+                v = fn()
+            except Exception as e:  # noqa: BLE001  (the headline must still print)
+                v = None
+                errors[name] = repr(e)
+            if name == "roofline_stages":
+                stages = v
+            elif name == "c1":
+                c1 = v
+            elif name == "c3":
+                c3 = v
+            else:
+                c4 = v
     h2d = sum(p.nbytes for p in pages)
     d2h = sum(o.nbytes for o in out)
     line = {
@@ -717,15 +982,25 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2: 302 MB of pages + >2 GB of activations per step (L2 = 126 MB)",
                    "sharding": "pages sharded across ranks, no collective on the data path"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps, "api": "LineDetection.predict_batch(host pages, copy=False) -> host masks in pinned staging buffers"},
+                "ms_per_step": e2e_ms / args.steps,
+                "api": "LineDetection.predict_batch(list of pageable numpy pages) -> list of fresh numpy masks (the "
+                       "reference's ownership: pageable in, caller-owned arrays out)"},
+        "e2e_io_binding": {"value": total_pages / (iob_ms / 1e3), "unit": UNIT, "ms_per_step": iob_ms / args.steps,
+                           "api": "predict_batch(pages, pinned=caller-pinned tensors, copy=False): masks stay in the "
+                                  "object's pinned staging buffers (onnxruntime io-binding style of use)"},
         "gpu_launches": int(launches),
+        "simt_conv_launches": int(eng.simt_launch_count()),
+        "conv_plans_built": int(eng.conv_plans_built()),
         "roofline": roofline,
+        "roofline_stages": stages,
         "cpu_baseline": ({"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                           "sample": "1 page (24 tiles), one pass through oracle/ (cv2 host code + torch-CPU fp32 "
                                     "network), all host threads"} if cpu_v else None),
         "clocks": sampler.summary(),
         "mask_checksum": checksum,
-        "other_workloads": extras,
+        "c1": c1, "c3": c3, "c5": c5,
+        "other_workloads": {"c4": c4, "c5": c5, "c1": "top-level key c1", "c3": "top-level key c3",
+                            **({"errors": errors} if errors else {})},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -242,6 +242,15 @@ int bdrc_ocr_forward(bdrc_ctx* ctx, bdrc_model* m, const void* lines_bf16, int L
 int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout,
                     int blank, int32_t* ids, int32_t* lens, void* stream);
 
+/* Front end of the beam-search decode (CTCDecoder.ctc_beam_decode / pyctcdecode decode_beams, BDRC/inference.py:
+ * 114-118, 386-414): per (line, time step) the candidate tokens of the log-softmaxed row -- log p >= min_logp
+ * (pyctcdecode's token_min_logp, -5), at most bdrc_ctc_topk_width() of them, sorted by descending log p (ties: lower
+ * index), the arg-max always present.  tokens / logps: [L][T][width], counts: [L][T].  The prefix merge over
+ * these candidates is host code (ocr_inference_b200/ctc_beam.py). */
+int bdrc_ctc_topk(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout, float min_logp,
+                  int32_t* tokens, float* logps, int32_t* counts, void* stream);
+int bdrc_ctc_topk_width(void);
+
 /* ---- test hook: one convolution through the implicit-GEMM engine ------------------------ */
 /* x bf16 NHWC [N][H][W][Cin]; w fp32 OIHW (host); bias fp32 (host, may be NULL); residual
  * bf16 NHWC or NULL; y bf16 (or fp32 if out_fp32) NHWC [N][Ho][Wo][Cout]. */

@@ -83,6 +83,9 @@ _SIGS = {
     "bdrc_ocr_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "bdrc_ocr_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "bdrc_ctc_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                              c_void_p]),
+    "bdrc_ctc_topk_width": (c_int, []),
     "bdrc_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p]),
     "bdrc_depthwise3x3_test": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

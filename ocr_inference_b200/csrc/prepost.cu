@@ -536,6 +536,67 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
   return v > bv || (v == bv && i < bi);
 }
 
+// ------------------------------------------------------------------------------------------
+// Beam-search front end (BDRC/inference.py:114-118, 386-414: CTCDecoder.ctc_beam_decode): per time step the
+// log-softmax of the row and its candidate tokens -- those with log p >= min_logp, at most CTC_TOPK of them, in
+// descending order (ties: lower index first), the arg-max always included.  One warp per (line, step); the
+// prefix merge over these few candidates per step runs on the host (ocr_inference_b200/ctc_beam.py).
+// ------------------------------------------------------------------------------------------
+constexpr int CTC_TOPK = 16;
+__global__ void __launch_bounds__(256)
+ctc_topk_kernel(const float* __restrict__ logits, int L, int V, int T, int layout, float min_logp,
+                int32_t* __restrict__ tok, float* __restrict__ logp, int32_t* __restrict__ cnt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= L * T) return;
+  const int l = warp / T, t = warp - l * T;
+  const float* base = logits + (size_t)l * V * T;
+  const size_t sv = layout == BDRC_LAYOUT_TV ? 1 : (size_t)T;
+  const float* row = base + (layout == BDRC_LAYOUT_TV ? (size_t)t * V : (size_t)t);
+  // lane-strided copy of the row: v = lane, lane + 32, ...  (V <= 32 * 8)
+  float x[8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int v = lane + 32 * j;
+    x[j] = v < V ? row[(size_t)v * sv] : -INFINITY;
+    m = fmaxf(m, x[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += (lane + 32 * j < V) ? expf(x[j] - m) : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // xor tree: same bits in every lane
+  const float lse = m + logf(sum);
+  int n = 0;
+  const size_t ob = ((size_t)l * T + t) * CTC_TOPK;
+  for (int k = 0; k < CTC_TOPK; ++k) {
+    // warp arg-max over what is left: larger value wins, on equal values the lower token index
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int v = lane + 32 * j;
+      if (v < V && (x[j] > bv || (x[j] == bv && v < bi))) { bv = x[j]; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (bi == 0x7fffffff) break;                       // row exhausted (or NaN / -inf only)
+    const float lp = bv - lse;
+    if (k > 0 && !(lp >= min_logp)) break;
+    if (lane == 0) { tok[ob + k] = bi; logp[ob + k] = lp; }
+    ++n;
+    if ((bi & 31) == lane) x[bi >> 5] = -INFINITY;     // remove it from its owner's registers
+  }
+  if (lane == 0) cnt[(size_t)l * T + t] = n;
+}
+
 constexpr int CTC_ROWS = 128;
 __global__ void __launch_bounds__(512)
 ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, int blank,
@@ -866,5 +927,23 @@ int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
+
+int bdrc_ctc_topk(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int layout, float min_logp,
+                  int32_t* tokens, float* logps, int32_t* counts, void* stream) {
+  if (!ctx) return BDRC_ERR_ARG;
+  if (L == 0) return 0;
+  BDRC_REQUIRE(ctx, logits && tokens && logps && counts && V > 0 && V <= 256 && T > 0 &&
+                        (layout == BDRC_LAYOUT_TV || layout == BDRC_LAYOUT_VT),
+               "ctc_topk: bad arguments (V=%d T=%d; V <= 256)", V, T);
+  const long long warps = (long long)L * T;
+  bdrc_prof_begin(ctx, "a-9.ctc_topk", 0, (cudaStream_t)stream);
+  ctc_topk_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, L, V, T, layout, min_logp, tokens,
+                                                                                 logps, counts);
+  bdrc_prof_end(ctx, (cudaStream_t)stream);
+  BDRC_CHECK_LAUNCH(ctx);
+  return 0;
+}
+
+int bdrc_ctc_topk_width(void) { return CTC_TOPK; }
 
 }  // extern "C"

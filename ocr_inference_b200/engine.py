@@ -537,3 +537,17 @@ class Engine:
         self._check(self.lib.bdrc_ctc_greedy(self.ctx.h, logits.data_ptr(), L, V, T, layout, blank, ids.data_ptr(),
                                              lens.data_ptr(), self.stream), "ctc_greedy")
         return ids, lens
+
+    def ctc_topk(self, logits: torch.Tensor, layout: int = LAYOUT_TV, min_logp: float = -5.0):
+        """Beam-search front end: (tokens int32 [L,T,K], log-probs fp32 [L,T,K], counts int32 [L,T])."""
+        logits = logits.contiguous()
+        L = int(logits.shape[0])
+        T, V = (int(logits.shape[1]), int(logits.shape[2])) if layout == LAYOUT_TV else \
+            (int(logits.shape[2]), int(logits.shape[1]))
+        K = int(self.lib.bdrc_ctc_topk_width())
+        tok = torch.zeros((L, T, K), dtype=torch.int32, device=self.device)
+        lp = torch.full((L, T, K), float("-inf"), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros((L, T), dtype=torch.int32, device=self.device)
+        self._check(self.lib.bdrc_ctc_topk(self.ctx.h, logits.data_ptr(), L, V, T, layout, min_logp, tok.data_ptr(),
+                                           lp.data_ptr(), cnt.data_ptr(), self.stream), "ctc_topk")
+        return tok, lp, cnt

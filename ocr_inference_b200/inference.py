@@ -18,7 +18,7 @@ import torch
 
 from .data import (CharsetEncoder, DewarpingResult, Encoding, KenLMConfig, LayoutDetectionConfig,  # noqa: F401
                    Line, LineDetectionConfig, OCRLine, OCRModelConfig, OpStatus)
-from .engine import LAYOUT_TV, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
+from .engine import LAYOUT_TV, LAYOUT_VT, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
 from .weights import MAGIC, load_reference_checkpoint
 
 _ENGINES: dict[int, Engine] = {}
@@ -48,18 +48,21 @@ def _read_weights(src):
 
 
 class CTCDecoder:
-    """Greedy CTC decoder with the reference's vocabulary conventions (BDRC/inference.py:75-118):
-    index 0 is '<blk>' when add_blank, label i maps to charset[i-1]."""
+    """CTC decoder with the reference's vocabulary conventions (BDRC/inference.py:75-118): index 0 is '<blk>' when
+    add_blank, label i maps to charset[i-1].  ctc_decode is the greedy best path (north_star); ctc_beam_decode is
+    the beam search of pyctcdecode without a language model (spec: ocr_inference_b200/ctc_beam.py; the
+    reference's fork is unpinned, so parity with it is unpinned)."""
 
     def __init__(self, charset: str | list[str], add_blank: bool, kenlm_config: KenLMConfig | None = None):
         self.blank_sign = "<blk>"
+        self.ctc_beam_width = 64                      # (sic) set but never passed on by the reference (:84)
         self.charset = list(charset) if isinstance(charset, str) else charset
         self.ctc_vocab = self.charset.copy()
         if add_blank:
             self.ctc_vocab.insert(0, self.blank_sign)
         self.blank_index = self.ctc_vocab.index(self.blank_sign) if self.blank_sign in self.ctc_vocab else 0
         if kenlm_config is not None:
-            # LM-fused beam search lives in an un-vendored fork (requirements.txt:13): out of scope
+            # LM-fused beam search needs KenLM + the un-vendored pyctcdecode fork (requirements.txt:13): out of scope
             print("KenLM disabled: beam search with a language model is not part of the B200 hot path")
 
     def encode(self, label: str):
@@ -71,13 +74,33 @@ class CTCDecoder:
     def ids_to_text(self, ids: Sequence[int]) -> str:
         return "".join(self.ctc_vocab[i] for i in ids).replace(self.blank_sign, "")
 
-    def ctc_decode(self, logits) -> str:
-        """logits (T, V) array-like -> text; runs the greedy kernel on the GPU."""
+    def _device_logits(self, logits):
+        """(T, V) or (V, T) array-like -> (device tensor [1, ., .], layout): the reference transposes when the
+        first axis has the vocabulary's length (BDRC/inference.py:373-376, 387-390)."""
         eng = get_engine()
-        t = torch.as_tensor(np.ascontiguousarray(logits, dtype=np.float32)).to(eng.device)[None]
-        ids, lens = eng.ctc_greedy(t, layout=LAYOUT_TV, blank=self.blank_index)
+        a = np.ascontiguousarray(logits, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError(f"logits must be 2-D (time x vocab or vocab x time), got shape {a.shape}")
+        layout = LAYOUT_VT if a.shape[0] == len(self.ctc_vocab) else LAYOUT_TV
+        return eng, torch.from_numpy(a).to(eng.device)[None], layout
+
+    def ctc_decode(self, logits) -> str:
+        """logits (T, V) or (V, T) array-like -> text; runs the greedy kernel on the GPU."""
+        eng, t, layout = self._device_logits(logits)
+        ids, lens = eng.ctc_greedy(t, layout=layout, blank=self.blank_index)
         n = int(lens[0].item())
         return self.ids_to_text(ids[0, :n].tolist())
+
+    def beams_from_candidates(self, tokens: np.ndarray, logps: np.ndarray, counts: np.ndarray):
+        from .ctc_beam import beams_to_output, merge_frames
+
+        return beams_to_output(merge_frames(tokens, logps, counts, self.blank_index), self.ctc_vocab, self.blank_index)
+
+    def ctc_beam_decode(self, logits):
+        """logits (T, V) or (V, T) -> list of OutputBeam (text, logit_score, ...), best first."""
+        eng, t, layout = self._device_logits(logits)
+        tok, lp, cnt = eng.ctc_topk(t, layout=layout)
+        return self.beams_from_candidates(tok[0].cpu().numpy(), lp[0].cpu().numpy(), cnt[0].cpu().numpy())
 
 
 class Detection:
@@ -272,6 +295,54 @@ class OCRInference:
     def run(self, line_image: np.ndarray, pre_pad: bool = True, use_lm: bool = False) -> str:
         return self.run_batch([line_image], pre_pad, use_lm)[0]
 
+    # ---- the reference's lower-level entry points (BDRC/inference.py:359-414) -----------------------------
+    def _predict(self, image_batch: np.ndarray) -> np.ndarray:
+        """A prepared line in ANY of the reference's input layouts -- [1, H, W], [1, W, H] (swap_hw) or
+        [1, 1, H, W] (squeeze_channel off), values in {-1, +1} -- -> logits [T, V] (np.squeeze'd like :368).
+        swap_hw / squeeze_channel only describe how an ONNX graph wants the same image handed over; the B200
+        network consumes the line in its own time-major layout, so they change nothing but this unpacking."""
+        x = np.asarray(image_batch, dtype=np.float32)
+        if not self._squeeze_channel_dim:
+            if x.ndim != 4 or x.shape[1] != 1:
+                raise ValueError(f"squeeze_channel is off: expected [1, 1, H, W], got {x.shape}")
+            x = x[:, 0]
+        if x.ndim != 3:
+            raise ValueError(f"expected a [1, H, W] line batch, got {x.shape}")
+        if self._swap_hw:
+            x = np.transpose(x, (0, 2, 1))
+        if x.shape[1:] != (self._input_height, self._input_width):
+            raise ValueError(f"line batch {x.shape} does not match the model input {self._input_height}x{self._input_width}")
+        from .engine import OCR_CPAD
+
+        eng = self.engine
+        lines = torch.zeros((x.shape[0], self._input_width, OCR_CPAD), dtype=torch.bfloat16, device=eng.device)
+        lines[:, :, : self._input_height] = torch.from_numpy(np.ascontiguousarray(x)).to(eng.device).permute(0, 2, 1)
+        return np.squeeze(eng.ocr_forward(self.ocr_session, lines).cpu().numpy())
+
+    def _decode(self, logits: np.ndarray, use_lm: bool = False) -> str:
+        return self.ctc_decoder.ctc_decode(logits)          # [V, T] inputs are transposed there (:373-376)
+
+    def _decode_beams(self, logits: np.ndarray, use_lm: bool = False):
+        return self.ctc_decoder.ctc_beam_decode(logits)
+
+    def run_beam_batch(self, line_images: Sequence[np.ndarray], pre_pad: bool = True) -> list:
+        """Beam-search decode of many lines: a-7 and a-8 as in run_batch, per-step candidates on the GPU
+        (bdrc_ctc_topk), prefix merge per line on the host.  -> list (per line) of lists of OutputBeam."""
+        if len(line_images) == 0:
+            return []
+        for img in line_images:
+            self._check_fit(img, pre_pad)
+        eng = self.engine
+        dev, hw, off = eng.pack_crops(list(line_images))
+        lines, _ = eng.ocr_prepare_lines(dev, hw, off, len(line_images), self._input_height, self._input_width, pre_pad)
+        tok, lp, cnt = eng.ctc_topk(eng.ocr_forward(self.ocr_session, lines), layout=LAYOUT_TV)
+        tok, lp, cnt = tok.cpu().numpy(), lp.cpu().numpy(), cnt.cpu().numpy()
+        return [self.ctc_decoder.beams_from_candidates(tok[i], lp[i], cnt[i]) for i in range(len(line_images))]
+
+    def run_beam_code(self, line_image: np.ndarray, pre_pad: bool = True) -> list:
+        """BDRC/inference.py:400-414."""
+        return self.run_beam_batch([line_image], pre_pad)[0]
+
     def run_packed(self, crops_dev, hw_dev, off_dev, n: int, pre_pad: bool):
         """Lines already resident on the GPU (from extract_line_images): text per line."""
         eng = self.engine
@@ -419,6 +490,29 @@ class OCRPipeline:
             texts = self.ocr_inference.run_batch([np.asarray(k[0]) for k in keep], self.use_line_prepadding) if keep else []
         return OpStatus.SUCCESS, self._make_ocr_lines([k[1] for k in keep], texts, target_encoding)
 
+    def run_text_recognition_eval(self, line_images: list, sorted_lines: list,
+                                  target_encoding: Encoding = Encoding.UNICODE, top_k_beams: int = 10):
+        """Stage 5 in eval mode (BDRC/inference.py:668-726): beam-search decode, the top beam's text (spaces
+        removed, section sign -> space), ctc_conf = exp(length-normalised log score), logits = the beams' scores."""
+        import math
+
+        keep = [(np.asarray(img), ln) for img, ln in zip(line_images, sorted_lines)
+                if img.shape[0] != 0 and img.shape[1] != 0]
+        all_beams = self.ocr_inference.run_beam_batch([k[0] for k in keep], self.use_line_prepadding) if keep else []
+        ocr_lines = []
+        for (_, ln), beams in zip(keep, all_beams):
+            if not beams:
+                continue
+            beams = beams[:top_k_beams]
+            pred = beams[0].text.strip().replace(" ", "").replace("§", " ")
+            pred = self._convert(pred, target_encoding)
+            norm_logp = beams[0].logit_score / max(len(beams[0].text), 1)
+            ocr_lines.append(OCRLine(
+                guid=ln.guid, text=pred,
+                encoding=Encoding.WYLIE.name if target_encoding == Encoding.WYLIE._name_ else Encoding.UNICODE.name,
+                ctc_conf=float(math.exp(norm_logp)), logits=[float(b.logit_score) for b in beams], lm_scores=None))
+        return OpStatus.SUCCESS, ocr_lines
+
     def _make_ocr_lines(self, lines: list, texts: list, target_encoding) -> list:
         ocr_lines = []
         for ln, t in zip(lines, texts):
@@ -447,8 +541,6 @@ class OCRPipeline:
                 return OpStatus.FAILED, "OCR pipeline not ready"
             if image is None:
                 return OpStatus.FAILED, "Input image is None"
-            if eval_mode:
-                return OpStatus.FAILED, "OCR processing failed: eval_mode (beam search) is not part of the B200 hot path"
             try:
                 status, result = self.detect_lines(image)
                 if status == OpStatus.FAILED:
@@ -480,7 +572,11 @@ class OCRPipeline:
             except Exception as e:  # noqa: BLE001
                 return OpStatus.FAILED, f"Line extraction failed: {str(e)}"
             try:
-                status, result = self.run_text_recognition(line_images, sorted_lines, target_encoding=target_encoding)
+                if eval_mode:
+                    status, result = self.run_text_recognition_eval(line_images, sorted_lines,
+                                                                    target_encoding=target_encoding)
+                else:
+                    status, result = self.run_text_recognition(line_images, sorted_lines, target_encoding=target_encoding)
                 if status == OpStatus.FAILED:
                     return status, result
                 ocr_lines = result
@@ -939,18 +1035,16 @@ class ModernBookFormatLayoutDetection:
 
     def run(self, directory: str, output_dir: str, filter_classes=None, batch_size: int = 4, num_workers: int = 4,
             class_threshold: float = 0.8):
-        import cv2
-        from glob import glob
-
         if filter_classes:
             for c in filter_classes:
                 if c not in self.classes:
                     raise ValueError(f"ERROR: provided filter classes: {filter_classes} are not part of the model's classes!")
         os.makedirs(output_dir, exist_ok=True)
-        paths = sorted(p for p in glob(os.path.join(directory, "*")) if p.lower().endswith((".jpg", ".png", ".jpeg")))
-        step = max(1, int(batch_size))
-        for b0 in range(0, len(paths), step):
-            chunk = paths[b0:b0 + step]
-            imgs = [cv2.cvtColor(cv2.imread(p, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB) for p in chunk]
-            for p, masks in zip(chunk, self.predict_masks_batch(imgs, class_threshold, copy=False)):
-                self.extract_json_data({"image_name": os.path.basename(p)}, masks, filter_classes, output_dir)
+        from .dataio import PageLoader
+
+        # the files are decoded ahead by `num_workers` host threads (the reference's DataLoader workers, :935-941);
+        # `batch_size` pages share one forward call
+        loader = PageLoader(directory, workers=max(1, int(num_workers)), prefetch=2 * max(1, int(batch_size)))
+        for imgs, metas in loader.batches(max(1, int(batch_size))):
+            for meta, masks in zip(metas, self.predict_masks_batch(imgs, class_threshold, copy=False)):
+                self.extract_json_data(meta, masks, filter_classes, output_dir)

@@ -103,19 +103,22 @@ def _fitted(prefix: str, path: str | None = None) -> dict[str, np.ndarray]:
 
 
 def seg_weights_fitted(seed: int = 11, path: str | None = None) -> dict[str, np.ndarray]:
-    """seg_weights(seed, 1) with the last two 1x1 layers (decoder.block2.0.1, segmentation_head.0)
-    replaced by the tensors tests/golden/make_heads.py fitted to synthetic text bands: the network then
-    emits line-like masks on synthetic.page() inputs, so the pipeline stages after it see realistic work."""
-    assert seed == 11, "the committed fit belongs to seed 11"
+    """seg_weights(seed, 1) with the whole DeepLabV3+ decoder (ASPP, block1, block2, head: 1.15 M parameters)
+    replaced by the tensors tests/golden/train_standins.py trained against the thinned text-band mask of
+    synthetic text / stroke-band pages (the ResNet-34 body keeps the seeded random init): the network then emits
+    one clean blob per text line, like a trained line model, so the stages after it see realistic work."""
+    assert seed == 11, "the committed tensors belong to seed 11"
     w = seg_weights(seed, 1, 3)
     w.update(_fitted("seg.", path))
     return w
 
 
 def easter2_weights_fitted(path: str | None = None) -> dict[str, np.ndarray]:
-    """Easter2 (V = 77, H = 80) trained with CTC on synthetic.glyph_line() by tests/golden/make_heads.py;
-    values are the committed fp16 tensors widened to fp32.  Gives peaky, temporally coherent logits like a
-    real checkpoint, which is what the >= 95 % identical-decoded-lines parity target presupposes."""
+    """Easter2 (V = 77, H = 80) trained with CTC by tests/golden/train_standins.py on the line crops the pipeline's
+    own extraction cuts out of synthetic.text_page() pages plus synthetic.glyph_line() crops; values are the
+    committed fp16 tensors widened to fp32.  It reads its pages (316 / 316 held-out page lines equal to the
+    generator's transcription, tests/golden/fitted_heads_report.json), which is what the >= 95 % identical-
+    decoded-lines parity target presupposes."""
     w = _fitted("ocr.", path)
     if "conv1.weight" not in w:           # fixture holds only the output layers: rest is the seeded init
         base = easter2_weights(7, 77, 80)

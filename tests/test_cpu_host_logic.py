@@ -374,3 +374,34 @@ def test_modern_layout_weight_source_prefers_a_container_over_the_reference_pth(
     assert M._weights_source(LayoutDetectionConfig(w, "", "x", 512, classes)) is w
     with pytest.raises(FileNotFoundError):
         M._weights_source(LayoutDetectionConfig(str(tmp_path / "no.pth"), str(tmp_path / "no.onnx"), "x", 512, classes))
+
+
+def test_image_dataset_and_page_loader(tmp_path):
+    """dataio.ImageInferenceDataset (BDRC/inference.py:829-857) and PageLoader: sorted file order, CHW u8 RGB
+    tensors with the decoder's pixels, meta fields, read-ahead that keeps order and propagates decode errors."""
+    import cv2
+
+    from ocr_inference_b200.dataio import ImageInferenceDataset, PageLoader
+
+    rng = np.random.default_rng(1)
+    imgs = {}
+    for name, shape in (("b.png", (40, 60, 3)), ("a.jpg", (50, 30, 3)), ("c.jpeg", (20, 20, 3)), ("g.png", (16, 24))):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        cv2.imwrite(str(tmp_path / name), img)
+        imgs[name] = img
+    (tmp_path / "notes.txt").write_text("not an image")
+    ds = ImageInferenceDataset(str(tmp_path))
+    assert [os.path.basename(p) for p in ds.paths] == ["a.jpg", "b.png", "c.jpeg", "g.png"] and len(ds) == 4
+    t, meta = ds[1]
+    assert meta == {"image_name": "b.png", "orig_shape": (40, 60)} and t.dtype == torch.uint8 and tuple(t.shape) == (3, 40, 60)
+    assert np.array_equal(t.numpy().transpose(1, 2, 0), imgs["b.png"][..., ::-1])        # PNG is lossless; BGR -> RGB
+    tg, _ = ds.get_item(3)
+    assert tuple(tg.shape) == (3, 16, 24)                                                  # gray file, mode "rgb"
+    tg1, _ = ImageInferenceDataset(str(tmp_path), mode="unchanged")[3]
+    assert tuple(tg1.shape) == (1, 16, 24) and np.array_equal(tg1[0].numpy(), imgs["g.png"])
+    seen = [(m["image_name"], p.shape) for p, m in PageLoader(str(tmp_path), workers=3, prefetch=2)]
+    assert seen == [("a.jpg", (50, 30, 3)), ("b.png", (40, 60, 3)), ("c.jpeg", (20, 20, 3)), ("g.png", (16, 24, 3))]
+    assert [len(b[0]) for b in PageLoader(str(tmp_path)).batches(3)] == [3, 1]
+    (tmp_path / "d.png").write_bytes(b"broken")
+    with pytest.raises(OSError):
+        list(PageLoader(str(tmp_path)))

@@ -1,9 +1,10 @@
-"""GPU parity with TRAINED-LIKE weights (tests/golden/fitted_heads.npz, made by tests/golden/make_heads.py).
+"""GPU parity with TRAINED stand-in weights (tests/golden/fitted_heads.npz, made by tests/golden/train_standins.py).
 
 BASELINE.json's target is ">= 95 % identical decoded lines vs the reference CPU path".  With random-init
 weights most time steps are near-ties (test_gpu_nets.py measures tie-excluded argmax parity there); here the
-recogniser was CTC-trained on synthetic glyph lines and the segmentation head fitted to synthetic text
-bands, so whole decoded lines and whole line masks can be compared the way a user would.
+recogniser was CTC-trained on the pipeline's own line crops of synthetic text pages (and on glyph lines) and the
+segmentation decoder on synthetic text bands, so whole decoded lines and whole line masks can be compared the
+way a user would.  Whole pages with the GPU's own mask: tests/test_gpu_pages.py.
 """
 import numpy as np
 import pytest
@@ -43,6 +44,7 @@ def test_trained_recogniser_identical_decoded_lines(engine):
     print(f"identical decoded lines GPU vs oracle: {same}/48; equal to the ground-truth transcription: {right}/48; "
           f"oracle top-2 margin / logit std: median {np.median(margin) / ref_logits.std():.2f}")
     assert same >= 46, f"only {same}/48 decoded lines identical to the CPU oracle"
+    assert right >= 44, f"the stand-in recogniser reads only {right}/48 of its lines"
     # every per-step argmax difference sits on a near-tie of the oracle: top-2 margin inside the bf16 tolerance
     dev, hw, off = engine.pack_crops(crops)
     lines, _ = engine.ocr_prepare_lines(dev, hw, off, 48, 80, 2000, False)
@@ -81,11 +83,16 @@ def test_fitted_segmentation_mask_matches_oracle(engine):
     print(f"mask agreement {agree:.5f}; decided pixels {dec_full.mean():.4f}; line pixels {float((ref_mask > 0).mean()):.3f}")
     assert np.array_equal(mask[dec_full], ref_mask[dec_full])
     assert agree >= 0.995
-    # the fitted head must give line-shaped output on these pages, or the pipeline tests exercise nothing
-    band = synth.band_mask(boxes, 1024, 1536, grow=2, thin=0.45) > 0      # what make_heads.py fitted
+    # the trained decoder must give line-shaped output on these pages, or the pipeline tests exercise nothing:
+    # IoU with the band target it was trained on, and about one contour per text line
+    import cv2
+
+    band = synth.band_mask(boxes, 1024, 1536, grow=2, thin=0.45) > 0      # what train_standins.py trained against
     iou = float(((mask > 0) & band).sum() / max(1, ((mask > 0) | band).sum()))
-    print(f"IoU with the fitted band target {iou:.3f}")
-    assert iou > 0.15
+    n_cnt = len(cv2.findContours(mask, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)[0])
+    print(f"IoU with the band target {iou:.3f}; {n_cnt} contours for {len(boxes)} lines")
+    assert iou >= 0.7
+    assert n_cnt <= 3 * len(boxes)
 
 
 def test_pipeline_page_to_text_trained_recogniser(engine, monkeypatch):

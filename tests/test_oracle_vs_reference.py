@@ -108,3 +108,72 @@ def test_check_line_tps_matches_reference_on_narrow_and_wide_lines(ref):
                 checked += 1
                 narrow += int(w < 160)
     assert checked >= 8 and narrow >= 2, (checked, narrow)
+
+
+def test_exporters_write_the_reference_files(ref, tmp_path):
+    """exporter.py (PageXML / text / JSON) against BDRC/exporter.py on the same lines: identical files (the XML
+    apart from its time stamp), for contours and for bounding boxes, with and without rotation."""
+    import copy
+    import re
+    from uuid import uuid1
+
+    import cv2
+
+    from ocr_inference_b200 import exporter as mine
+    from ocr_inference_b200.data import BBox, Line, OCRLine
+
+    ref_exp = __import__("BDRC.exporter", fromlist=["PageXMLExporter"])
+    ref_data = __import__("BDRC.data", fromlist=["Line"])
+    rng = np.random.default_rng(4)
+    image = np.zeros((900, 1400, 3), np.uint8)
+    lines, texts = [], []
+    for i in range(5):
+        canvas = np.zeros((900, 1400), np.uint8)
+        pts = np.stack([np.arange(100, 1300, 40), 100 + 150 * i + rng.integers(-8, 9, 30)], axis=1).astype(np.int32)
+        cv2.polylines(canvas, [pts], False, 255, 22)
+        cnt = max(cv2.findContours(canvas, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)[0], key=cv2.contourArea)
+        x, y, w, h = cv2.boundingRect(cnt)
+        lines.append((uuid1(), cnt, (x, y, w, h), (x + w // 2, y + h // 2)))
+        texts.append((lines[-1][0], f"line {i} ཀ་", "UNICODE"))
+    for kw in (dict(), dict(bbox=True), dict(angle=1.5, optimize=False)):
+        for cls in ("PageXMLExporter", "JsonExporter", "TextExporter"):
+            outs = []
+            for mod, dmod, sub in ((ref_exp, ref_data, "ref"), (mine, None, "mine")):
+                d = tmp_path / f"{sub}_{cls}_{len(kw)}"
+                d.mkdir(exist_ok=True)
+                L = (dmod.Line if dmod else Line)
+                B = (dmod.BBox if dmod else BBox)
+                O = (dmod.OCRLine if dmod else OCRLine)
+                ls = [L(g, c.copy(), B(*bb), ctr) for g, c, bb, ctr in lines]
+                ts = [O(g, t, e, None, None, None) for g, t, e in texts]
+                ex = getattr(mod, cls)(str(d))
+                if cls == "TextExporter":
+                    ex.export_lines(image, "page_01", ls, ts)
+                    ex.export_text("page_02", ts)
+                else:
+                    ex.export_lines(image, "page_01", ls, ts, **kw)
+                files = sorted(p for p in d.iterdir())
+                outs.append([re.sub(r"<Created>[^<]*</Created>", "<Created/>", p.read_text(encoding="UTF-8")) for p in files])
+                assert files
+            assert outs[0] == outs[1], (cls, kw)
+
+
+def test_parquet_writers_match_the_reference(ref, tmp_path):
+    import pyarrow.parquet as pq
+
+    from ocr_inference_b200 import dataio
+    from ocr_inference_b200.data import OCRLine
+
+    ref_utils = __import__("BDRC.utils", fromlist=["write_result_parquet"])
+    result = {"image_name": "p1.jpg", "image_width": 300, "image_height": 200, "num_contours": 2,
+              "contours": [[(1, 2), (30, 2), (30, 20)], [(5, 50), (90, 52), (88, 70), (4, 66)]],
+              "bboxes": [(1, 2, 30, 19), (4, 50, 87, 21)]}
+    ref_utils.write_result_parquet(result, tmp_path / "ref")
+    dataio.write_result_parquet(result, tmp_path / "mine")
+    a, b = pq.read_table(tmp_path / "ref" / "p1.parquet"), pq.read_table(tmp_path / "mine" / "p1.parquet")
+    assert a.schema == b.schema and a.to_pylist() == b.to_pylist()
+    lines = [OCRLine("g1", "abc", "UNICODE", 0.9, [-1.0, -2.5], None), OCRLine("g2", "", "UNICODE", 0.5, [-3.0], [0.1, 0.2])]
+    ref_utils.save_ocr_lines_parquet(lines, tmp_path / "ref.parquet")
+    dataio.save_ocr_lines_parquet(lines, tmp_path / "mine.parquet")
+    a, b = pq.read_table(tmp_path / "ref.parquet"), pq.read_table(tmp_path / "mine.parquet")
+    assert a.schema == b.schema and a.to_pylist() == b.to_pylist()
