@@ -73,6 +73,10 @@ int bdrc_profile_get(bdrc_ctx* ctx, int i, const char** name, float* ms, double*
  * the reference assembles its OCR input line by line in numpy (BDRC/inference.py:336-347, 618-666). */
 int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_t* dst_off, int n, void* dst,
                      int threads);
+/* n independent host -> host copies with up to `threads` native threads (no GPU work): hands result masks out of
+ * the pinned staging buffers as fresh caller-owned arrays, the ownership the reference's predict() has
+ * (BDRC/inference.py:170-183 returns a new ndarray per call). */
+int bdrc_host_copy(const void* const* src, void* const* dst, const int64_t* nbytes, int n, int threads);
 
 /* ---- models: replaces ort.InferenceSession(path)  BDRC/inference.py:128-130, 294 ------- */
 /* blob_host: a "BDRCW1" weight container (see ocr_inference_b200/weights.py), fp32 OIHW
@@ -216,6 +220,29 @@ int bdrc_extract_lines(bdrc_ctx* ctx, const uint8_t* page, int H, int W, int C,
                        const int32_t* kh_host, uint8_t* crops, size_t crops_capacity,
                        int32_t* crop_hw, int64_t* crop_off, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* ---- a-10 (GPU half): connected-component census of the line mask ----------------------- */
+/* The pixel-scanning part of the host geometry: cv2.boundingRect(mask) and the slice census of
+ * get_line_threshold (BDRC/line_detection.py:362-421: ~70 cv2.findContours calls on 20-pixel slices whose only
+ * output is "median contour centre // contour count" of the fullest slice), by union-find connected-component
+ * labelling on the device: foreground components (8-connected) + holes (4-connected background components that
+ * do not reach the slice frame) = the contours findContours(RETR_LIST) returns; their bounding boxes give the
+ * centres.  Polygons (approxPolyDP, hulls, filled ROI masks) stay cv2 work on the host.
+ * row_any: u8 [H] (1 where the row holds foreground: the host's row compaction starts from it);
+ * header: int32 [16] = {x, y, w, h of boundingRect (w = 0: empty), x_steps, strip w, strip h, best slice,
+ * its contour count n, centres written, overflow flag, 0...}; centers: int32 [bdrc_census_max_centers()], the
+ * "cy + ch // 2" values of the best slice in unspecified order (their median is what is used).
+ * All outputs are device pointers. */
+size_t bdrc_mask_census_workspace_bytes(int H, int W, int slice_width);
+int bdrc_census_max_centers(void);
+int bdrc_mask_census(bdrc_ctx* ctx, const uint8_t* mask, int H, int W, int slice_width, uint8_t* row_any,
+                     int32_t* header, int32_t* centers, void* workspace, size_t workspace_bytes, void* stream);
+/* 8-connected foreground components of a mask with bounding box and pixel count
+ * (cv2.connectedComponentsWithStats, connectivity 8, without the background label): n_comp (device int32) and up to
+ * max_comp records int32 {x0, y0, x1, y1 (inclusive), area, root pixel} in unspecified order. */
+size_t bdrc_mask_components_workspace_bytes(int H, int W);
+int bdrc_mask_components(bdrc_ctx* ctx, const uint8_t* mask, int H, int W, int32_t* n_comp, int32_t* stats,
+                         int max_comp, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a-7: OCRInference._prepare_ocr_line  BDRC/inference.py:313-357 --------------------- */
 /* crops: L ragged HWC u8 (3 ch) images at byte offsets crop_off, sizes crop_hw (h,w).

@@ -32,6 +32,7 @@ _SIGS = {
     "bdrc_profile_get": (c_int, [c_void_p, c_int, C.POINTER(C.c_char_p), C.POINTER(c_float),
                                  C.POINTER(c_double)]),
     "bdrc_host_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+    "bdrc_host_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "bdrc_load_weights": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, C.POINTER(c_void_p)]),
     "bdrc_free_model": (None, [c_void_p]),
     "bdrc_seg_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -83,6 +84,13 @@ _SIGS = {
     "bdrc_ocr_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "bdrc_ocr_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "bdrc_mask_census_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bdrc_census_max_centers": (c_int, []),
+    "bdrc_mask_census": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    "bdrc_mask_components_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "bdrc_mask_components": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                     c_void_p]),
     "bdrc_ctc_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
     "bdrc_ctc_topk_width": (c_int, []),

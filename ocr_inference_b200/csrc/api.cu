@@ -187,6 +187,35 @@ int bdrc_host_gather(const void* const* src, const int64_t* nbytes, const int64_
   return BDRC_OK;
 }
 
+// n independent host -> host copies (src[i] -> dst[i], nbytes[i]) split evenly over a few native threads:
+// the hand-out of result masks as fresh caller-owned arrays (Detection.predict_batch, copy=True).
+int bdrc_host_copy(const void* const* src, void* const* dst, const int64_t* nbytes, int n, int threads) {
+  if (n < 0 || (n > 0 && (!src || !dst || !nbytes))) return BDRC_ERR_ARG;
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (nbytes[i] < 0 || (nbytes[i] > 0 && (!src[i] || !dst[i]))) return BDRC_ERR_ARG;
+    total += nbytes[i];
+  }
+  if (total == 0) return BDRC_OK;
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, HostPool::kMax + 1), total / (1 << 20)));
+  auto work = [&](int t) {
+    const int64_t lo = total * t / T, hi = total * (t + 1) / T;
+    int64_t pos = 0;
+    for (int i = 0; i < n && pos < hi; ++i) {
+      const int64_t a = std::max(lo, pos), b = std::min(hi, pos + nbytes[i]);
+      if (b > a)
+        std::memcpy(static_cast<uint8_t*>(dst[i]) + (a - pos), static_cast<const uint8_t*>(src[i]) + (a - pos), (size_t)(b - a));
+      pos += nbytes[i];
+    }
+  };
+  if (T == 1) {
+    work(0);
+    return BDRC_OK;
+  }
+  HostPool::get().run(T, work);
+  return BDRC_OK;
+}
+
 int bdrc_conv2d_test(bdrc_ctx* ctx, const void* x, int N, int H, int W, int Cin,
                      const float* w_host, const float* bias_host, int Cout, int R, int S,
                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,

@@ -303,11 +303,11 @@ struct PostBatch {
 };
 
 __global__ void __launch_bounds__(256) seg_post_line_lowres_batch_kernel(const PostBatch b) {
-  const PostPage pg = b.pg[blockIdx.y];
-  const int upr = (pg.W0 + 15) >> 4;                       // 16-pixel units per row
-  const long long u = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (u >= (long long)upr * pg.H0) return;
-  const int y = (int)(u / upr), x16 = (int)(u - (long long)y * upr) * 16;
+  // block = 64 units x 4 rows, grid = (units / 64, rows / 4, pages): no index division anywhere
+  const PostPage pg = b.pg[blockIdx.z];
+  const int y = blockIdx.y * 4 + threadIdx.y;
+  const int x16 = (blockIdx.x * 64 + threadIdx.x) * 16;
+  if (y >= pg.H0 || x16 >= pg.W0) return;
   const int P = b.P, L = P / 4;
   const int ty = y / P, yy = y - ty * P, tx = x16 / P, xx0 = x16 - tx * P;
   const float sc = (float)(L - 1) / (float)(P - 1);
@@ -824,7 +824,7 @@ int bdrc_seg_postprocess_lowres_batch(bdrc_ctx* ctx, const float* const* logits_
     memset(&b, 0, sizeof(b));
     b.P = patch;
     b.thr_logit = sigmoid_logit_threshold(thr);
-    long long max_units = 0;
+    int max_w = 0, max_h = 0;
     for (int k = 0; k < n; ++k) {
       const int i = p0 + k;
       BDRC_REQUIRE(ctx, logits_lowres[i] && masks[i] && nty[i] > 0 && ntx[i] > 0 && Hc[i] <= nty[i] * patch &&
@@ -832,12 +832,12 @@ int bdrc_seg_postprocess_lowres_batch(bdrc_ctx* ctx, const float* const* logits_
                    "seg_postprocess_lowres_batch: page %d: size %dx%d inconsistent with %dx%d tiles", i, Hc[i], Wc[i],
                    nty[i], ntx[i]);
       b.pg[k] = PostPage{logits_lowres[i], masks[i], ntx[i], Hc[i], Wc[i]};
-      const long long units = (long long)ceil_div(Wc[i], 16) * Hc[i];
-      if (units > max_units) max_units = units;
+      if (Wc[i] > max_w) max_w = Wc[i];
+      if (Hc[i] > max_h) max_h = Hc[i];
     }
-    dim3 grid((unsigned)((max_units + 255) / 256), (unsigned)n);
+    dim3 grid((unsigned)ceil_div(ceil_div(max_w, 16), 64), (unsigned)ceil_div(max_h, 4), (unsigned)n);
     bdrc_prof_begin(ctx, "a-3.seg_post", 0, s);
-    seg_post_line_lowres_batch_kernel<<<grid, 256, 0, s>>>(b);
+    seg_post_line_lowres_batch_kernel<<<grid, dim3(64, 4), 0, s>>>(b);
     bdrc_prof_end(ctx, s);
     BDRC_CHECK_LAUNCH(ctx);
   }

@@ -111,7 +111,7 @@ class Engine:
     def _upload(self, key: str, host: torch.Tensor) -> torch.Tensor:
         """Asynchronous H2D of a buffer obtained from _pinned(key, ...)."""
         dev = host.to(self.device, non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(blocking=True)          # host threads wait on it (_pinned): sleep, do not spin
         ev.record(torch.cuda.current_stream(self.device))
         self._pin[(key, threading.get_ident())][1] = ev
         return dev
@@ -140,10 +140,20 @@ class Engine:
         d = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
         if nbytes:
             d.copy_(slot[0][:nbytes].view(img.shape), non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(blocking=True)          # the upload thread waits on it before it refills the slot
         ev.record(torch.cuda.current_stream(self.device))
         slot[1] = ev
         return d, ev
+
+    def host_copy_many(self, src_ptrs: list, dst_ptrs: list, nbytes: list, threads: int = 4):
+        """Host memory -> host memory, n ranges, by a few native threads with the GIL released (bdrc_host_copy)."""
+        n = len(src_ptrs)
+        if n == 0:
+            return
+        sp = np.array(src_ptrs, dtype=np.uint64)
+        dp = np.array(dst_ptrs, dtype=np.uint64)
+        nb = np.array(nbytes, dtype=np.int64)
+        self._check(self.lib.bdrc_host_copy(sp.ctypes.data, dp.ctypes.data, nb.ctypes.data, n, threads), "host_copy")
 
     def simt_launch_count(self) -> int:
         return self.ctx.simt_launch_count()
@@ -551,3 +561,40 @@ class Engine:
         self._check(self.lib.bdrc_ctc_topk(self.ctx.h, logits.data_ptr(), L, V, T, layout, min_logp, tok.data_ptr(),
                                            lp.data_ptr(), cnt.data_ptr(), self.stream), "ctc_topk")
         return tok, lp, cnt
+
+    # ---- a-10, GPU half ------------------------------------------------------------------------
+    CENSUS_HDR_BYTES = 64
+
+    def mask_census(self, mask: torch.Tensor, slice_width: int = 20) -> torch.Tensor:
+        """Connected-component census of a line mask u8 [H, W] on the device (bdrc_mask_census) -> ONE u8 device
+        buffer [64 B header | 4 * max_centers B centres | H B row occupancy]; parse_census() reads its host copy."""
+        mask = mask.contiguous()
+        H, W = int(mask.shape[0]), int(mask.shape[1])
+        mc = int(self.lib.bdrc_census_max_centers())
+        out = torch.empty((self.CENSUS_HDR_BYTES + 4 * mc + H,), dtype=torch.uint8, device=self.device)
+        ws = self._workspace("census", int(self.lib.bdrc_mask_census_workspace_bytes(H, W, slice_width)))
+        base = out.data_ptr()
+        self._check(self.lib.bdrc_mask_census(self.ctx.h, mask.data_ptr(), H, W, slice_width,
+                                              base + self.CENSUS_HDR_BYTES + 4 * mc, base, base + self.CENSUS_HDR_BYTES,
+                                              ws.data_ptr(), ws.numel(), self.stream), "mask_census")
+        return out
+
+    def parse_census(self, buf: np.ndarray, H: int):
+        """Host copy of mask_census()'s buffer -> dict(bbox, x_steps, n, centers, row_any, overflow)."""
+        from .line_detection import parse_census
+
+        return parse_census(buf, H, int(self.lib.bdrc_census_max_centers()))
+
+    def mask_components(self, mask: torch.Tensor, max_comp: int = 4096):
+        """8-connected components of a mask on the device -> int array [n, 6] {x0, y0, x1, y1, area, root} (host)."""
+        mask = mask.contiguous()
+        H, W = int(mask.shape[0]), int(mask.shape[1])
+        n = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        stats = torch.empty((max_comp, 6), dtype=torch.int32, device=self.device)
+        ws = self._workspace("components", int(self.lib.bdrc_mask_components_workspace_bytes(H, W)))
+        self._check(self.lib.bdrc_mask_components(self.ctx.h, mask.data_ptr(), H, W, n.data_ptr(), stats.data_ptr(), max_comp,
+                                                  ws.data_ptr(), ws.numel(), self.stream), "mask_components")
+        k = int(n.item())
+        if k > max_comp:
+            raise _lib.BdrcError(f"mask_components: {k} components exceed max_comp = {max_comp}")
+        return stats[:k].cpu().numpy()

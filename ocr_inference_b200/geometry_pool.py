@@ -36,13 +36,13 @@ def _worker(tasks, results):
         job = tasks.get()
         if job is None:
             break
-        ticket, name, shape, merge_lines = job
+        ticket, name, shape, merge_lines, census = job
         try:
             shm = shms.get(name)
             if shm is None:
                 shm = shms[name] = shared_memory.SharedMemory(name=name)
             mask = np.ndarray(shape, dtype=np.uint8, buffer=shm.buf)
-            results.put(("done", ticket, page_geometry(mask, merge_lines)))
+            results.put(("done", ticket, page_geometry(mask, merge_lines, census=census)))
         except Exception:  # noqa: BLE001
             results.put(("error", ticket, traceback.format_exc()))
     for shm in shms.values():
@@ -107,7 +107,8 @@ class GeometryPool:
                     raise RuntimeError("GeometryPool: closed or a worker process died")
                 self._cv.wait(timeout=1.0)
 
-    def submit(self, mask: np.ndarray, merge_lines: bool = True) -> Future:
+    def submit(self, mask: np.ndarray, merge_lines: bool = True, census: dict | None = None) -> Future:
+        """`census` (optional): line_detection.parse_census() of the GPU's connected-component census of `mask`."""
         if self._closed or self._broken:
             raise RuntimeError("GeometryPool is closed or a worker process died")
         if mask.ndim != 2 or mask.dtype != np.uint8:
@@ -119,7 +120,7 @@ class GeometryPool:
             self._ticket += 1
             t = self._ticket
             self._pending[t] = (fut, slot)
-        self._tasks.put((t, slot.name, tuple(mask.shape), bool(merge_lines)))
+        self._tasks.put((t, slot.name, tuple(mask.shape), bool(merge_lines), census))
         return fut
 
     def _read(self):

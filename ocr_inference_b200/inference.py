@@ -131,21 +131,26 @@ class Detection:
         logits = self.engine.seg_forward(self._inference, tiles)
         return self.engine.seg_postprocess(logits, meta, self._mode, class_threshold)
 
-    def _predict_device_batch(self, pages_dev: Sequence[torch.Tensor], class_threshold: float) -> list[torch.Tensor]:
+    def _predict_device_batch(self, pages_dev: Sequence[torch.Tensor], class_threshold: float, census: bool = False):
         """Several device-resident pages through ONE forward call (tiles of all pages share the
-        batch dimension; per-tile reductions are per batch element, so this is exact)."""
+        batch dimension; per-tile reductions are per batch element, so this is exact).
+        census=True (single-channel masks only) also returns, per page, the device buffer of the mask's
+        connected-component census (Engine.mask_census: row occupancy + the slice census of get_line_threshold)."""
         eng = self.engine
         tiles, metas = eng.seg_preprocess_batch(list(pages_dev), self._patch_size)         # a-1, one launch
         need_full = any((m["Hc"], m["Wc"]) != (m["H0"], m["W0"]) for m in metas)
         logits = eng.seg_forward(self._inference, tiles, lowres=not need_full)             # a-2
         if not need_full:
-            return eng.seg_postprocess_lowres_batch(logits, metas, self._mode, class_threshold)   # a-3, one launch
-        outs, o = [], 0
-        for meta in metas:
-            n = meta["nty"] * meta["ntx"]
-            outs.append(eng.seg_postprocess(logits[o:o + n], meta, self._mode, class_threshold))
-            o += n
-        return outs
+            outs = eng.seg_postprocess_lowres_batch(logits, metas, self._mode, class_threshold)   # a-3, one launch
+        else:
+            outs, o = [], 0
+            for meta in metas:
+                n = meta["nty"] * meta["ntx"]
+                outs.append(eng.seg_postprocess(logits[o:o + n], meta, self._mode, class_threshold))
+                o += n
+        if not census:
+            return outs
+        return outs, [eng.mask_census(m) if m.dim() == 2 else None for m in outs]         # a-10, GPU half
 
     def predict(self, image: np.ndarray, class_threshold: float | None = None) -> np.ndarray:
         thr = self._default_threshold if class_threshold is None else class_threshold
@@ -155,70 +160,137 @@ class Detection:
         self._tls.ring_k = getattr(self._tls, "ring_k", 0) + 1
         page, _ = self.engine.upload_page(np.ascontiguousarray(image[..., :3], dtype=np.uint8), ring, self._tls.ring_k)
         self._tls.last = (image, page)
-        return self._predict_device(page, thr).cpu().numpy()
+        mask_dev = self._predict_device(page, thr)
+        if getattr(self, "with_census", False) and mask_dev.dim() == 2:
+            # the mask leaves with its connected-component census (computed on the GPU while the mask is still
+            # there); line_detection.build_raw_line_data / get_line_threshold pick it up from the array
+            from .line_detection import Mask3, parse_census
+
+            cen = self.engine.mask_census(mask_dev).cpu().numpy()
+            mask = mask_dev.cpu().numpy().view(Mask3)
+            mask.census = parse_census(cen, int(mask.shape[0]))
+            return mask
+        return mask_dev.cpu().numpy()
 
     def predict_batch(self, images: Sequence[np.ndarray], class_threshold: float | None = None,
                       pinned: Sequence[torch.Tensor] | None = None, copy: bool = True) -> list[np.ndarray]:
-        """Same result as [predict(i) for i in images]; uploads run ahead of compute on a copy
-        stream and masks come back through pinned buffers.  With copy=False the returned arrays
-        alias this object's pinned staging buffers and stay valid until the next predict_batch call
-        (the io-binding style of use); copy=True (default) hands out fresh arrays like the reference."""
+        """Same result as [predict(i) for i in images], as a three-stage pipeline: a helper thread moves the
+        (pageable) pages through a ring of pinned slots onto the copy-in stream, this thread launches one forward
+        per group of pages as soon as the group's uploads are queued, and a second helper thread hands the masks
+        out as their group's D2H copy completes.  With copy=False the returned arrays alias this object's pinned
+        staging buffers and stay valid until the next predict_batch call (the io-binding style of use);
+        copy=True (default) hands out fresh arrays like the reference."""
         thr = self._default_threshold if class_threshold is None else class_threshold
         eng = self.engine
         dev = eng.device
+        n = len(images)
+        if n == 0:
+            return []
         compute = torch.cuda.current_stream(dev)
         copy_in = getattr(self, "_copy_in", None) or torch.cuda.Stream(dev)
-        self._copy_in = copy_in
-        ups, evs = [], []
+        copy_out = getattr(self, "_copy_out", None) or torch.cuda.Stream(dev)
+        self._copy_in, self._copy_out = copy_in, copy_out
+        if not hasattr(self, "_host_bufs"):
+            self._host_bufs = {}
+        ups: list = [None] * n
+        evs: list = [None] * n
+        ready = [threading.Event() for _ in range(n)]
+        failed: list = []
         copy_in.wait_stream(compute)
-        with torch.cuda.stream(copy_in):
+
+        def uploader():
+            torch.cuda.set_device(dev)
             ring = getattr(self, "_up_slots", None)
             if ring is None:
                 ring = self._up_slots = [[None, None] for _ in range(4)]
-            for i, img in enumerate(images):
-                if pinned is not None:
-                    d = pinned[i].to(dev, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_in)
-                else:       # pageable page: through the pinned slot ring
-                    d, ev = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, i)
-                ups.append(d)
-                evs.append(ev)
-        outs = []
+            try:
+                with torch.cuda.stream(copy_in):
+                    for i, img in enumerate(images):
+                        if pinned is not None:
+                            ups[i] = pinned[i].to(dev, non_blocking=True)
+                            evs[i] = torch.cuda.Event()
+                            evs[i].record(copy_in)
+                        else:       # pageable page: through the pinned slot ring (native copy threads, GIL released)
+                            ups[i], evs[i] = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, i)
+                        ready[i].set()
+            except Exception as e:  # noqa: BLE001
+                failed.append(e)
+            finally:
+                for r in ready:
+                    r.set()
+
+        up_thread = threading.Thread(target=uploader, name="bdrc-upload", daemon=True)
+        up_thread.start()
         # pages per forward call: a small first group starts computing after two uploads, then groups of 6
         # landscape pages (144 tiles: one 148-tile chunk, ~whole waves per ResNet stage); later groups upload meanwhile
-        sizes, left = [], len(ups)
+        sizes, left = [], n
         while left > 0:
             sizes.append(min(left, 2 if not sizes else 6))
             left -= sizes[-1]
         starts = [sum(sizes[:i]) for i in range(len(sizes))]
-        copy_out = getattr(self, "_copy_out", None) or torch.cuda.Stream(dev)
-        self._copy_out = copy_out
-        if not hasattr(self, "_host_bufs"):
-            self._host_bufs = {}
-        for g0, group in zip(starts, sizes):
-            for d, ev in zip(ups[g0:g0 + group], evs[g0:g0 + group]):
-                compute.wait_event(ev)
-                d.record_stream(compute)
-            masks = self._predict_device_batch(ups[g0:g0 + group], thr)
-            done = torch.cuda.Event()
-            done.record(compute)
-            # masks go home on their own stream: a D2H copy queued on the compute stream would hold back the
-            # next group's kernels for its whole duration
-            copy_out.wait_event(done)
-            with torch.cuda.stream(copy_out):
-                for m in masks:
-                    key = ("mask_host", len(outs), tuple(m.shape))
-                    h = self._host_bufs.get(key)
-                    if h is None:
-                        h = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
-                        self._host_bufs[key] = h
-                    h.copy_(m, non_blocking=True)
-                    m.record_stream(copy_out)
-                    outs.append(h)
-        copy_out.synchronize()
+        outs: list = [None] * n
+        group_done: "list[tuple[int, int, torch.cuda.Event, list]]" = []
+        hand_out = threading.Semaphore(0)
+
+        def finisher():
+            # fresh, caller-owned arrays: one native multi-threaded copy per group out of the pinned staging buffers
+            for _ in sizes:
+                hand_out.acquire()
+                if failed:
+                    return
+                g0, group, ev, hosts = group_done.pop(0)
+                ev.synchronize()
+                if not copy:
+                    for k, h in enumerate(hosts):
+                        outs[g0 + k] = h.numpy()
+                    continue
+                fresh = [np.empty(tuple(h.shape), dtype=np.uint8) for h in hosts]
+                eng.host_copy_many([h.data_ptr() for h in hosts], [f.ctypes.data for f in fresh], [f.nbytes for f in fresh])
+                for k, f in enumerate(fresh):
+                    outs[g0 + k] = f
+
+        fin_thread = threading.Thread(target=finisher, name="bdrc-masks", daemon=True)
+        fin_thread.start()
+        try:
+            for g0, group in zip(starts, sizes):
+                for i in range(g0, g0 + group):
+                    if not ready[i].wait(timeout=300.0):
+                        raise TimeoutError("page upload did not finish")
+                    if failed:
+                        raise failed[0]
+                    compute.wait_event(evs[i])
+                    ups[i].record_stream(compute)
+                masks = self._predict_device_batch(ups[g0:g0 + group], thr)
+                done = torch.cuda.Event()
+                done.record(compute)
+                # masks go home on their own stream: a D2H copy queued on the compute stream would hold back the
+                # next group's kernels for its whole duration
+                copy_out.wait_event(done)
+                hosts = []
+                with torch.cuda.stream(copy_out):
+                    for k, m in enumerate(masks):
+                        key = ("mask_host", g0 + k, tuple(m.shape))
+                        h = self._host_bufs.get(key)
+                        if h is None:
+                            h = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
+                            self._host_bufs[key] = h
+                        h.copy_(m, non_blocking=True)
+                        m.record_stream(copy_out)
+                        hosts.append(h)
+                    ev = torch.cuda.Event(blocking=True)     # the hand-out thread sleeps on it
+                    ev.record(copy_out)
+                group_done.append((g0, group, ev, hosts))
+                hand_out.release()
+        except Exception as e:  # noqa: BLE001
+            failed.append(e)
+            for _ in sizes:
+                hand_out.release()
+        up_thread.join()
+        fin_thread.join()
         compute.synchronize()
-        return [o.numpy().copy() if copy else o.numpy() for o in outs]
+        if failed:
+            raise failed[0]
+        return outs
 
 
 class LineDetection(Detection):
@@ -388,6 +460,7 @@ class OCRPipeline:
         self._tls = threading.local()   # .fast: run_ocr keeps line crops on the device between stages 4 and 5
         if isinstance(self.line_config, LineDetectionConfig):
             self.line_inference = LineDetection(self.line_config, engine=self.engine)
+            self.line_inference.with_census = True      # masks travel with their GPU census (a-10, GPU half)
             self.ready = True
         elif isinstance(self.line_config, LayoutDetectionConfig):
             self.line_inference = LayoutDetection(self.line_config, engine=self.engine)
@@ -734,7 +807,7 @@ class OCRPipeline:
         up_thread.start()
 
         # ---- host geometry + line extraction of one page (worker threads) ------------------------
-        def page_stage(i: int, mask_host: np.ndarray, mask_ev: torch.cuda.Event):
+        def page_stage(i: int, mask_host: np.ndarray, mask_ev: torch.cuda.Event, census_host=None):
             if not hasattr(tls, "stream"):
                 torch.cuda.set_device(dev)
                 # high priority: the small extraction kernels of a page go ahead of the next conv launch of the
@@ -747,7 +820,15 @@ class OCRPipeline:
                     image = images[i]
                     line_mask = mask_host if layout_ch is None else mask_host[:, :, layout_ch]
                     det._tls.last = (image, pages_dev[i])
-                    geo = gpool.submit(line_mask, merge_lines).result() if gpool is not None else None
+                    census = None
+                    if census_host is not None:
+                        from .line_detection import Mask3, parse_census
+
+                        census = parse_census(census_host, int(line_mask.shape[0]))
+                        if gpool is None:
+                            line_mask = line_mask.view(Mask3)
+                            line_mask.census = census
+                    geo = gpool.submit(line_mask, merge_lines, census).result() if gpool is not None else None
                     if geo is not None and geo[0] == "failed":
                         return OpStatus.FAILED, geo[1]
                     if geo is not None and geo[0] == "ok":
@@ -817,21 +898,29 @@ class OCRPipeline:
                     if i not in up_ev:
                         raise RuntimeError("page upload failed")
                     compute.wait_event(up_ev[i])
-                masks = det._predict_device_batch([pages_dev[i] for i in idx], thr)
+                masks, cens = det._predict_device_batch([pages_dev[i] for i in idx], thr, census=layout_ch is None)
                 seg_done = torch.cuda.Event()
                 seg_done.record(compute)
                 copy_out.wait_event(seg_done)
                 with torch.cuda.stream(copy_out):
-                    for i, m in zip(idx, masks):
+                    for i, m, c in zip(idx, masks, cens):
                         key = ("mask_host", i, tuple(m.shape))
                         h = det._host_bufs.get(key)
                         if h is None:
                             h = det._host_bufs[key] = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
                         h.copy_(m, non_blocking=True)
                         m.record_stream(copy_out)
-                        ev = torch.cuda.Event()
+                        ch = None
+                        if c is not None:
+                            ckey = ("census_host", i, int(c.numel()))
+                            ch = det._host_bufs.get(ckey)
+                            if ch is None:
+                                ch = det._host_bufs[ckey] = torch.empty(c.shape, dtype=torch.uint8, pin_memory=True)
+                            ch.copy_(c, non_blocking=True)
+                            c.record_stream(copy_out)
+                        ev = torch.cuda.Event(blocking=True)     # host threads wait on it: sleep, do not spin
                         ev.record(copy_out)
-                        futures[i] = pool.submit(page_stage, i, h.numpy(), ev)
+                        futures[i] = pool.submit(page_stage, i, h.numpy(), ev, ch.numpy() if ch is not None else None)
             except Exception:  # noqa: BLE001
                 for i in idx:
                     futures.pop(i, None)

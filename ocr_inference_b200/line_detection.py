@@ -41,10 +41,11 @@ class RowCompaction:
     (tests/test_cpu_host_logic.py checks this against cv2 on the full mask).  `small` is None when compaction
     would not pay (most rows occupied)."""
 
-    def __init__(self, mask: np.ndarray, worth: float = 0.6):
+    def __init__(self, mask: np.ndarray, worth: float = 0.6, occ: np.ndarray | None = None):
+        """`occ` (optional): per-row "holds foreground" flags already computed on the GPU (bdrc_mask_census)."""
         self.small = self.ymap = None
         H = int(mask.shape[0])
-        occ = mask.max(axis=1) != 0
+        occ = (mask.max(axis=1) != 0) if occ is None or len(occ) != H else (np.asarray(occ) != 0)
         n_occ = int(np.count_nonzero(occ))
         self.empty = n_occ == 0
         if self.empty or H < 64:
@@ -147,16 +148,21 @@ class Mask3(np.ndarray):
 
     gray = None
     rows = None          # RowCompaction of `gray`
+    census = None        # parse_census() of the GPU's connected-component census of `gray` (or of this 2-D mask)
 
     def __array_finalize__(self, obj):
-        self.gray = self.rows = None
+        self.gray = self.rows = self.census = None
 
 
 def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold: float = 0.5):
     """:212-244 -> (rotated image, rotated 3-channel mask, contours with area > 10, angle)."""
+    census = getattr(line_mask, "census", None)         # a 2-D mask that came with its GPU census (Detection.predict)
+    if census is not None and census["overflow"]:
+        census = None
     if line_mask.ndim == 3:
-        line_mask = cv2.cvtColor(line_mask, cv2.COLOR_BGR2GRAY)
-    rows = RowCompaction(line_mask) if line_mask.ndim == 2 and line_mask.dtype == np.uint8 else None
+        line_mask, census = cv2.cvtColor(line_mask, cv2.COLOR_BGR2GRAY), None
+    rows = RowCompaction(line_mask, occ=census["row_any"] if census else None) \
+        if line_mask.ndim == 2 and line_mask.dtype == np.uint8 else None
     found = get_contours_compact(line_mask, rows)
     areas = [cv2.contourArea(c) for c in found]
     angle = get_rotation_angle_from_lines(line_mask, _contours=found, _areas=areas)
@@ -166,16 +172,17 @@ def build_raw_line_data(image: np.ndarray, line_mask: np.ndarray, rot_threshold:
         rows = RowCompaction(out_mask)
         found = get_contours_compact(out_mask, rows)
         areas = [cv2.contourArea(c) for c in found]
+        census = None        # belongs to the unrotated mask
     else:
         # unrotated: the reference runs the identical findContours call a second time (:238); reuse it
         out_mask, out_img = line_mask, image
     contours = [c for c, a in zip(found, areas) if a > 10]
     mask3 = cv2.cvtColor(out_mask, cv2.COLOR_GRAY2RGB).view(Mask3)
-    mask3.gray, mask3.rows = out_mask, rows
+    mask3.gray, mask3.rows, mask3.census = np.asarray(out_mask), rows, census
     return out_img, mask3, contours, angle
 
 
-def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold: float = 0.5):
+def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold: float = 0.5, census: dict | None = None):
     """Everything between the line mask and the GPU line extraction that needs no pixels of the page and no GPU
     (build_raw_line_data without rotation, filter_line_contours, build_line_data, sort_lines_by_threshold2 and
     the filled-contour ROI masks of extract_line_images), as ONE picklable call for a geometry worker process
@@ -184,7 +191,9 @@ def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold
       ("failed", message)              the reference's stage-2 failure messages (inference.py:521-528)
       ("ok", angle, lines, rois, masks, hs)   lines = [(guid, contour, (x, y, w, h), center)] in reading order
     """
-    rows = RowCompaction(line_mask)
+    if census is not None and census["overflow"]:
+        census = None
+    rows = RowCompaction(line_mask, occ=census["row_any"] if census else None)
     found = get_contours_compact(line_mask, rows)
     areas = [cv2.contourArea(c) for c in found]
     angle = get_rotation_angle_from_lines(line_mask, _contours=found, _areas=areas)
@@ -198,7 +207,7 @@ def page_geometry(line_mask: np.ndarray, merge_lines: bool = True, rot_threshold
         return ("failed", "No valid lines after filtering")
     line_data = [build_line_data(c, _guid=False) for c in filtered]
     linked = line_mask.view(Mask3)          # lets get_line_threshold reuse the row compaction
-    linked.gray, linked.rows = line_mask, rows
+    linked.gray, linked.rows, linked.census = line_mask, rows, census
     sorted_lines, _ = sort_lines_by_threshold2(linked, line_data, group_lines=merge_lines)
     for ln in sorted_lines:                 # single-chunk rows keep their chunk line: it gets its guid now
         if ln.guid is None:
@@ -233,8 +242,34 @@ def build_line_data(contour: np.ndarray, optimize: bool = True, _guid: bool = Tr
 # ------------------------------------------------------------------------------------------------
 
 
+def parse_census(buf: np.ndarray, H: int, max_centers: int = 4096) -> dict:
+    """The buffer Engine.mask_census() fills (bdrc_mask_census: connected-component census of the mask on the GPU),
+    as the host sees it.  No GPU needed: geometry worker processes call this."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    hdr = buf[:64].view(np.int32)
+    n_c = int(hdr[9])
+    return {"bbox": (int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3])), "x_steps": int(hdr[4]), "best": int(hdr[7]),
+            "n": int(hdr[8]), "centers": buf[64:64 + 4 * n_c].view(np.int32).copy(),
+            "row_any": buf[64 + 4 * max_centers:64 + 4 * max_centers + H].copy(), "overflow": bool(hdr[10]),
+            "slice_width": 20}
+
+
+def threshold_from_census(census: dict) -> float:
+    """get_line_threshold's result from the GPU census: the slices' contour counts and the fullest slice's
+    bounding-box centres were computed by connected-component labelling on the device (csrc/geometry.cu)."""
+    if census["x_steps"] == 0:
+        return 0.0
+    if census["n"] == 0 or len(census["centers"]) == 0:
+        print("number of contours is 0")
+        return 0.0
+    return float(np.median(census["centers"]) // census["n"])
+
+
 def get_line_threshold(line_prediction: np.ndarray, slice_width: int = 20) -> float:
     """:362-421: census of contours in vertical slices; median centre-y of the fullest slice // n."""
+    census = getattr(line_prediction, "census", None)
+    if census is not None and not census["overflow"] and census["slice_width"] == slice_width:
+        return threshold_from_census(census)
     gray = getattr(line_prediction, "gray", None)
     rows = None
     if gray is not None and gray.shape == line_prediction.shape[:2]:
