@@ -19,6 +19,9 @@ from .weights import write_blob
 SEG, OCR = 1, 2
 POST_SIGMOID, POST_SOFTMAX = 0, 1
 LAYOUT_TV, LAYOUT_VT = 0, 1
+# events that host threads wait on are created with cudaEventBlockingSync: the waiting thread sleeps instead of
+# spinning on a core (the page -> text path keeps ~10 such threads per GPU); BDRC_SPIN_EVENTS=1 restores spinning
+BLOCKING_EVENTS = os.environ.get("BDRC_SPIN_EVENTS", "0") != "1"
 OCR_CPAD = 128
 PATCH = 512
 
@@ -111,7 +114,7 @@ class Engine:
     def _upload(self, key: str, host: torch.Tensor) -> torch.Tensor:
         """Asynchronous H2D of a buffer obtained from _pinned(key, ...)."""
         dev = host.to(self.device, non_blocking=True)
-        ev = torch.cuda.Event(blocking=True)          # host threads wait on it (_pinned): sleep, do not spin
+        ev = torch.cuda.Event(blocking=BLOCKING_EVENTS)          # host threads wait on it (_pinned): sleep, do not spin
         ev.record(torch.cuda.current_stream(self.device))
         self._pin[(key, threading.get_ident())][1] = ev
         return dev
@@ -140,7 +143,7 @@ class Engine:
         d = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
         if nbytes:
             d.copy_(slot[0][:nbytes].view(img.shape), non_blocking=True)
-        ev = torch.cuda.Event(blocking=True)          # the upload thread waits on it before it refills the slot
+        ev = torch.cuda.Event(blocking=BLOCKING_EVENTS)          # the upload thread waits on it before it refills the slot
         ev.record(torch.cuda.current_stream(self.device))
         slot[1] = ev
         return d, ev

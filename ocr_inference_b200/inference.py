@@ -18,7 +18,7 @@ import torch
 
 from .data import (CharsetEncoder, DewarpingResult, Encoding, KenLMConfig, LayoutDetectionConfig,  # noqa: F401
                    Line, LineDetectionConfig, OCRLine, OCRModelConfig, OpStatus)
-from .engine import LAYOUT_TV, LAYOUT_VT, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
+from .engine import BLOCKING_EVENTS, LAYOUT_TV, LAYOUT_VT, OCR, POST_SIGMOID, POST_SOFTMAX, SEG, Engine
 from .weights import MAGIC, load_reference_checkpoint
 
 _ENGINES: dict[int, Engine] = {}
@@ -277,7 +277,7 @@ class Detection:
                         h.copy_(m, non_blocking=True)
                         m.record_stream(copy_out)
                         hosts.append(h)
-                    ev = torch.cuda.Event(blocking=True)     # the hand-out thread sleeps on it
+                    ev = torch.cuda.Event(blocking=BLOCKING_EVENTS)     # the hand-out thread sleeps on it
                     ev.record(copy_out)
                 group_done.append((g0, group, ev, hosts))
                 hand_out.release()
@@ -898,7 +898,9 @@ class OCRPipeline:
                     if i not in up_ev:
                         raise RuntimeError("page upload failed")
                     compute.wait_event(up_ev[i])
-                masks, cens = det._predict_device_batch([pages_dev[i] for i in idx], thr, census=layout_ch is None)
+                want_census = layout_ch is None and getattr(det, "with_census", False)
+                r_ = det._predict_device_batch([pages_dev[i] for i in idx], thr, census=want_census)
+                masks, cens = r_ if want_census else (r_, [None] * len(r_))
                 seg_done = torch.cuda.Event()
                 seg_done.record(compute)
                 copy_out.wait_event(seg_done)
@@ -918,7 +920,7 @@ class OCRPipeline:
                                 ch = det._host_bufs[ckey] = torch.empty(c.shape, dtype=torch.uint8, pin_memory=True)
                             ch.copy_(c, non_blocking=True)
                             c.record_stream(copy_out)
-                        ev = torch.cuda.Event(blocking=True)     # host threads wait on it: sleep, do not spin
+                        ev = torch.cuda.Event(blocking=BLOCKING_EVENTS)     # host threads wait on it: sleep, do not spin
                         ev.record(copy_out)
                         futures[i] = pool.submit(page_stage, i, h.numpy(), ev, ch.numpy() if ch is not None else None)
             except Exception:  # noqa: BLE001
