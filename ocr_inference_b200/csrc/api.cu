@@ -68,6 +68,18 @@ int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine) {
   return BDRC_OK;
 }
 
+// Host threads that wait for the GPU (stream / event synchronisation, blocking copies) either spin on a core
+// (the driver's default when there are more CPUs than contexts) or sleep until the device interrupts.  The
+// page -> text path keeps ~10 such threads per GPU (page stages, upload ring, mask hand-out): spinning burns the
+// host cores that the geometry needs and that an 8-GPU box does not have (4 per GPU).  Sets the scheduling flag
+// of the device's primary context, which torch shares.
+int bdrc_set_blocking_sync(bdrc_ctx* ctx, int on) {
+  if (!ctx) return BDRC_ERR_ARG;
+  BDRC_CUDA(ctx, cudaSetDevice(ctx->device));
+  BDRC_CUDA(ctx, cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+  return BDRC_OK;
+}
+
 int bdrc_profile_enable(bdrc_ctx* ctx, int on) {
   if (!ctx) return BDRC_ERR_ARG;
   ctx->profile = on != 0;
