@@ -496,7 +496,7 @@ size_t ocr_bytes_per_line(int Wt, int vocab) {
   auto add = [&](size_t elems, size_t sz) { b += align_up(elems * sz, 1024); };
   add(T2 * 128, 2);
   for (int i = 0; i < 5; ++i) add(T * 512, 2);
-  add(256, 4);
+  add((size_t)256 * (se_fused_chunks() + 1) + 32, 4);
   (void)vocab;
   return b + 8 * 1024;
 }
@@ -517,9 +517,10 @@ int ocr_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const bf16* lines, int L, int
   bf16* b2 = A.take<bf16>((size_t)L * T * 512);
   bf16* b3 = A.take<bf16>((size_t)L * T * 512);
   bf16* b4 = A.take<bf16>((size_t)L * T * 512);
-  float* gate = A.take<float>((size_t)L * 256);
+  float* gate = A.take<float>(se_fused_scratch_floats(L, 256));   // SE partial sums, gates, ticket counters
   if (!A.ok) return bdrc_fail(ctx, BDRC_ERR_ARG, "ocr_forward: workspace too small");
 
+  BDRC_TRY(se_fused_reset(ctx, gate, L, 256, s));
   // conv1 sees the image rows as channels; they were zero-padded to OCR_CPAD by the prep kernel,
   // the packed weights' Cin_pad covers it (extra K columns are zero)
   ConvWeights w1 = m->conv["conv1"];
@@ -550,11 +551,8 @@ int ocr_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const bf16* lines, int L, int
     BDRC_TRY(conv_launch(ctx, "ocr.convk", m->conv[p + ".conv_c"], mk1d(db, L, T, 256, ks[u], 1, 1, da, 256, 0), s));
     const FcWeights& f1 = m->fc[p + ".se_fc1"];
     const FcWeights& f2 = m->fc[p + ".se_fc2"];
-    bdrc_prof_begin(ctx, "ocr.se_gate", 0, s);
-    BDRC_TRY(se_gate_launch(ctx, da, L, T, 256, f1.w, f1.b, 32, f2.w, f2.b, gate, s));
-    bdrc_prof_end(ctx, s);
-    bdrc_prof_begin(ctx, "ocr.se_apply", 0, s);
-    BDRC_TRY(se_apply_launch(ctx, P, 512, da, gate, L, T, 256, P + 256, 512, s));
+    bdrc_prof_begin(ctx, "ocr.se", 0, s);
+    BDRC_TRY(se_fused_launch(ctx, P, 512, da, L, T, 256, f1.w, f1.b, 32, f2.w, f2.b, P + 256, 512, gate, s));
     bdrc_prof_end(ctx, s);
     prev = P; prev_ld = 512; data_off = 256; cin = 256;
   }

@@ -572,73 +572,130 @@ aspp_pool_bias_kernel(const bf16* __restrict__ x, int HW, int Cin, const float* 
   }
 }
 
-// one CTA per line: column mean over T, FC -> ReLU -> FC -> sigmoid
+// Squeeze-excite as two short, fully parallel launches:
+//   se_partial_gate_kernel : L * SE_CH CTAs; CTA (l, q) sums chunk q of line l's d column-wise (fixed order) into
+//                            partial[l][q][C]; the LAST CTA of a line to finish (a ticket counter) adds the SE_CH
+//                            partials in chunk order -- bit-reproducible whichever CTA it is -- and evaluates the
+//                            gate MLP once per line, weights staged in shared memory with every load in flight;
+//   se_apply_kernel        : data = relu(res + d * gate), elementwise, d from L2 where the conv just left it.
+// History (B200, 64 lines, per unit): one-CTA-per-line gate kernel + apply 21 + 16 us; a thread-block-cluster
+// version with the partial sums in distributed shared memory 37-54 us (clusters of 4-8 CTAs with a 32-64 KB slab
+// schedule in too few waves); per-chunk CTAs that each evaluate the MLP 50 us (19 M warp instructions, every CTA
+// pays the weight fetch latency); this version: see profiles/README.md.
+constexpr int SE_CH = 8;
 __global__ void __launch_bounds__(256)
-se_gate_kernel(const bf16* __restrict__ d, int T, int C, const float* __restrict__ W1,
-               const float* __restrict__ b1, int Cmid, const float* __restrict__ W2,
-               const float* __restrict__ b2, float* __restrict__ gate) {
-  extern __shared__ float se_smem[];
-  float* m = se_smem;        // [C]
-  float* z = se_smem + C;    // [Cmid]
-  float* part = z + Cmid;    // [slices][C] partial sums
-  const int l = blockIdx.x;
+se_partial_gate_kernel(const bf16* __restrict__ d, int T, int C, float* __restrict__ partial, int* __restrict__ tickets,
+                       const float* __restrict__ W1, const float* __restrict__ b1, int Cmid, const float* __restrict__ W2,
+                       const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float se_sm[];                 // [slices][C] partial sums, later the MLP's staging
+  __shared__ int last;
+  const int q = blockIdx.x % SE_CH, l = blockIdx.x / SE_CH;
+  const int Tq = (T + SE_CH - 1) / SE_CH;
+  const int t0 = q * Tq, t1 = min(T, t0 + Tq);
   const bf16* db = d + (size_t)l * T * C;
-  {
-    const int C8 = C / 8;
-    const int slices = blockDim.x / C8 > 0 ? blockDim.x / C8 : 1;
-    const int cg = threadIdx.x % C8, ps = threadIdx.x / C8;
-    if (ps < slices) {
-      float acc[8];
+  const int C8 = C / 8;
+  const int slices = blockDim.x / C8 > 0 ? blockDim.x / C8 : 1;
+  const int cg = threadIdx.x % C8, ps = threadIdx.x / C8;
+  if (ps < slices) {
+    float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int t = ps; t < T; t += slices) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(db + (size_t)t * C + cg * 8)), f);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t = t0 + ps; t < t1; t += 4 * slices) {      // four rows in flight per thread, summed in time order
+      uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + u * slices;
+        v[u] = tt < t1 ? __ldg(reinterpret_cast<const uint4*>(db + (size_t)tt * C + cg * 8)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) part[(size_t)ps * C + cg * 8 + j] = acc[j];
+      for (int u = 0; u < 4; ++u) {
+        if (t + u * slices < t1) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
-      for (int q = 0; q < slices; ++q) s += part[(size_t)q * C + c];
-      m[c] = s / (float)T;
-    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) se_sm[(size_t)ps * C + cg * 8 + j] = acc[j];
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sum = 0.f;
+    for (int k = 0; k < slices; ++k) sum += se_sm[(size_t)k * C + c];
+    partial[((size_t)l * SE_CH + q) * C + c] = sum;
+  }
+  __threadfence();                                  // this CTA's partial is visible before its ticket is drawn
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&tickets[l], 1) == SE_CH - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // ---- the line's gate, once: mean -> FC -> ReLU -> FC -> sigmoid ----
+  float* m = se_sm;                              // [C]
+  float* z = m + C;                              // [Cmid]
+  float* w1s = z + Cmid;                         // [Cmid][C]
+  float* w2s = w1s + (size_t)Cmid * C;           // [C][Cmid + 1]  (padded: a thread per row reads conflict-free)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < SE_CH; ++k) sum += __ldcg(partial + ((size_t)l * SE_CH + k) * C + c);
+    m[c] = sum / (float)T;
+  }
+  for (int i = threadIdx.x; i < Cmid * C / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(W1) + i);
+  for (int i = threadIdx.x; i < C * Cmid; i += blockDim.x) w2s[(i / Cmid) * (Cmid + 1) + i % Cmid] = __ldg(W2 + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int o = warp; o < Cmid; o += nw) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(W1[(size_t)o * C + c], m[c], s);
-    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-    if (lane == 0) z[o] = fmaxf(s + b1[o], 0.f);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum = fmaf(w1s[(size_t)o * C + c], m[c], sum);
+    for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+    if (lane == 0) z[o] = fmaxf(sum + b1[o], 0.f);
   }
   __syncthreads();
   for (int o = threadIdx.x; o < C; o += blockDim.x) {
-    float s = b2[o];
-    for (int c = 0; c < Cmid; ++c) s = fmaf(W2[(size_t)o * Cmid + c], z[c], s);
-    gate[(size_t)l * C + o] = 1.f / (1.f + expf(-s));
+    float sum = b2[o];
+    for (int c = 0; c < Cmid; ++c) sum = fmaf(w2s[(size_t)o * (Cmid + 1) + c], z[c], sum);
+    gate[(size_t)l * C + o] = 1.f / (1.f + expf(-sum));
   }
+  if (threadIdx.x == 0) tickets[l] = 0;            // ready for the next unit / call
 }
 
-__global__ void se_apply_kernel(const bf16* __restrict__ res, int res_ld, const bf16* __restrict__ d,
-                                const float* __restrict__ gate, int T, int C, size_t total8,
-                                bf16* __restrict__ out, int out_ld) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total8) return;
+__global__ void __launch_bounds__(256)
+se_apply_kernel(const bf16* __restrict__ res, int res_ld, const bf16* __restrict__ d, const float* __restrict__ gate, int T,
+                int C, size_t total8, bf16* __restrict__ out, int out_ld) {
   const int C8 = C / 8;
-  const int c8 = (int)(idx % C8);
-  const size_t row = idx / C8;          // l*T + t
-  const int l = (int)(row / T);
-  float r[8], dv[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * res_ld + c8 * 8)), r);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(d) + idx), dv);
-  const float* gp = gate + (size_t)l * C + c8 * 8;
+  // two 16-byte items per thread, both loads in flight before either is used
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  uint4 rv[2], dv4[2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(dv[j], gp[j], r[j]), 0.f);
-  *reinterpret_cast<uint4*>(out + row * out_ld + c8 * 8) = pack8(o);
+  for (int u = 0; u < 2; ++u) {
+    const size_t idx = i0 + u;
+    if (idx < total8) {
+      const size_t row = idx / C8;
+      rv[u] = __ldg(reinterpret_cast<const uint4*>(res + row * res_ld + (idx - row * C8) * 8));
+      dv4[u] = __ldg(reinterpret_cast<const uint4*>(d) + idx);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const size_t idx = i0 + u;
+    if (idx < total8) {
+      const size_t row = idx / C8;          // l * T + t
+      const int c8 = (int)(idx - row * C8), l = (int)(row / T);
+      float r[8], dv[8], o[8];
+      unpack8(rv[u], r);
+      unpack8(dv4[u], dv);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)l * C + c8 * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)l * C + c8 * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(dv[j], g[j], r[j]), 0.f);
+      *reinterpret_cast<uint4*>(out + row * out_ld + c8 * 8) = pack8(o);
+    }
+  }
 }
 
 }  // namespace
@@ -755,19 +812,41 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
   return 0;
 }
 
-int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
-                   const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
-                   cudaStream_t s) {
-  se_gate_kernel<<<L, 256, (size_t)(C + Cmid + (256 / (C / 8)) * C) * sizeof(float), s>>>(d, T, C, W1, b1, Cmid, W2, b2, gate);
+int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, int L, int T, int C, const float* W1,
+                    const float* b1, int Cmid, const float* W2, const float* b2, bf16* out, int out_ld, float* scratch,
+                    cudaStream_t s) {
+  BDRC_REQUIRE(ctx, C % 8 == 0 && C / 8 <= 256 && res_ld % 8 == 0 && out_ld % 8 == 0 && Cmid >= 1 && scratch &&
+                        (Cmid * C) % 4 == 0,
+               "se_fused: C, res_ld, out_ld must be multiples of 8");
+  // scratch (fp32 words, se_fused_scratch_floats(L, C)): [L][SE_CH][C] partial sums | [L][C] gate | [L] tickets (zeroed
+  // once per forward by the caller with se_fused_reset)
+  float* partial = scratch;
+  float* gate = partial + (size_t)L * SE_CH * C;
+  int* tickets = reinterpret_cast<int*>(gate + (size_t)L * C);
+  const int slices = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  size_t smem = (size_t)slices * C * sizeof(float);
+  const size_t mlp = (size_t)(C + Cmid + Cmid * C + C * (Cmid + 1)) * sizeof(float);
+  if (mlp > smem) smem = mlp;
+  BDRC_REQUIRE(ctx, smem <= 200 * 1024, "se_fused: gate MLP too large for shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    BDRC_CUDA(ctx, cudaFuncSetAttribute(se_partial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  se_partial_gate_kernel<<<L * SE_CH, 256, smem, s>>>(d, T, C, partial, tickets, W1, b1, Cmid, W2, b2, gate);
+  BDRC_CHECK_LAUNCH(ctx);
+  const size_t total8 = (size_t)L * T * (C / 8);
+  se_apply_kernel<<<(unsigned)((total8 + 511) / 512), 256, 0, s>>>(res, res_ld, d, gate, T, C, total8, out, out_ld);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
 
-int se_apply_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, const float* gate, int L, int T,
-                    int C, bf16* out, int out_ld, cudaStream_t s) {
-  BDRC_REQUIRE(ctx, C % 8 == 0 && res_ld % 8 == 0 && out_ld % 8 == 0, "se_apply: C, res_ld, out_ld must be multiples of 8");
-  const size_t total8 = (size_t)L * T * (C / 8);
-  se_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(res, res_ld, d, gate, T, C, total8, out, out_ld);
-  BDRC_CHECK_LAUNCH(ctx);
+size_t se_fused_scratch_floats(int L, int C) { return (size_t)L * SE_CH * C + (size_t)L * C + (size_t)L + 16; }
+
+int se_fused_reset(bdrc_ctx* ctx, float* scratch, int L, int C, cudaStream_t s) {
+  BDRC_CUDA(ctx, cudaMemsetAsync(scratch + (size_t)L * SE_CH * C + (size_t)L * C, 0, (size_t)L * sizeof(int), s));
   return 0;
 }
+
+int se_fused_chunks(void) { return SE_CH; }
+

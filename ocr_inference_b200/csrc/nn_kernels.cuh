@@ -34,14 +34,17 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
                           int Cout, int Cout_pad, float* bias_eff, const float* mean_in, cudaStream_t s);
 // mean_in (optional): precomputed g [N][Cin] (aspp_dw3_launch produces it while the map is in shared memory)
 
-// Easter2 squeeze-excite over time: gate = sigmoid(W2 relu(W1 mean_T(d) + b1) + b2)
-int se_gate_launch(bdrc_ctx* ctx, const bf16* d, int L, int T, int C, const float* W1,
-                   const float* b1, int Cmid, const float* W2, const float* b2, float* gate,
-                   cudaStream_t s);
-// data = relu(res + d * gate); res rows have stride res_ld, out rows stride out_ld (channel slices of wider buffers)
-int se_apply_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, const float* gate, int L, int T,
-                    int C, bf16* out, int out_ld, cudaStream_t s);
-
+// Easter2 squeeze-excite over time: data = relu(res + d * sigmoid(W2 relu(W1 mean_T(d) + b1) + b2));
+// res rows have stride res_ld, out rows stride out_ld (channel slices of wider buffers).
+// two short parallel launches (nn_kernels.cu: per-chunk column sums + the gate by the line's last CTA, then the
+// elementwise apply).  scratch: se_fused_scratch_floats(L, C) fp32 words of the caller's workspace whose ticket
+// counters se_fused_reset zeroes once per forward.
+int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, int L, int T, int C, const float* W1,
+                    const float* b1, int Cmid, const float* W2, const float* b2, bf16* out, int out_ld, float* scratch,
+                    cudaStream_t s);
+size_t se_fused_scratch_floats(int L, int C);
+int se_fused_reset(bdrc_ctx* ctx, float* scratch, int L, int C, cudaStream_t s);
+int se_fused_chunks(void);
 // Stem + max-pool fused on the tensor cores (stem_tc.cu): u8 tiles [N][512][512] (3 identical channels
 // folded) -> bf16 NHWC [N][128][128][64].  w_bf16: [64 cout][64 k] with k = 8 * kernel_row + kernel_col.
 int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* w_bf16, const float* bias, bf16* out,
