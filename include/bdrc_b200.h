@@ -61,6 +61,9 @@ uint64_t bdrc_simt_launch_count(bdrc_ctx* ctx);
 uint64_t bdrc_conv_plans_built(bdrc_ctx* ctx);
 /* conv engine: 0 = tcgen05/TMEM implicit GEMM (product path), 1 = SIMT (debug cross-check) */
 int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine);
+/* decoder tail of the segmentation network: 1 = one fused kernel (default), 0 = the three-kernel form (cross-check in
+ * tests; BDRC_NO_DEC_TAIL=1 selects it at context creation) */
+int bdrc_set_dec_tail(bdrc_ctx* ctx, int fused);
 /* host threads waiting for this device sleep (on = 1, cudaDeviceScheduleBlockingSync) or spin (0, the driver's
  * default); applies to the device's primary context, i.e. to every runtime user in the process */
 int bdrc_set_blocking_sync(bdrc_ctx* ctx, int on);

@@ -168,7 +168,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
       }
 
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);
+      mbar_wait_relaxed(smem_u32(&tfull_bar[acc]), acc_phase, p.errflag, 4);   // sleeps between polls: the other group's epilogue warps need the issue slots
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)(acc * G * p.BN);
 #pragma unroll
@@ -376,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const int par_w = ((tw % p.stride_w) + p.stride_w) % p.stride_w;
             const int off_w = floordiv(tw - par_w, p.stride_w);
             for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.errflag, 1);
+              mbar_wait_relaxed(smem_u32(&empty_bar[stage]), phase ^ 1, p.errflag, 1);
               const uint32_t fb = full0 + (uint32_t)stage * 8u;
               const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
               if (CTAS == 2) {
@@ -568,7 +568,7 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const bool carry = (st > st_begin) && (y0 != 0);
       for (int q = carry ? 2 : 0; q < 6; ++q) {
         const uint32_t slot = L % SLOTS, use = L / SLOTS;
-        mbar_wait(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
+        mbar_wait_relaxed(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
         if (elect_one()) {
           const uint32_t fb = full0 + slot * 8u;
           mbar_arrive_expect_tx(fb, SLAB_ROW_TX);

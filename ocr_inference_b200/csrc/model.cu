@@ -72,6 +72,8 @@ struct bdrc_model {
   float* pool_w = nullptr;        // [256][512]
   float* pool_b = nullptr;
   float* proj_b = nullptr;
+  float* head_wf = nullptr;       // [C][256] fp32 holding the bf16-rounded head weights (fused decoder tail)
+  float* head_bf = nullptr;       // [C]
   int ocr_in_h = 0;
 };
 
@@ -212,6 +214,15 @@ int load_seg(Loader& L, int n_classes) {
   BDRC_TRY(L.depthwise("decoder.block2.0.0", 304));
   BDRC_TRY(L.conv("decoder.block2.0.1", 256, 304, 1, 1));
   BDRC_TRY(L.conv("segmentation_head.0", n_classes, 256, 1, 1));
+  {
+    const BlobTensor* hw = L.get("segmentation_head.0.weight", {n_classes, 256, 1, 1});
+    const BlobTensor* hb = L.get("segmentation_head.0.bias", {n_classes});
+    if (!hw || !hb) return BDRC_ERR_WEIGHTS;
+    std::vector<float> wf(hw->numel);
+    for (size_t i = 0; i < hw->numel; ++i) wf[i] = __bfloat162float(__float2bfloat16(hw->data[i]));   // as conv_pack_weights stores them
+    BDRC_TRY(dev_copy(ctx, m, wf, &m->head_wf));
+    BDRC_TRY(dev_copy(ctx, m, std::vector<float>(hb->data, hb->data + n_classes), &m->head_bf));
+  }
   return 0;
 }
 
@@ -432,15 +443,19 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
   bdrc_prof_end(ctx, s);
   BDRC_TRY(conv_launch(ctx, "dec.skip1x1", m->conv["decoder.block1.0"],
                        mk(skip, n, 128, 128, 64, 0, 1, 1, 1, dcat, 304, 256, 1), s));
-  bdrc_prof_begin(ctx, "dec.dw3x3", 2.0 * n * 128 * 128 * 304 * 9, s);
-  BDRC_TRY(depthwise3x3_launch(ctx, dcat, 304, 0, n, 128, 128, 304, 1, m->dw["decoder.block2.0.0"].w9c, d2dw, 304, 0, s));
-  bdrc_prof_end(ctx, s);
-  // 1x1 304 -> 256 + ReLU, then the head 1x1 256 -> C (ipynb:L455-L466); fp32 NHWC low-res logits.
-  // (A SIMT per-pixel dot product for the head inside the first conv's epilogue was built in round 1 and
-  // measured slower, 0.322 ms against 0.184 + 0.083 ms per 48 tiles: the layer is epilogue-bound.  Removed.)
-  BDRC_TRY(conv_launch(ctx, "dec.1x1", m->conv["decoder.block2.0.1"],
-                       mk(d2dw, n, 128, 128, 304, 0, 1, 1, 1, d2pw, 256, 0, 1), s));
-  {
+  // depthwise 3x3 (304) -> 1x1 304 -> 256 + ReLU -> head 1x1 256 -> C (ipynb:L455-L466); fp32 NHWC low-res logits.
+  if (ctx->conv_engine == 0 && !ctx->no_dec_tail && dec_tail_supported(304, 256, C, 128, 128)) {
+    // one kernel: the 304- and 256-channel activations of this resolution never reach HBM (dec_tail.cu)
+    bdrc_prof_begin(ctx, "dec.tail dw3x3+1x1+head", 2.0 * n * 128 * 128 * (304.0 * 9 + 256.0 * 304 + (double)C * 256), s);
+    BDRC_TRY(dec_tail_launch(ctx, dcat, n, 128, 128, 304, m->dw["decoder.block2.0.0"].w9c, m->conv["decoder.block2.0.1"],
+                             m->head_wf, m->head_bf, C, low, s));
+    bdrc_prof_end(ctx, s);
+  } else {
+    bdrc_prof_begin(ctx, "dec.dw3x3", 2.0 * n * 128 * 128 * 304 * 9, s);
+    BDRC_TRY(depthwise3x3_launch(ctx, dcat, 304, 0, n, 128, 128, 304, 1, m->dw["decoder.block2.0.0"].w9c, d2dw, 304, 0, s));
+    bdrc_prof_end(ctx, s);
+    BDRC_TRY(conv_launch(ctx, "dec.1x1", m->conv["decoder.block2.0.1"],
+                         mk(d2dw, n, 128, 128, 304, 0, 1, 1, 1, d2pw, 256, 0, 1), s));
     ConvArgs a = mk(d2pw, n, 128, 128, 256, 0, 1, 1, 1, low, low_ld, 0, 0);
     a.out_fp32 = 1;
     BDRC_TRY(conv_launch(ctx, "head1x1", m->conv["segmentation_head.0"], a, s));

@@ -54,3 +54,10 @@ int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* 
 // rate rates[i], weights w9c[i] fp32 [9][C].
 int aspp_dw3_launch(bdrc_ctx* ctx, const bf16* x, int N, int C, const int rates[3], const float* const w9c[3],
                     bf16* const out[3], float* mean_out, cudaStream_t s);
+
+// Decoder tail in one kernel (dec_tail.cu): depthwise 3x3 (C channels, pad 1) -> 1x1 conv C -> 256 + bias + ReLU -> head
+// 1x1 256 -> head_C + bias.  x: bf16 NHWC [N][H][W][C]; pw: the packed 1x1 weights; head_w_f32: [head_C][256] fp32 holding
+// the bf16-rounded head weights; out: fp32 NHWC [N][H][W][head_C].
+int dec_tail_supported(int C, int Cout, int head_C, int H, int W);
+int dec_tail_launch(bdrc_ctx* ctx, const bf16* x, int N, int H, int W, int C, const float* dw_w9c, const ConvWeights& pw,
+                    const float* head_w_f32, const float* head_b, int head_C, float* out, cudaStream_t s);

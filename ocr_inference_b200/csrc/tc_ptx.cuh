@@ -42,6 +42,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// The same bounded wait for warps that share their SM with SIMT-heavy warps (dec_tail.cu): a failed poll sleeps a few
+// tens of nanoseconds instead of re-polling at once.  Measured with ncu on the fused decoder tail: the tight loops of
+// the eight waiting warps issued HALF of all instructions of the kernel (118 M polls x ~10 instructions) and took the
+// issue slots the depthwise warps needed.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* errflag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  for (;;) {
+    __nanosleep(40);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((++spins & 0x3fff) == 0) {
+      if (clock64() - t0 > 4000000000LL) {
+        if (errflag) atomicExch(errflag, code);
+        __threadfence_system();
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
   asm volatile(

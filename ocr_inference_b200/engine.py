@@ -158,6 +158,10 @@ class Engine:
         nb = np.array(nbytes, dtype=np.int64)
         self._check(self.lib.bdrc_host_copy(sp.ctypes.data, dp.ctypes.data, nb.ctypes.data, n, threads), "host_copy")
 
+    def set_dec_tail(self, fused: bool = True):
+        """Decoder tail of the segmentation network as one fused kernel (default) or three (cross-check)."""
+        self._check(self.lib.bdrc_set_dec_tail(self.ctx.h, int(bool(fused))), "set_dec_tail")
+
     def set_blocking_sync(self, on: bool = True):
         """Host threads waiting for this GPU sleep instead of spinning (see bdrc_set_blocking_sync)."""
         self._check(self.lib.bdrc_set_blocking_sync(self.ctx.h, int(bool(on))), "set_blocking_sync")

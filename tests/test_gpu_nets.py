@@ -177,3 +177,29 @@ def test_modern_layout_run_writes_json(engine, tmp_path):
     mref = ho.torch_path_post(ref_logits, meta, 0.3)
     assert masks.shape == mref.shape == (5, 600, 800)
     assert (masks != mref).mean() < 0.02      # bf16 logits: only pixels near the 0.3 probability level differ
+
+
+@pytest.mark.parametrize("n_classes,n_tiles", [(1, 7), (5, 3)])
+def test_fused_decoder_tail_equals_the_three_kernel_form(engine, n_classes, n_tiles):
+    """dec_tail.cu (depthwise 3x3 -> 1x1 304 -> 256 + ReLU -> head in one kernel) against the three kernels it
+    replaces: the depthwise taps accumulate in the same order and both forms round to bf16 at the same two places, so
+    the only difference is the fp32 summation order of the head's 256-term dot product."""
+    from ocr_inference_b200.synthetic_weights import seg_weights
+
+    model = engine.load_model(1, seg_weights(11 + n_classes, n_classes, 3), n_classes)
+    x = (torch.rand((n_tiles, 512, 512), device="cuda", generator=torch.Generator("cuda").manual_seed(5)) > 0.25).to(torch.uint8)
+    try:
+        engine.set_dec_tail(False)
+        ref = engine.seg_forward(model, x, lowres=True).clone()
+        engine.set_dec_tail(True)
+        got = engine.seg_forward(model, x, lowres=True).clone()
+        again = engine.seg_forward(model, x, lowres=True)
+    finally:
+        engine.set_dec_tail(True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, again)                          # deterministic
+    scale = float(ref.std())
+    err = float((got - ref).abs().max())
+    print(f"fused vs three-kernel decoder tail: max |diff| {err:.3e} at logit std {scale:.3f}")
+    assert err <= 2e-4 * max(1.0, scale) + 1e-4 * float(ref.abs().max())
+    assert float(ref.abs().max()) > 0.1
