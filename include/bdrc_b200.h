@@ -64,6 +64,9 @@ int bdrc_set_conv_engine(bdrc_ctx* ctx, int engine);
 /* decoder tail of the segmentation network: 1 = one fused kernel (default), 0 = the three-kernel form (cross-check in
  * tests; BDRC_NO_DEC_TAIL=1 selects it at context creation) */
 int bdrc_set_dec_tail(bdrc_ctx* ctx, int fused);
+/* 64 -> 64 channel 3x3 layers on 128-pixel-wide maps (ResNet layer 1): 1 = the wide-N kernel (three horizontal taps
+ * in the N dimension, default), 0 = the slab kernel (cross-check in tests; BDRC_NO_WIDE_CONV=1 at context creation) */
+int bdrc_set_wide_conv(bdrc_ctx* ctx, int on);
 /* host threads waiting for this device sleep (on = 1, cudaDeviceScheduleBlockingSync) or spin (0, the driver's
  * default); applies to the device's primary context, i.e. to every runtime user in the process */
 int bdrc_set_blocking_sync(bdrc_ctx* ctx, int on);

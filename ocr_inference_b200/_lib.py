@@ -26,6 +26,7 @@ _SIGS = {
     "bdrc_simt_launch_count": (c_u64, [c_void_p]),
     "bdrc_set_blocking_sync": (c_int, [c_void_p, c_int]),
     "bdrc_set_dec_tail": (c_int, [c_void_p, c_int]),
+    "bdrc_set_wide_conv": (c_int, [c_void_p, c_int]),
     "bdrc_conv_plans_built": (c_u64, [c_void_p]),
     "bdrc_set_conv_engine": (c_int, [c_void_p, c_int]),
     "bdrc_profile_enable": (c_int, [c_void_p, c_int]),

@@ -22,6 +22,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--use_fast_math" if False else "-DBDRC_NO_FAST_MATH",  # exact expf/rounding needed for parity
     "-I", os.path.join(HERE, "..", "include"),
+    *os.environ.get("BDRC_NVCC_EXTRA", "").split(),   # e.g. -DBDRC_EXPERIMENTS for the timing experiments of conv_tc.cu
 ]
 
 

@@ -43,6 +43,7 @@ int bdrc_create(int device, bdrc_ctx** out) {
   cudaMemset(ctx->d_errflag, 0, sizeof(int));
   if (const char* e = getenv("BDRC_ALLOW_SIMT")) ctx->allow_simt = e[0] == '1';
   if (const char* e = getenv("BDRC_NO_DEC_TAIL")) ctx->no_dec_tail = e[0] == '1';
+  if (const char* e = getenv("BDRC_NO_WIDE_CONV")) ctx->no_wide_conv = e[0] == '1';
   *out = ctx;
   return BDRC_OK;
 }
@@ -84,6 +85,12 @@ int bdrc_set_blocking_sync(bdrc_ctx* ctx, int on) {
 int bdrc_set_dec_tail(bdrc_ctx* ctx, int fused) {
   if (!ctx) return BDRC_ERR_ARG;
   ctx->no_dec_tail = !fused;
+  return BDRC_OK;
+}
+
+int bdrc_set_wide_conv(bdrc_ctx* ctx, int on) {
+  if (!ctx) return BDRC_ERR_ARG;
+  ctx->no_wide_conv = !on;
   return BDRC_OK;
 }
 

@@ -26,6 +26,7 @@ struct bdrc_ctx {
   uint64_t launches = 0;                   // kernels launched through this ctx
   int conv_engine = 0;                     // 0 = tcgen05 implicit GEMM, 1 = SIMT (debug cross-check, explicit)
   bool no_dec_tail = false;                // BDRC_NO_DEC_TAIL=1: run the decoder tail as three kernels (cross-check)
+  bool no_wide_conv = false;               // BDRC_NO_WIDE_CONV=1: 64-channel 3x3 layers on the slab kernel (cross-check)
   bool allow_simt = false;                 // BDRC_ALLOW_SIMT=1: shapes the tcgen05 engine cannot tile may run SIMT
   uint64_t simt_launches = 0;              // convolutions that ran on the SIMT engine (bdrc_simt_launch_count)
   uint64_t tc_plans_built = 0;             // tensor-map / tiling plans built (cache misses of conv_tc_launch)

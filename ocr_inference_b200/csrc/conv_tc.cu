@@ -51,7 +51,8 @@ struct TcParams {
   int out_ld, out_coff, out_fp32, relu, out_tma;
   int* errflag;
   int dbg_skip;   // -DBDRC_EXPERIMENTS builds only -- bit 0: skip A loads, 1: skip B loads, 2: skip epilogue math + I/O,
-                  // 3: skip the TMA stores, 4: skip the residual loads
+                  // 3: skip the TMA stores, 4: skip the residual loads; wide kernel -- 5 (32): skip the epilogue,
+                  // 6 (64): skip the MMAs, 7 (128): skip the residual, 8 (256): skip the TMA stores
 };
 
 using namespace tcptx;
@@ -644,6 +645,316 @@ conv_tc_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
+// "wide" kernel: the slab kernel's layers (3x3, stride 1, 64 -> 64, 128-pixel-wide maps) with the three
+// HORIZONTAL taps moved from the A operand into the N dimension
+// ---------------------------------------------------------------------------------------
+// At N = 64 every tcgen05.mma reads 4 KB of A for 2 KB of B and the shared-memory operand path, not the tensor
+// pipe, sets the pace (the slab kernel: ~97 clocks per 32-clock MMA, 675-755 TFLOP/s).  Here one MMA multiplies an
+// UNSHIFTED input row (128 pixels x 16 channels) with the weights of all three horizontal taps of one filter row,
+//     D[p][s*64 + co] += in[o + r - 1][p][ci] * W[co][r][s][ci]          (N = 192, K = 3 rows x 64 channels)
+// so the A bytes per FLOP drop to a third (12 MMAs of N = 192 per output row instead of 36 of N = 64), and the
+// horizontal shift is applied once per output element in the epilogue:
+//     out[o][x][co] = D[x-1][co] + D[x][64 + co] + D[x+1][128 + co]     (zero outside the row = the conv padding)
+// The x-1 / x+1 terms come from the neighbouring TMEM lanes: warp shuffles inside a lane quarter, a 64-float
+// hand-over through shared memory between the four warps of an epilogue group.  The packed weight tiles of the
+// taps (r, 0..2) are consecutive 64-row blocks in shared memory, i.e. already one 192-row K-major B operand.
+// An M tile is one image row; input rows stream ONCE through a ring of 16 KB slots (no halo columns), a CTA owns a
+// contiguous range of output rows, accumulators (192 columns) are double-buffered in TMEM, one epilogue group
+// (4 warps) per buffer.
+constexpr int WIDE_SLOTS = 5;
+constexpr uint32_t WIDE_ROW_BYTES = 128 * 128;                     // 128 px x 64 ch bf16
+constexpr uint32_t WIDE_XCH_BYTES = 2 * 4 * 2 * 64 * 4;            // groups x warps x {left, right} x 64 floats
+constexpr uint32_t WIDE_ACC_COLS = 192;
+constexpr int WIDE_THREADS = 128 + 512;   // 4 control warps + 16 epilogue warps
+constexpr size_t WIDE_SMEM =
+    1024 + (size_t)WIDE_SLOTS * WIDE_ROW_BYTES + SLAB_B_BYTES + 1024 + 4 * OUT_STAGE_BYTES + WIDE_XCH_BYTES;
+
+// The residual of a ResNet block is fetched by TMA into the very staging buffer the result leaves from (same
+// SWIZZLE_128B layout: a thread reads the chunk it is about to overwrite), one output row ahead per epilogue group.
+// Per-thread 16-byte global loads of the residual (the shared epilogue above) made the residual launches of these
+// layers 1.56x slower than the plain ones (ncu r02: 301 us against 193 us per 148 tiles at +310 MB of reads).
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
+conv_tc_wide_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const __grid_constant__ CUtensorMap tmapO, const __grid_constant__ CUtensorMap tmapR,
+                    const TcParams p) {
+  constexpr int SLOTS = WIDE_SLOTS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tcptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* rows = smem;
+  uint8_t* bmat = rows + (size_t)SLOTS * WIDE_ROW_BYTES;
+  uint8_t* bar_base = bmat + SLAB_B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + SLOTS;
+  uint64_t* bfull_bar = empty_bar + SLOTS;
+  uint64_t* tfull_bar = bfull_bar + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;      // [group][buffer]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 4);
+  uint8_t* stage_out = bar_base + 1024;      // [group][buffer] x 16 KB
+  float* xch = reinterpret_cast<float*>(stage_out + 4 * OUT_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int H = p.Hout;
+  // contiguous range of output rows (flattened image-major) for this CTA
+  const int f_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int f_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < SLOTS; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(bfull_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 8);   // the eight warps of the buffer's epilogue group
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&rfull_bar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t full0 = smem_u32(&full_bar[0]);
+    const uint32_t bfull = smem_u32(bfull_bar);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bfull, SLAB_B_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(bmat) + (uint32_t)t * SLAB_B_TAP_BYTES, &tmapB, bfull, t * BK, 0);
+    }
+    __syncwarp();
+    uint32_t L = 0;   // row-load counter: load L goes to slot L % SLOTS, use L / SLOTS
+    for (int f = f_begin; f < f_end; ++f) {
+      const int img = f / H, o = f - img * H;
+      const bool new_seg = (f == f_begin) || (o == 0);
+      const int y_lo = new_seg ? (o > 0 ? o - 1 : 0) : o + 1;
+      const int y_hi = o + 1 < H ? o + 1 : H - 1;
+      for (int y = y_lo; y <= y_hi; ++y) {
+        const uint32_t slot = L % SLOTS, use = L / SLOTS;
+        mbar_wait_relaxed(smem_u32(&empty_bar[slot]), (use & 1) ^ 1, p.errflag, 11);
+        if (elect_one()) {
+          const uint32_t fb = full0 + slot * 8u;
+          mbar_arrive_expect_tx(fb, WIDE_ROW_BYTES);
+          tma_load_4d(smem_u32(rows) + slot * WIDE_ROW_BYTES, &tmapA, fb, 0, 0, y, img);
+        }
+        __syncwarp();
+        ++L;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(smem_u32(bfull_bar), 0, p.errflag, 12);
+    uint32_t next_L = 0, seg_base = 0, waited = 0;
+    int seg_row0 = 0;
+    for (int f = f_begin; f < f_end; ++f) {
+      const int img = f / H, o = f - img * H;
+      if ((f == f_begin) || (o == 0)) {
+        seg_base = next_L;
+        seg_row0 = o > 0 ? o - 1 : 0;
+        next_L += (o > 0 ? 1u : 0u) + 1u + (o + 1 < H ? 1u : 0u);
+      } else {
+        next_L += (o + 1 < H ? 1u : 0u);
+      }
+      const int acc = (f - f_begin) & 1;
+      const uint32_t acc_use = (uint32_t)(f - f_begin) >> 1;
+      mbar_wait(smem_u32(&tempty_bar[acc]), (acc_use & 1) ^ 1, p.errflag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * WIDE_ACC_COLS;
+      uint32_t accumulate = 0;
+      for (int r = 0; r < 3; ++r) {
+        const int y = o + r - 1;
+        if (y < 0 || y >= H) continue;
+        const uint32_t li = seg_base + (uint32_t)(y - seg_row0);
+        while (waited <= li) {
+          mbar_wait(smem_u32(&full_bar[waited % SLOTS]), (waited / SLOTS) & 1, p.errflag, 3);
+          ++waited;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_sdesc(smem_u32(rows) + (li % SLOTS) * WIDE_ROW_BYTES);
+          const uint64_t bdesc = make_sdesc(smem_u32(bmat) + (uint32_t)(r * 3) * SLAB_B_TAP_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            if (!DBG(p, 64))
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (accumulate | k) ? 1u : 0u);
+        }
+        __syncwarp();
+        accumulate = 1;
+      }
+      if (elect_one()) {
+        // rows whose last consumer was this output row go back to the producer when the MMAs retire
+        if (o > 0) tc_commit(smem_u32(&empty_bar[(seg_base + (uint32_t)(o - 1 - seg_row0)) % SLOTS]));
+        if ((f + 1 == f_end) || (o == H - 1)) {
+          tc_commit(smem_u32(&empty_bar[(seg_base + (uint32_t)(o - seg_row0)) % SLOTS]));
+          if (o + 1 < H) tc_commit(smem_u32(&empty_bar[(seg_base + (uint32_t)(o + 1 - seg_row0)) % SLOTS]));
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: group e (8 warps) drains accumulator buffer e =====================
+    // a warp owns a TMEM lane quarter (warp % 4, hardware rule) and one half of the 64 output channels: four warps per
+    // scheduler hide the tcgen05.ld / shuffle / shared-memory latencies of one another (with four warps per buffer the
+    // epilogue, 3.7 k clocks per row, was slower than the 1.6 k clocks of MMAs it has to keep up with)
+    const int wrank = warp & 3;
+    const int egrp = ((warp - 4) >> 2) & 1;
+    const int half = (warp - 4) >> 3;
+    const int m = wrank * 32 + lane;                 // pixel x of the row = TMEM lane
+    const bool issuer = (threadIdx.x == 128 + 128 * egrp);
+    const bool has_res = p.residual != nullptr && !DBG(p, 128);
+    uint8_t* sbuf0 = stage_out + (size_t)egrp * 2 * OUT_STAGE_BYTES;
+    float* xl_mine = xch + ((egrp * 4 + wrank) * 2 + 0) * 64;      // lane 31's s = 0 terms, for the warp to the right
+    float* xr_mine = xch + ((egrp * 4 + wrank) * 2 + 1) * 64;      // lane 0's s = 2 terms, for the warp to the left
+    const float* xl_nb = xch + ((egrp * 4 + (wrank > 0 ? wrank - 1 : 0)) * 2 + 0) * 64;
+    const float* xr_nb = xch + ((egrp * 4 + (wrank < 3 ? wrank + 1 : 3)) * 2 + 1) * 64;
+    const uint32_t rfull0 = smem_u32(&rfull_bar[egrp * 2]);
+    auto load_residual = [&](int f, uint32_t buf) {   // issuer only
+      const int img = f / H, o = f - img * H;
+      mbar_arrive_expect_tx(rfull0 + buf * 8u, OUT_STAGE_BYTES);
+      tma_load_4d(smem_u32(sbuf0 + (size_t)buf * OUT_STAGE_BYTES), &tmapR, rfull0 + buf * 8u, 0, 0, o, img);
+    };
+    if (has_res && issuer && f_begin + egrp < f_end) load_residual(f_begin + egrp, 0u);
+    uint32_t i = 0;
+    for (int f = f_begin + egrp; f < f_end; f += 2, ++i) {
+      const uint32_t buf = i & 1u;
+      const int img = f / H, o = f - img * H;
+      uint8_t* sbuf = sbuf0 + (size_t)buf * OUT_STAGE_BYTES;
+      mbar_wait_relaxed(smem_u32(&tfull_bar[egrp]), i & 1u, p.errflag, 4);
+      tc_fence_after();
+      if (DBG(p, 32)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[egrp]));
+        continue;
+      }
+      const uint32_t tbase = tmem_base + ((uint32_t)(wrank * 32) << 16) + (uint32_t)egrp * WIDE_ACC_COLS;
+      if (issuer) {
+        if (has_res) {
+          // the store of this group's previous row has left the other buffer: fetch the next row's residual into it
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (f + 2 < f_end) load_residual(f + 2, buf ^ 1u);
+        } else {
+          // this buffer was last read by the store two rows back
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + egrp) : "memory");
+      if (has_res) mbar_wait_relaxed(rfull0 + buf * 8u, (i >> 1) & 1u, p.errflag, 5);
+      // ---- shifted sum + bias (+ residual, ReLU) -> bf16 -> swizzled staging, 16 channels at a time ----
+      // TMEM reads are the scarce resource here (~100 B/clk/SM, shared with the MMAs' accumulator traffic): every
+      // accumulator column is read exactly once, the boundary lanes hand their terms over through shared memory
+      // between the load and the arithmetic (a named barrier of the four warps of this channel half).
+      const float* bias = p.bias + (size_t)img * p.bias_img_stride;
+      uint8_t* rowp = sbuf + (size_t)m * 128;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * half + cc;
+        uint32_t v0[16], v1[16], v2[16];
+        tc_ld16(tbase + (uint32_t)(c * 16), v0);
+        tc_ld16(tbase + (uint32_t)(64 + c * 16), v1);
+        tc_ld16(tbase + (uint32_t)(128 + c * 16), v2);
+        tc_wait_ld();
+        if (cc == 1) {
+          // accumulator drained (this warp's share): hand the buffer back as early as possible
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[egrp]));
+        }
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(xl_mine + c * 16 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(xr_mine + c * 16 + j) = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(3 + egrp * 2 + half) : "memory");
+        float fo[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 16 + j4));
+          // the neighbour quarters' hand-over values as unconditional broadcast loads (a per-element load under
+          // `if (lane == 0)` serialises 128 divergent shared-memory round trips per row: measured 12 k clocks)
+          const float4 l4 = *reinterpret_cast<const float4*>(xl_nb + c * 16 + j4);
+          const float4 r4 = *reinterpret_cast<const float4*>(xr_nb + c * 16 + j4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 + jj;
+            float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
+            float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
+            up = lane == 0 ? (wrank > 0 ? ll[jj] : 0.0f) : up;
+            dn = lane == 31 ? (wrank < 3 ? rr[jj] : 0.0f) : dn;
+            fo[j] = (up + __uint_as_float(v1[j])) + (dn + bb[jj]);
+          }
+        }
+        uint4* c0p = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ (m & 7)) << 4));
+        uint4* c1p = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ (m & 7)) << 4));
+        if (has_res) {
+          const uint4 r0 = *c0p, r1 = *c1p;
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+            fo[2 * j] += __low2float(h);
+            fo[2 * j + 1] += __high2float(h);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) fo[j] = fmaxf(fo[j], 0.0f);
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(fo[2 * j], fo[2 * j + 1]);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *c0p = make_uint4(w[0], w[1], w[2], w[3]);
+        *c1p = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + egrp) : "memory");
+      if (issuer && !DBG(p, 256)) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+            ::"l"(reinterpret_cast<uint64_t>(&tmapO)), "r"(smem_u32(sbuf)), "r"(0), "r"(0), "r"(o), "r"(img)
+            : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 typedef BdrcEncodeTiledFn EncodeTiledFn;
@@ -737,9 +1048,9 @@ bool slab_eligible(const ConvWeights& w, const ConvArgs& a) {
 // Everything one launch needs.  Built once per distinct (weights, ConvArgs) and kept in the context
 // (TcCache): a forward re-uses the same few dozen entries call after call, so the steady state encodes no
 // tensor maps and derives no tiling on the host.
-enum { TC_GENERIC1 = 0, TC_GENERIC2 = 1, TC_SLAB = 2 };
+enum { TC_GENERIC1 = 0, TC_GENERIC2 = 1, TC_SLAB = 2, TC_WIDE = 3 };
 struct TcLaunch {
-  CUtensorMap mapA, mapB, mapO;
+  CUtensorMap mapA, mapB, mapO, mapR;
   TcParams p;
   int kind = TC_GENERIC1;
   unsigned grid = 0;
@@ -751,7 +1062,7 @@ struct TcKey {
   const void *w, *b, *in, *out, *residual, *bias_override;
   int Cout, Cout_pad, Cin, Cin_pad, R, S;
   int N, Hin, Win, in_ld, in_coff, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, Hout, Wout;
-  int bias_img_stride, res_ld, out_ld, out_coff, out_fp32, relu, sm_count;
+  int bias_img_stride, res_ld, out_ld, out_coff, out_fp32, relu, sm_count, variant;
 };
 
 }  // namespace
@@ -838,6 +1149,48 @@ int build_slab(bdrc_ctx* ctx, EncodeTiledFn enc, const ConvWeights& w, const Con
   return 0;
 }
 
+// the slab kernel's layers on the wide kernel: additionally the residual (if any) must allow 16-byte loads
+bool wide_eligible(const ConvWeights& w, const ConvArgs& a) {
+  return slab_eligible(w, a) && w.Cout == 64 && (a.residual == nullptr || a.res_ld % 8 == 0);
+}
+
+int build_wide(bdrc_ctx* ctx, EncodeTiledFn enc, const ConvWeights& w, const ConvArgs& a, TcLaunch* L) {
+  {
+    const cuuint64_t ld = (cuuint64_t)a.in_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)w.Cin, (cuuint64_t)a.Win, (cuuint64_t)a.Hin, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Win * ld * 2, (cuuint64_t)a.Hin * a.Win * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, 128, 1, 1};
+    BDRC_TRY(encode(ctx, enc, &L->mapA, 4, const_cast<bf16*>(a.in) + a.in_coff, dims, strides, box,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "wide A"));
+  }
+  BDRC_TRY(encode_weights(ctx, enc, &L->mapB, w, 64));
+  BDRC_TRY(encode_out(ctx, enc, &L->mapO, w, a, 128, 1));
+  L->mapR = L->mapO;
+  if (a.residual) {
+    const cuuint64_t ld = (cuuint64_t)a.res_ld;
+    cuuint64_t dims[4] = {64, (cuuint64_t)a.Wout, (cuuint64_t)a.Hout, (cuuint64_t)a.N};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)a.Wout * ld * 2, (cuuint64_t)a.Hout * a.Wout * ld * 2};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    BDRC_TRY(encode(ctx, enc, &L->mapR, 4, const_cast<bf16*>(a.residual), dims, strides, box,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "wide residual"));
+  }
+  TcParams& p = L->p;
+  common_params(ctx, w, a, &p);
+  p.tiles_n = 1; p.tiles_w = 1; p.tiles_h = a.Hout;
+  p.total_tiles = a.N * a.Hout;                      // output rows
+  p.BW = 128; p.BH = 1; p.BN = 192; p.stages = 0; p.G = 1;
+  p.R = 3; p.S = 3; p.kchunks = 1;
+  p.stride_h = p.stride_w = 1; p.pad_h = p.pad_w = 1; p.dil_h = p.dil_w = 1;
+  p.idesc = make_idesc_bf16(BM, 192);
+  p.tmem_cols = 512;
+  p.out_fp32 = 0;
+  p.out_tma = 1;
+  L->kind = TC_WIDE;
+  L->grid = (unsigned)(p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count);
+  L->smem = WIDE_SMEM;
+  return 0;
+}
+
 int build_generic(bdrc_ctx* ctx, EncodeTiledFn enc, const ConvWeights& w, const ConvArgs& a, TcLaunch* L) {
   TcPlan pl;
   if (!make_plan(w, a, &pl)) return bdrc_fail(ctx, BDRC_ERR_UNSUPPORTED, "conv_tc: unsupported shape");
@@ -892,6 +1245,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SLAB_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE_SMEM);
     attr_rc = e;
   });
   if (attr_rc != cudaSuccess)
@@ -905,7 +1259,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
   key.stride_h = a.stride_h; key.stride_w = a.stride_w; key.pad_h = a.pad_h; key.pad_w = a.pad_w;
   key.dil_h = a.dil_h; key.dil_w = a.dil_w; key.Hout = a.Hout; key.Wout = a.Wout;
   key.bias_img_stride = a.bias_img_stride; key.res_ld = a.res_ld; key.out_ld = a.out_ld; key.out_coff = a.out_coff;
-  key.out_fp32 = a.out_fp32; key.relu = a.relu; key.sm_count = ctx->sm_count;
+  key.out_fp32 = a.out_fp32; key.relu = a.relu; key.sm_count = ctx->sm_count; key.variant = ctx->no_wide_conv ? 1 : 0;
   const std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
 
   TcLaunch L;
@@ -920,7 +1274,8 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     auto it = cache->map.find(k);
     if (it == cache->map.end()) {
       TcLaunch fresh;
-      BDRC_TRY(slab_eligible(w, a) ? build_slab(ctx, enc, w, a, &fresh) : build_generic(ctx, enc, w, a, &fresh));
+      if (!ctx->no_wide_conv && wide_eligible(w, a)) BDRC_TRY(build_wide(ctx, enc, w, a, &fresh));
+      else BDRC_TRY(slab_eligible(w, a) ? build_slab(ctx, enc, w, a, &fresh) : build_generic(ctx, enc, w, a, &fresh));
       if (cache->map.size() >= 8192) cache->map.clear();   // callers that never repeat a buffer address
       it = cache->map.emplace(k, fresh).first;
       ctx->tc_plans_built++;
@@ -930,7 +1285,7 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(L.kind == TC_WIDE ? WIDE_THREADS : NUM_THREADS);
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
@@ -953,6 +1308,8 @@ int conv_tc_launch(bdrc_ctx* ctx, const ConvWeights& w, const ConvArgs& a, cudaS
     BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, L.mapA, L.mapB, L.mapO, L.p));
   else if (L.kind == TC_GENERIC1)
     BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, L.mapA, L.mapB, L.mapO, L.p));
+  else if (L.kind == TC_WIDE)
+    BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_wide_kernel, L.mapA, L.mapB, L.mapO, L.mapR, L.p));
   else
     BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_tc_slab_kernel, L.mapA, L.mapB, L.mapO, L.p));
   BDRC_CHECK_LAUNCH(ctx);

@@ -6,15 +6,19 @@
 // mask), so the 3x49 stem weights fold to 49 per output channel and the conv is a GEMM with
 // K = 7 rows x 8 (7 taps + one zero column) = 56, padded to 64 = one 128-byte swizzle row.
 //
-// One CTA produces a 4 x 32 patch of POOLED outputs: it needs the 9 x 65 stem pixels around it
-//   1. stage the 23 x 144 byte input patch in shared memory (zero outside the image),
-//   2. im2col: 585 (-> 640) A rows x 64 bf16, written by the threads in the SWIZZLE_128B K-major layout
+// One CTA produces a 4 x 16 patch of POOLED outputs: it needs the 9 x 33 stem pixels around it
+//   1. stage the 23 x 80 byte input patch in shared memory (zero outside the image),
+//   2. im2col: 297 (-> 384) A rows x 64 bf16, written by the threads in the SWIZZLE_128B K-major layout
 //      (u8 -> bf16 is exact; the window of a stem pixel is 7 runs of 8 consecutive bytes),
-//   3. 5 M-tiles x 4 tcgen05.mma (M128 N64 K16), fp32 accumulators in TMEM,
+//   3. 3 M-tiles x 4 tcgen05.mma (M128 N64 K16), fp32 accumulators in TMEM,
 //   4. epilogue: TMEM -> +bias, ReLU, bf16 -> shared memory (aliasing the A tiles), zero for stem
 //      pixels outside the 256 x 256 stem image (exact: every pooled window holds a valid pixel >= 0),
 //   5. 3x3/s2 max over shared memory -> 16-byte stores of the pooled NHWC tile.
 // The 403 MB stem activation of a 48-tile chunk never exists in HBM.
+// The five phases of a patch are separated by block-wide barriers, so ONE resident CTA leaves the SM idle in
+// every hand-over; a CTA is therefore sized (3 M-tiles = 256 TMEM columns, 60 KB of shared memory, <= 64
+// registers) so that TWO are resident per SM and one's im2col / pooling overlaps the other's MMAs / epilogue
+// (round 1: 4 x 32 patches, 5 M-tiles, 512 TMEM columns, one CTA per SM: 0.60 ms per 148 tiles).
 #include "nn_kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -23,18 +27,19 @@ using namespace tcptx;
 namespace {
 
 constexpr int SP = 512;                 // input tile size
-constexpr int PT_H = 4, PT_W = 32;      // pooled outputs per CTA tile
+constexpr int PT_H = 4, PT_W = 16;      // pooled outputs per CTA tile
 constexpr int SR_H = 2 * PT_H + 1;      // 9 stem rows
-constexpr int SR_W = 2 * PT_W + 1;      // 65 stem cols
-constexpr int M_VALID = SR_H * SR_W;    // 585
-constexpr int M_TILES = 5;              // 640 rows
+constexpr int SR_W = 2 * PT_W + 1;      // 33 stem cols
+constexpr int M_VALID = SR_H * SR_W;    // 297
+constexpr int M_TILES = 3;              // 384 rows
+constexpr uint32_t STEM_TMEM_COLS = 256;  // 3 x 64 accumulator columns, power of two; two CTAs share the SM's 512
 constexpr int PATCH_ROWS = 4 * PT_H + 7;     // 23 input rows
-constexpr int PATCH_PITCH = 144;             // bytes; 36 aligned words starting at image col 4*px0 - 8
+constexpr int PATCH_PITCH = 4 * PT_W + 16;   // bytes; aligned words starting at image col 4*px0 - 8
 constexpr int STEM_THREADS = 512;
 constexpr uint32_t A_TILE_BYTES = 128 * 128;  // 16 KB
-constexpr uint32_t SMEM_A = M_TILES * A_TILE_BYTES;          // 80 KB (also the pooled staging S)
+constexpr uint32_t SMEM_A = M_TILES * A_TILE_BYTES;          // 48 KB (also the pooled staging S)
 constexpr uint32_t SMEM_B = 64 * 128;                        // 8 KB
-constexpr uint32_t SMEM_PATCH = PATCH_ROWS * PATCH_PITCH;    // 3312 B
+constexpr uint32_t SMEM_PATCH = PATCH_ROWS * PATCH_PITCH;    // 1840 B
 constexpr uint32_t SMEM_TOTAL = 1024 + SMEM_A + SMEM_B + 4096 + 256;
 
 __device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int k) {
@@ -44,7 +49,10 @@ __device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int k) {
   return __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
 }
 
-__global__ void __launch_bounds__(STEM_THREADS, 1)
+static_assert(SMEM_PATCH <= 3328, "bias lives at patch + 3328");
+static_assert(M_TILES * 64 <= STEM_TMEM_COLS, "accumulators must fit the TMEM allocation");
+
+__global__ void __launch_bounds__(STEM_THREADS, 2)
 stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restrict__ wb, const float* __restrict__ bias,
                     bf16* __restrict__ out, int* errflag) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -70,7 +78,7 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(STEM_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -207,7 +215,7 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(STEM_TMEM_COLS) : "memory");
   }
 }
 
@@ -221,7 +229,7 @@ int stem_tc_pool_launch(bdrc_ctx* ctx, const uint8_t* tiles, int N, const bf16* 
     attr_set = true;
   }
   const int total = N * (128 / PT_H) * (128 / PT_W);
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  const int grid = total < 2 * ctx->sm_count ? total : 2 * ctx->sm_count;   // two resident CTAs per SM
   stem_tc_pool_kernel<<<grid, STEM_THREADS, SMEM_TOTAL, s>>>(tiles, N, w_bf16, bias, out, ctx->d_errflag);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;

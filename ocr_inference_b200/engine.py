@@ -119,12 +119,13 @@ class Engine:
         self._pin[(key, threading.get_ident())][1] = ev
         return dev
 
-    def upload_page(self, img: np.ndarray, ring: list, k: int):
+    def upload_page(self, img: np.ndarray, ring: list, k: int, threads: int | None = None):
         """Asynchronous H2D of a pageable u8 array on the current stream through slot k of a ring of pinned
         buffers (`ring` = [[tensor | None, event | None], ...], owned by the caller): a few native threads copy
         the array into the slot (bdrc_host_gather, GIL released), the DMA out of it does not block the host, so
         the copy of the next page overlaps it.  A plain pageable .to() moves ~7 GB/s from one thread (2.7 ms per
-        19 MB page).  Returns (device tensor, event recorded after the copy)."""
+        19 MB page; the native copy: 16 / 32 / 65 GB/s with 1 / 4 / 8 threads on a 16-core box).  Returns (device tensor,
+        event recorded after the copy)."""
         img = np.ascontiguousarray(img)
         nbytes = int(img.nbytes)
         slot = ring[k % len(ring)]
@@ -137,7 +138,8 @@ class Engine:
             nb = np.array([nbytes], dtype=np.int64)
             zero = np.zeros(1, dtype=np.int64)
             self._check(self.lib.bdrc_host_gather(ptr.ctypes.data, nb.ctypes.data, zero.ctypes.data, 1,
-                                                  slot[0].data_ptr(), 4), "host_gather")
+                                                  slot[0].data_ptr(), int(threads or getattr(self, "upload_threads", 4))),
+                        "host_gather")
         elif nbytes:
             np.copyto(slot[0][:nbytes].numpy().reshape(img.shape), img)
         d = torch.empty(img.shape, dtype=torch.uint8, device=self.device)
@@ -161,6 +163,10 @@ class Engine:
     def set_dec_tail(self, fused: bool = True):
         """Decoder tail of the segmentation network as one fused kernel (default) or three (cross-check)."""
         self._check(self.lib.bdrc_set_dec_tail(self.ctx.h, int(bool(fused))), "set_dec_tail")
+
+    def set_wide_conv(self, on: bool = True):
+        """64-channel 3x3 layers on the wide-N kernel (default) or the slab kernel (cross-check)."""
+        self._check(self.lib.bdrc_set_wide_conv(self.ctx.h, int(bool(on))), "set_wide_conv")
 
     def set_blocking_sync(self, on: bool = True):
         """Host threads waiting for this GPU sleep instead of spinning (see bdrc_set_blocking_sync)."""

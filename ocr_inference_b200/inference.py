@@ -173,7 +173,8 @@ class Detection:
         return mask_dev.cpu().numpy()
 
     def predict_batch(self, images: Sequence[np.ndarray], class_threshold: float | None = None,
-                      pinned: Sequence[torch.Tensor] | None = None, copy: bool = True) -> list[np.ndarray]:
+                      pinned: Sequence[torch.Tensor] | None = None, copy: bool = True,
+                      group_sizes: Sequence[int] | None = None) -> list[np.ndarray]:
         """Same result as [predict(i) for i in images], as a three-stage pipeline: a helper thread moves the
         (pageable) pages through a ring of pinned slots onto the copy-in stream, this thread launches one forward
         per group of pages as soon as the group's uploads are queued, and a second helper thread hands the masks
@@ -194,6 +195,10 @@ class Detection:
             self._host_bufs = {}
         ups: list = [None] * n
         evs: list = [None] * n
+        # the upload is the only host work of this call: all the copy threads the box can spare (measured on 16 cores,
+        # 16 pages: 35.2 ms per call with 4 threads, 32.3 ms with 8)
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))      # processes sharing this host's cores
+        up_threads = getattr(eng, "upload_threads", None) or max(2, min(8, (os.cpu_count() or 8) // (2 if ranks == 1 else ranks)))
         ready = [threading.Event() for _ in range(n)]
         failed: list = []
         copy_in.wait_stream(compute)
@@ -211,7 +216,8 @@ class Detection:
                             evs[i] = torch.cuda.Event()
                             evs[i].record(copy_in)
                         else:       # pageable page: through the pinned slot ring (native copy threads, GIL released)
-                            ups[i], evs[i] = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, i)
+                            ups[i], evs[i] = eng.upload_page(np.ascontiguousarray(img[..., :3], dtype=np.uint8), ring, i,
+                                                             threads=up_threads)
                         ready[i].set()
             except Exception as e:  # noqa: BLE001
                 failed.append(e)
@@ -224,8 +230,10 @@ class Detection:
         # pages per forward call: a small first group starts computing after two uploads, then groups of 6
         # landscape pages (144 tiles: one 148-tile chunk, ~whole waves per ResNet stage); later groups upload meanwhile
         sizes, left = [], n
+        plan = list(group_sizes) if group_sizes else list(getattr(self, "group_plan", None) or [2])
         while left > 0:
-            sizes.append(min(left, 2 if not sizes else 6))
+            want = plan[len(sizes)] if len(sizes) < len(plan) else 6
+            sizes.append(max(1, min(left, int(want))))
             left -= sizes[-1]
         starts = [sum(sizes[:i]) for i in range(len(sizes))]
         outs: list = [None] * n
