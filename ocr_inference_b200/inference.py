@@ -708,9 +708,17 @@ class OCRPipeline:
             cv_threads = cv2.getNumThreads()
             cv2.setNumThreads(1)
             try:
-                out = []
-                for c0 in range(0, len(images), chunk_pages):
-                    out.extend(self._run_ocr_staged(images[c0:c0 + chunk_pages], workers, gpool, **kw))
+                # chunks are software-pipelined: the segmentation of chunk k+1 is queued on the GPU before this
+                # thread waits for the geometry of chunk k and runs its recognition (on a stream of its own), so the
+                # device does not idle through the geometry tail, the text decode and the next chunk's first uploads
+                out, pending = [], None
+                for k, c0 in enumerate(range(0, len(images), chunk_pages)):
+                    fin = self._run_ocr_staged(images[c0:c0 + chunk_pages], workers, gpool, _slot=k & 1, _defer=True, **kw)
+                    if pending is not None:
+                        out.extend(pending())
+                    pending = fin
+                if pending is not None:
+                    out.extend(pending())
                 return out
             finally:
                 cv2.setNumThreads(cv_threads)
@@ -772,9 +780,13 @@ class OCRPipeline:
 
     def _run_ocr_staged(self, images, workers: int, gpool=None, k_factor: float = 2.5, bbox_tolerance: float = 4.0,
                         merge_lines: bool = True, use_tps: bool = False, tps_threshold: float = 0.25,
-                        target_encoding: Encoding = Encoding.UNICODE, eval_mode: bool = False):
+                        target_encoding: Encoding = Encoding.UNICODE, eval_mode: bool = False, _slot: int = 0,
+                        _defer: bool = False):
         """One chunk of pages through the staged schedule (see run_ocr_batch).  A page on which any
-        stage raises is re-run through run_ocr, which owns the reference's error messages."""
+        stage raises is re-run through run_ocr, which owns the reference's error messages.
+        _defer=True returns, once every segmentation group of the chunk is queued and its page stages are submitted,
+        a function that collects them, runs the recognition and returns the results (run_ocr_batch calls it after it
+        has queued the next chunk); _slot selects the set of pinned mask buffers (two chunks are in flight)."""
         eng, det = self.engine, self.line_inference
         dev = eng.device
         n = len(images)
@@ -788,7 +800,7 @@ class OCRPipeline:
             results[i] = self.run_ocr(images[i], k_factor, bbox_tolerance, merge_lines, use_tps, tps_threshold,
                                       target_encoding, eval_mode)
         if not good:
-            return results
+            return (lambda: results) if _defer else results
         compute = torch.cuda.current_stream(dev)
         copy_in = getattr(det, "_copy_in", None) or torch.cuda.Stream(dev)
         copy_out = getattr(det, "_copy_out", None) or torch.cuda.Stream(dev)
@@ -907,7 +919,8 @@ class OCRPipeline:
         futures = {}
         sizes, left = [], len(good)
         while left > 0:
-            sizes.append(min(left, 2 if not sizes else 6))
+            # a small first group starts the GPU after two uploads; a chunk queued behind another one needs none
+            sizes.append(min(left, 2 if (not sizes and not (_defer and _slot)) else 6))
             left -= sizes[-1]
         g0 = 0
         thr = det._default_threshold
@@ -929,7 +942,7 @@ class OCRPipeline:
                 copy_out.wait_event(seg_done)
                 with torch.cuda.stream(copy_out):
                     for i, m, c in zip(idx, masks, cens):
-                        key = ("mask_host", i, tuple(m.shape))
+                        key = ("mask_host", _slot, i, tuple(m.shape))
                         h = det._host_bufs.get(key)
                         if h is None:
                             h = det._host_bufs[key] = torch.empty(m.shape, dtype=torch.uint8, pin_memory=True)
@@ -937,7 +950,7 @@ class OCRPipeline:
                         m.record_stream(copy_out)
                         ch = None
                         if c is not None:
-                            ckey = ("census_host", i, int(c.numel()))
+                            ckey = ("census_host", _slot, i, int(c.numel()))
                             ch = det._host_bufs.get(ckey)
                             if ch is None:
                                 ch = det._host_bufs[ckey] = torch.empty(c.shape, dtype=torch.uint8, pin_memory=True)
@@ -953,32 +966,45 @@ class OCRPipeline:
         up_thread.join()
 
         # ---- recognition: the crops of all pages as one batch -------------------------------------
-        staged_pages = []
-        for i in good:
-            if i not in futures:
-                continue
-            r = futures[i].result()
-            if r is None:
-                results[i] = "retry"
-            elif r[0] == OpStatus.FAILED:
-                results[i] = r
-            else:
-                staged_pages.append((i, r[1]))
-        try:
-            texts = self._recognise_packs([(p[3], p[4]) for _, p in staged_pages])
-            for (i, (rot_mask, sorted_lines, kept, _, _, angle)), tx in zip(staged_pages, texts):
-                results[i] = (OpStatus.SUCCESS, [rot_mask, sorted_lines, self._make_ocr_lines(kept, tx, target_encoding),
-                                                 angle])
-        except Exception:  # noqa: BLE001
-            for i, _ in staged_pages:
-                results[i] = "retry"
-        torch.cuda.synchronize(dev)       # every stream is done with pages_dev / crops before they are freed
-        pages_dev.clear()
-        for i in range(n):
-            if isinstance(results[i], str):
-                results[i] = self.run_ocr(images[i], k_factor, bbox_tolerance, merge_lines, use_tps, tps_threshold,
-                                          target_encoding, eval_mode)
-        return results
+        def finish():
+            staged_pages = []
+            for i in good:
+                if i not in futures:
+                    continue
+                r = futures[i].result()
+                if r is None:
+                    results[i] = "retry"
+                elif r[0] == OpStatus.FAILED:
+                    results[i] = r
+                else:
+                    staged_pages.append((i, r[1]))
+            # on a high-priority stream of its own: the next chunk's segmentation may already be queued on the compute
+            # stream, and the text of this chunk must not wait behind it
+            rec = getattr(self, "_rec_stream", None)
+            if rec is None:
+                rec = self._rec_stream = torch.cuda.Stream(dev, priority=-1)
+            try:
+                with torch.cuda.stream(rec):
+                    texts = self._recognise_packs([(p[3], p[4]) for _, p in staged_pages])
+                for (i, (rot_mask, sorted_lines, kept, _, _, angle)), tx in zip(staged_pages, texts):
+                    results[i] = (OpStatus.SUCCESS, [rot_mask, sorted_lines, self._make_ocr_lines(kept, tx, target_encoding),
+                                                     angle])
+            except Exception:  # noqa: BLE001
+                for i, _ in staged_pages:
+                    results[i] = "retry"
+            # the recognition waited for every page's extraction (their `done` events) and those for the masks, i.e. for
+            # the chunk's segmentation and uploads: once it has drained, no stream reads this chunk's pages or crops
+            rec.synchronize()
+            if any(isinstance(r, str) for r in results):
+                torch.cuda.synchronize(dev)   # a failed page may have left kernels behind on its thread's stream
+            pages_dev.clear()
+            for i in range(n):
+                if isinstance(results[i], str):
+                    results[i] = self.run_ocr(images[i], k_factor, bbox_tolerance, merge_lines, use_tps, tps_threshold,
+                                              target_encoding, eval_mode)
+            return results
+
+        return finish if _defer else finish()
 
     def _recognise_packs(self, packs, max_lines: int = 512) -> list[list[str]]:
         """packs: [((crops_dev, hw, off, real), done_event)] per page -> texts per page.  a-7 runs per page into

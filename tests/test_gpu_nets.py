@@ -203,3 +203,49 @@ def test_fused_decoder_tail_equals_the_three_kernel_form(engine, n_classes, n_ti
     print(f"fused vs three-kernel decoder tail: max |diff| {err:.3e} at logit std {scale:.3f}")
     assert err <= 2e-4 * max(1.0, scale) + 1e-4 * float(ref.abs().max())
     assert float(ref.abs().max()) > 0.1
+
+
+@pytest.mark.parametrize("N,H,residual,relu", [(2, 128, True, True), (5, 128, False, False), (3, 8, True, False), (1, 4, False, True)])
+def test_wide_conv_kernel_against_fp32_conv_and_the_slab_kernel(engine, N, H, residual, relu):
+    """conv_tc_wide_kernel (64 -> 64 channel 3x3 layers on 128-pixel-wide maps: three horizontal taps in the MMA's N
+    dimension, shifted sum in the epilogue, residual through TMA) against torch's fp32 conv2d on the bf16-rounded
+    operands, and against the slab kernel it replaces (same products, different fp32 summation order)."""
+    import ctypes as C
+
+    g = torch.Generator().manual_seed(100 + N + H)
+    x = torch.randn(N, H, 128, 64, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24.0).float()
+    b = torch.randn(64, generator=g).float()
+    res = torch.randn(N, H, 128, 64, generator=g).to(torch.bfloat16).cuda() if residual else None
+    wc = np.ascontiguousarray(w.numpy())
+    bc = np.ascontiguousarray(b.numpy())
+
+    def run(wide):
+        engine.set_wide_conv(wide)
+        y = torch.full((N, H, 128, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        rc = engine.lib.bdrc_conv2d_test(engine.ctx.h, x.data_ptr(), N, H, 128, 64, wc.ctypes.data, bc.ctypes.data, 64, 3, 3,
+                                         1, 1, 1, 1, 1, 1, res.data_ptr() if residual else None, int(relu), 0,
+                                         y.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, engine.lib.bdrc_last_error(engine.ctx.h)
+        torch.cuda.synchronize()
+        return y.float()
+
+    try:
+        slab = run(False)
+        wide = run(True)
+        wide2 = run(True)
+    finally:
+        engine.set_wide_conv(True)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().cuda(), b.cuda(),
+                                     padding=1).permute(0, 2, 3, 1)
+    if residual:
+        ref = ref + res.float()
+    if relu:
+        ref = torch.relu(ref)
+    assert torch.equal(wide, wide2)                                        # deterministic
+    tol = 2e-2 * float(ref.abs().max()) + 1e-3                            # bf16 output rounding
+    assert not torch.isnan(wide).any()
+    assert float((wide - ref).abs().max()) <= tol
+    # the two kernels differ by fp32 summation order only: at most one bf16 ulp of the output
+    assert float((wide - slab).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 1e-6
+    assert float((wide != slab).float().mean()) < 0.02
