@@ -34,12 +34,13 @@ constexpr int M_VALID = SR_H * SR_W;    // 297
 constexpr int M_TILES = 3;              // 384 rows
 constexpr uint32_t STEM_TMEM_COLS = 256;  // 3 x 64 accumulator columns, power of two; two CTAs share the SM's 512
 constexpr int PATCH_ROWS = 4 * PT_H + 7;     // 23 input rows
-constexpr int PATCH_PITCH = 4 * PT_W + 16;   // bytes; aligned words starting at image col 4*px0 - 8
+constexpr int PATCH_PITCH = 4 * PT_W + 16;   // input columns per patch row; aligned words starting at image col 4*px0 - 8
+constexpr int P1_PITCH = 2 * PATCH_PITCH;    // bytes per row of the bf16 copy of the patch
 constexpr int STEM_THREADS = 512;
 constexpr uint32_t A_TILE_BYTES = 128 * 128;  // 16 KB
 constexpr uint32_t SMEM_A = M_TILES * A_TILE_BYTES;          // 48 KB (also the pooled staging S)
 constexpr uint32_t SMEM_B = 64 * 128;                        // 8 KB
-constexpr uint32_t SMEM_PATCH = PATCH_ROWS * PATCH_PITCH;    // 1840 B
+constexpr uint32_t SMEM_PATCH = PATCH_ROWS * P1_PITCH;       // 3680 B
 constexpr uint32_t SMEM_TOTAL = 1024 + SMEM_A + SMEM_B + 4096 + 256;
 
 __device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int k) {
@@ -49,7 +50,7 @@ __device__ __forceinline__ uint32_t u8pair_to_bf16x2(uint32_t word, int k) {
   return __byte_perm(__float_as_uint(f0), __float_as_uint(f1), 0x7632);
 }
 
-static_assert(SMEM_PATCH <= 3328, "bias lives at patch + 3328");
+static_assert(SMEM_PATCH <= 3712, "bias lives at patch + 3712");
 static_assert(M_TILES * 64 <= STEM_TMEM_COLS, "accumulators must fit the TMEM allocation");
 
 __global__ void __launch_bounds__(STEM_THREADS, 2)
@@ -62,7 +63,7 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
   uint8_t* sP = sB + SMEM_B;                  // input patch
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sP + 4096);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  float* sBias = reinterpret_cast<float*>(sP + 3328);   // 64 floats after the patch (3312 -> 3328)
+  float* sBias = reinterpret_cast<float*>(sP + 3712);   // 64 floats after the patch (3680 -> 3712)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -97,41 +98,82 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
   const int total = N * tiles_y * tiles_x;
   uint32_t phase = 0;
 
+  // ---- per-thread constants of the tile loop (nothing below depends on the tile) ---------------
+  // patch loader: thread i < 460 owns the aligned word wq of patch row pr_ (and the word after it)
+  const bool p_live = tid < PATCH_ROWS * (PATCH_PITCH / 4);
+  const int pr_ = tid / (PATCH_PITCH / 4), pwq = tid - pr_ * (PATCH_PITCH / 4);
+  // im2col items i = tid + 512 * it -> (kernel row r, A row m): source offset in the bf16 patch (12 bits) and
+  // destination offset in the swizzled A tiles (16 bits); 0xFFFFFFFF = no item / row beyond the 297 valid ones
+  constexpr int IM_ITEMS = 7 * M_TILES * 128;
+  constexpr int IM_IT = (IM_ITEMS + STEM_THREADS - 1) / STEM_THREADS;   // 6
+  uint32_t im_item[IM_IT];
+#pragma unroll
+  for (int it = 0; it < IM_IT; ++it) {
+    const int i = tid + it * STEM_THREADS;
+    const int r = i / (M_TILES * 128), m = i - r * (M_TILES * 128);
+    uint32_t pk = 0xFFFFFFFFu;
+    if (i < IM_ITEMS && m < M_VALID) {
+      const int ry = m / SR_W, rx = m - ry * SR_W;
+      // the window of stem pixel (ry, rx), kernel row r: patch bytes 3 + 2 rx .. + 7 of row 2 ry + r; the bf16 copy
+      // holds patch byte e + 1 at element e, so the window starts at byte 4 + 4 rx of its row: four aligned words
+      const uint32_t src = (uint32_t)((2 * ry + r) * P1_PITCH + 4 + 4 * rx);
+      const uint32_t dst = (uint32_t)(m * 128 + ((r ^ (m & 7)) << 4));
+      pk = src | (dst << 12);
+    }
+    im_item[it] = pk;
+  }
+  // epilogue rows m = t * 128 + ml: bit t = row is one of the 297, bit 4 + t = stem row 0 of the patch, bit 8 + t = stem
+  // column 0 of the patch (outside the image for the patches on the top / left edge)
+  const int ml = (warp & 3) * 32 + lane;
+  uint32_t ep_flags = 0;
+#pragma unroll
+  for (int t = 0; t < M_TILES; ++t) {
+    const int m = t * 128 + ml;
+    const int ry = m / SR_W, rx = m - ry * SR_W;
+    if (m < M_VALID) ep_flags |= 1u << t;
+    if (ry == 0) ep_flags |= 16u << t;
+    if (rx == 0) ep_flags |= 256u << t;
+  }
+
+  auto load_patch = [&](int tile, uint32_t& lo, uint32_t& hi) {
+    lo = 0u; hi = 0u;
+    if (tile < total && p_live) {
+      const int tx = tile % tiles_x;
+      const int ty = (tile / tiles_x) % tiles_y;
+      const int n = tile / (tiles_x * tiles_y);
+      const int iy = 4 * (ty * PT_H) - 5 + pr_, ix = 4 * (tx * PT_W) - 8 + pwq * 4;
+      if (iy >= 0 && iy < SP) {
+        const uint8_t* rowp = in + ((size_t)n * SP + iy) * SP;
+        if (ix >= 0 && ix < SP) lo = __ldg(reinterpret_cast<const uint32_t*>(rowp + ix));
+        if (ix + 4 >= 0 && ix + 4 < SP) hi = __ldg(reinterpret_cast<const uint32_t*>(rowp + ix + 4));
+      }
+    }
+  };
+  uint32_t p_lo, p_hi;
+  load_patch(blockIdx.x, p_lo, p_hi);
+
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int tx = tile % tiles_x;
     const int ty = (tile / tiles_x) % tiles_y;
     const int n = tile / (tiles_x * tiles_y);
     const int px0 = tx * PT_W, py0 = ty * PT_H;
-    const int x_org = 4 * px0 - 8, y_org = 4 * py0 - 5;
-    const uint8_t* img = in + (size_t)n * SP * SP;
 
-    // ---- 1. input patch ----------------------------------------------------------------------
-    for (int i = tid; i < PATCH_ROWS * (PATCH_PITCH / 4); i += STEM_THREADS) {
-      const int r = i / (PATCH_PITCH / 4), wq = i - r * (PATCH_PITCH / 4);
-      const int iy = y_org + r, ix = x_org + wq * 4;
-      uint32_t v = 0;
-      if (iy >= 0 && iy < SP && ix >= 0 && ix < SP) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)iy * SP + ix));
-      *reinterpret_cast<uint32_t*>(sP + r * PATCH_PITCH + wq * 4) = v;
+    // ---- 1. input patch (fetched one tile ahead) as bf16, shifted by one column: element e = patch byte e + 1 -----
+    if (p_live) {
+      const uint32_t w = __funnelshift_r(p_lo, p_hi, 8);
+      *reinterpret_cast<uint2*>(sP + pr_ * P1_PITCH + pwq * 8) = make_uint2(u8pair_to_bf16x2(w, 0), u8pair_to_bf16x2(w, 2));
     }
     __syncthreads();   // also orders the previous tile's pooling reads of S before the rewrite of A
+    load_patch(tile + gridDim.x, p_lo, p_hi);   // consumed at the top of the next iteration: the L2 latency hides behind this tile
 
-    // ---- 2. im2col: item = (kernel row r, A row m); chunk r of row m = 8 bytes -> 8 bf16 ----------
-    for (int i = tid; i < 7 * M_TILES * 128; i += STEM_THREADS) {
-      const int r = i / (M_TILES * 128), m = i - r * (M_TILES * 128);
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m < M_VALID) {
-        const int ry = m / SR_W, rx = m - ry * SR_W;
-        const int b0 = 3 + 2 * rx;                                   // first byte of the 8-byte window
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sP + (2 * ry + r) * PATCH_PITCH + (b0 & ~3));
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        const int sh = (b0 & 3) * 8;
-        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        v.x = u8pair_to_bf16x2(lo, 0);
-        v.y = u8pair_to_bf16x2(lo, 2);
-        v.z = u8pair_to_bf16x2(hi, 0);
-        v.w = u8pair_to_bf16x2(hi, 2) & 0x0000FFFFu;                 // 8th tap column has no weight: keep it 0
+    // ---- 2. im2col: chunk r of A row m = 8 consecutive bf16 of the patch copy (the 8th meets a zero weight) ----------
+#pragma unroll
+    for (int it = 0; it < IM_IT; ++it) {
+      const uint32_t pk = im_item[it];
+      if (pk != 0xFFFFFFFFu) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(sP + (pk & 0xFFFu));
+        *reinterpret_cast<uint4*>(sA + (pk >> 12)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
       }
-      *reinterpret_cast<uint4*>(sA + (size_t)m * 128 + ((r ^ (m & 7)) << 4)) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -159,29 +201,29 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
     // ---- 4. epilogue: warp w -> TMEM lanes 32*(w%4).., column group q = w/4 of every tile ------------
     {
       const int q = warp >> 2;
-      const int ml = (warp & 3) * 32 + lane;
       float b[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) b[j] = sBias[q * 16 + j];
+      // rows that are not stem pixels of the image store zeros (exact for the max: every window holds a valid value >= 0)
+      const uint32_t dead = (~ep_flags & 7u) | (py0 == 0 ? (ep_flags >> 4) & 7u : 0u) | (px0 == 0 ? (ep_flags >> 8) & 7u : 0u);
 #pragma unroll
       for (int t = 0; t < M_TILES; ++t) {
         uint32_t v[16];
         tc_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * 64 + q * 16), v);
         tc_wait_ld();
-        const int m = t * 128 + ml;
-        const int ry = m / SR_W, rx = m - ry * SR_W;
-        const bool ok = (m < M_VALID) && (2 * py0 - 1 + ry >= 0) && (2 * px0 - 1 + rx >= 0);
+        const uint32_t keep = (dead >> t) & 1u ? 0u : 0xFFFFFFFFu;
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float f0 = ok ? fmaxf(__uint_as_float(v[2 * j]) + b[2 * j], 0.f) : 0.f;
-          const float f1 = ok ? fmaxf(__uint_as_float(v[2 * j + 1]) + b[2 * j + 1], 0.f) : 0.f;
-          const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+          // bias, ReLU and the bf16 rounding in one conversion: d = {hi: relu(a), lo: relu(b)}
+          const float f0 = __uint_as_float(v[2 * j]) + b[2 * j], f1 = __uint_as_float(v[2 * j + 1]) + b[2 * j + 1];
+          uint32_t h;
+          asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(f1), "f"(f0));
+          w[j] = h & keep;
         }
-        uint8_t* rowp = sA + (size_t)m * 128;
-        *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (m & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (m & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+        uint8_t* rowp = sA + (size_t)(t * 128 + ml) * 128;
+        *reinterpret_cast<uint4*>(rowp + (((2 * q) ^ (ml & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(rowp + (((2 * q + 1) ^ (ml & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
     tc_fence_before();
