@@ -9,18 +9,23 @@
 // (what the unfused path stores) and folds the head's per-pixel dot product.  Only the low-res logits reach HBM.
 //
 // Tile: 8 rows x 16 columns of output pixels (M = 128), K = 304 in five 64-channel chunks, N = 256.
-// Roles (512 threads):
+// Roles (768 threads):
 //   warp 0      TMA producer of the halo ring (4 slots): per chunk the (10 x 18 pixel) x 64-channel box of the concat
 //               buffer (zero padding and the 304 -> 320 channel tail by out-of-bounds fill)
 //   warp 3      TMA producer of the weight ring (2 slots): the 64 x 256 tile of the chunk
 //   warp 1      MMA issuer (4 x tcgen05.mma M128 N256 K16 per chunk), commits free the A / weight slots
 //   warp 2      TMEM allocation
-//   warps 4-11  depthwise: warp = output row of the tile, lane = (quad of 4 adjacent pixels, 8-channel group):
-//               18 shared-memory loads feed 4 outputs (sliding window), taps accumulate in the order r, s of the
-//               standalone depthwise kernel (bit-identical bf16 results)
-//   warps 12-15 epilogue: one TMEM lane (= pixel) per thread
+//   warps 4-19  depthwise, two groups of eight: group g produces the chunks with (chunk counter & 1) == g into A slot g,
+//               so two chunks are in production at a time (four depthwise warps per scheduler instead of two: the FMA
+//               and shared-memory latencies of one chunk hide behind the other's); warp = output row of the tile, lane =
+//               pair of channels; taps accumulate in the order r, s of the standalone depthwise kernel (bit-identical
+//               bf16 results)
+//   warps 20-23 epilogue: one TMEM lane (= pixel) per thread
 // Weights, A and the accumulators are double-buffered, the halo ring is four deep (a two-deep ring left the
 // depthwise warps waiting for TMA: 14.5 us per tile), persistent grid.
+#include <cstring>
+#include <type_traits>
+
 #include "nn_kernels.cuh"
 #include "tc_ptx.cuh"
 
@@ -34,7 +39,7 @@ constexpr int KC = 64;                            // channels per chunk
 constexpr uint32_t HALO_BYTES = HH * HW * 128;    // 23040
 constexpr uint32_t B_BYTES = 256 * 128;           // 32768
 constexpr uint32_t A_BYTES = 128 * 128;           // 16384
-constexpr int DT_THREADS = 512;
+constexpr int DT_THREADS = 768;
 constexpr int MAX_HEAD = 8;
 constexpr int HS = 4;                             // halo ring depth
 
@@ -42,27 +47,34 @@ struct DecTailParams {
   int n_img, H, W, C, chunks;      // C = 304, chunks = 5
   int tiles_x, tiles_y, total_tiles;
   const float* dw_w;               // [9][C] fp32
-  const float* bias;               // [256]
-  const float* head_w;             // [head_C][256] fp32 (bf16-rounded values)
-  const float* head_b;             // [head_C]
   float* out;                      // [n][H][W][head_C] fp32
   int head_C;
   uint32_t idesc;
   int* errflag;
 };
 
+// The epilogue's constants travel in the kernel parameters (constant bank): every thread of the epilogue needs the SAME
+// bias / head weight at the same time, so they are constant operands of the FADD / FFMA themselves.  As broadcast
+// shared-memory loads (the first version) they were 128 wavefronts per warp and tile on the resource this kernel is
+// bound by -- the depthwise loads, the MMA operand reads and the TMA writes all go through shared memory.
+template <int HC>
+struct TailConsts {
+  float bias[256];                 // 1x1 conv 304 -> 256
+  float head_b[HC];
+  float head_w[HC][256];           // fp32 holding the bf16-rounded head weights
+};
+
 template <int HC>     // head classes: compile-time, the per-pixel dot products live in registers
 __global__ void __launch_bounds__(DT_THREADS, 1)
-dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, const DecTailParams p) {
+dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW, const DecTailParams p,
+                const __grid_constant__ TailConsts<HC> kc_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                   // 2 x 32 KB (1024-aligned, SWIZZLE_128B)
   uint8_t* sA = sB + 2 * B_BYTES;                       // 2 x 16 KB (1024-aligned, SWIZZLE_128B, written by SIMT)
   uint8_t* sH = sA + 2 * A_BYTES;                       // HS x 23040 B halo (plain rows of 128 B)
   float* sDW = reinterpret_cast<float*>(sH + HS * HALO_BYTES);     // [9][chunks * 64]
-  float* sBias = sDW + 9 * p.chunks * KC;                          // [256]
-  float* sHead = sBias + 256;                                      // [MAX_HEAD][256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sHead + MAX_HEAD * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDW + 9 * p.chunks * KC);
   uint64_t* halo_full = bars;          // [HS]
   uint64_t* halo_empty = bars + 4;     // [HS]
   uint64_t* b_full = bars + 8;         // [2]
@@ -100,13 +112,11 @@ dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // constants: depthwise weights (zero beyond C), bias, head
+  // depthwise weights (zero beyond C)
   for (int i = threadIdx.x; i < 9 * CP; i += DT_THREADS) {
     const int k = i / CP, c = i - k * CP;
     sDW[i] = c < p.C ? __ldg(p.dw_w + (size_t)k * p.C + c) : 0.f;
   }
-  for (int i = threadIdx.x; i < 256; i += DT_THREADS) sBias[i] = __ldg(p.bias + i);
-  for (int i = threadIdx.x; i < p.head_C * 256; i += DT_THREADS) sHead[i] = __ldg(p.head_w + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -169,49 +179,43 @@ dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 20) {
     // ===================== depthwise producers of the A operand =====================
-    const int row = warp - 4;                     // output row of the tile
-    const int cg = lane & 7, quad = lane >> 3;    // 8-channel group, 4 adjacent pixels
+    // warp = output row of the tile (16 pixels), lane = one PAIR of channels of the chunk.  Every shared-memory access of
+    // the warp is then one 128-byte wavefront (a halo pixel's 64 channels; a row of the A tile) and a halo value is
+    // loaded once per filter row: 54 + 9 loads per thread and chunk.  This kernel is bound by shared-memory wavefronts
+    // (depthwise loads + MMA operand reads + TMA writes); with lane = (4 adjacent pixels, 8 channels) and 16-byte
+    // loads the same work cost 144 load wavefronts per warp and chunk instead of 72 (216 before the weight loads'
+    // bank conflicts were removed: 0.98 -> 0.84 ms per 148 tiles).
+    const int row = (warp - 4) & 7;
+    const uint32_t group = (uint32_t)(warp - 4) >> 3;
     uint32_t it = 0;
     for (int tile = first; tile < p.total_tiles; tile += step) {
       for (int kc = 0; kc < p.chunks; ++kc, ++it) {
+        if ((it & 1u) != group) continue;
         const uint32_t s = it & 1u, ph = (it >> 1) & 1u;          // A slot
         const uint32_t hs = it % HS, hph = (it / HS) & 1u;        // halo slot
         mbar_wait_relaxed(smem_u32(&halo_full[hs]), hph, p.errflag, 26);
-        const uint8_t* halo = sH + hs * HALO_BYTES;
-        float acc[4][8];
+        const uint8_t* halo = sH + hs * HALO_BYTES + lane * 4;
+        float acc[TW][2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+        for (int q = 0; q < TW; ++q) acc[q][0] = acc[q][1] = 0.f;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-          float w[3][8];
+          float2 w[3];
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sDW + (r * 3 + t) * CP + kc * KC + cg * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(sDW + (r * 3 + t) * CP + kc * KC + cg * 8 + 4);
-            w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
-            w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
-          }
-          const uint8_t* hrow = halo + (size_t)((row + r) * HW + quad * 4) * 128 + cg * 16;
+          for (int t = 0; t < 3; ++t) w[t] = *reinterpret_cast<const float2*>(sDW + (r * 3 + t) * CP + kc * KC + lane * 2);
+          const uint8_t* hrow = halo + (size_t)((row + r) * HW) * 128;
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {           // halo columns quad*4 + c feed outputs q = c - t (tap t)
-            const uint4 v = *reinterpret_cast<const uint4*>(hrow + c * 128);
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[2 * j] = __uint_as_float(u[j] << 16);
-              f[2 * j + 1] = __uint_as_float(u[j] & 0xFFFF0000u);
-            }
+          for (int c = 0; c < HW; ++c) {          // halo column c feeds outputs q = c - t (tap t): taps in the order r, s
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(hrow + c * 128);
+            const float f0 = __uint_as_float(u << 16), f1 = __uint_as_float(u & 0xFFFF0000u);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
               const int q = c - t;
-              if (q >= 0 && q < 4) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(f[j], w[t][j], acc[q][j]);
+              if (q >= 0 && q < TW) {
+                acc[q][0] = fmaf(f0, w[t].x, acc[q][0]);
+                acc[q][1] = fmaf(f1, w[t].y, acc[q][1]);
               }
             }
           }
@@ -221,25 +225,19 @@ dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&halo_empty[hs]));
         mbar_wait_relaxed(smem_u32(&a_empty[s]), ph ^ 1u, p.errflag, 27);   // the MMAs that read this A slot two chunks ago
-        // A tile: row m = pixel, 16-byte chunk cg XOR-swizzled with (m & 7)
-        uint8_t* a = sA + s * A_BYTES;
+        // A tile: row m = pixel, 16-byte chunk (lane / 4) XOR-swizzled with (m & 7); the warp writes one 128-byte row
+        uint8_t* a = sA + s * A_BYTES + (size_t)(row * TW) * 128 + (lane & 3) * 4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int m = row * TW + quad * 4 + q;
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(acc[q][2 * j], acc[q][2 * j + 1]);
-            o[j] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(a + (size_t)m * 128 + ((cg ^ (m & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int q = 0; q < TW; ++q) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(acc[q][0], acc[q][1]);
+          *reinterpret_cast<uint32_t*>(a + q * 128 + (((lane >> 2) ^ (q & 7)) << 4)) = *reinterpret_cast<const uint32_t*>(&h);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_full[s]));
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ===================== epilogue: bias + ReLU + bf16 rounding + head =====================
     const int q4 = warp & 3;                      // TMEM lane quarter
     const int m = q4 * 32 + lane;                 // pixel of the tile
@@ -253,33 +251,39 @@ dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
 #pragma unroll
       for (int c = 0; c < HC; ++c) hacc[c] = 0.f;
       const uint32_t tbase = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * 256u;
-      for (int c0 = 0; c0 < 256; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(tbase + (uint32_t)c0, v);
+      // 16 accumulator columns: bias + ReLU + the bf16 rounding of the unfused path's stored activation in one packed
+      // conversion, then the head's dot products; C0 is a compile-time constant (constant-bank operands)
+      auto fold = [&](const uint32_t* v, auto c0_tag) {
+        constexpr int C0 = decltype(c0_tag)::value;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          uint32_t h;
+          asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(h)
+              : "f"(__uint_as_float(v[j + 1]) + kc_.bias[C0 + j + 1]), "f"(__uint_as_float(v[j]) + kc_.bias[C0 + j]));
+          const float f0 = __uint_as_float(h << 16), f1 = __uint_as_float(h & 0xFFFF0000u);
+#pragma unroll
+          for (int c = 0; c < HC; ++c) {
+            hacc[c] = fmaf(f0, kc_.head_w[c][C0 + j], hacc[c]);
+            hacc[c] = fmaf(f1, kc_.head_w[c][C0 + j + 1], hacc[c]);
+          }
+        }
+      };
+      // the TMEM load of the next 16 columns is in flight while these are folded
+      uint32_t va[16], vb[16];
+      tc_ld16(tbase, va);
+      auto step32 = [&](auto c0_tag) {
+        constexpr int C0 = decltype(c0_tag)::value;
         tc_wait_ld();
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {                     // bias and head weights as 128-bit broadcast loads
-          const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float t = fmaxf(__uint_as_float(v[j + i]) + bb[i], 0.f);
-            f[j + i] = __bfloat162float(__float2bfloat16(t));   // the unfused path stores this layer as bf16
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < HC; ++c) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 h4 = *reinterpret_cast<const float4*>(sHead + c * 256 + c0 + j);
-            hacc[c] = fmaf(f[j + 0], h4.x, hacc[c]);
-            hacc[c] = fmaf(f[j + 1], h4.y, hacc[c]);
-            hacc[c] = fmaf(f[j + 2], h4.z, hacc[c]);
-            hacc[c] = fmaf(f[j + 3], h4.w, hacc[c]);
-          }
-        }
-      }
+        tc_ld16(tbase + (uint32_t)(C0 + 16), vb);
+        fold(va, std::integral_constant<int, C0>{});
+        tc_wait_ld();
+        if (C0 + 32 < 256) tc_ld16(tbase + (uint32_t)(C0 + 32), va);
+        fold(vb, std::integral_constant<int, C0 + 16>{});
+      };
+      step32(std::integral_constant<int, 0>{});   step32(std::integral_constant<int, 32>{});
+      step32(std::integral_constant<int, 64>{});  step32(std::integral_constant<int, 96>{});
+      step32(std::integral_constant<int, 128>{}); step32(std::integral_constant<int, 160>{});
+      step32(std::integral_constant<int, 192>{}); step32(std::integral_constant<int, 224>{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
@@ -287,7 +291,7 @@ dec_tail_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
       if (oy < p.H && ox < p.W) {
         float* o = p.out + (((size_t)n * p.H + oy) * p.W + ox) * p.head_C;
 #pragma unroll
-        for (int c = 0; c < HC; ++c) o[c] = hacc[c] + __ldg(p.head_b + c);
+        for (int c = 0; c < HC; ++c) o[c] = hacc[c] + kc_.head_b[c];
       }
     }
   }
@@ -308,8 +312,12 @@ int dec_tail_supported(int C, int Cout, int head_C, int H, int W) {
 }
 
 int dec_tail_launch(bdrc_ctx* ctx, const bf16* x, int N, int H, int W, int C, const float* dw_w9c, const ConvWeights& pw,
-                    const float* head_w_f32, const float* head_b, int head_C, float* out, cudaStream_t s) {
-  BDRC_REQUIRE(ctx, dec_tail_supported(C, pw.Cout, head_C, H, W) && pw.R == 1 && pw.S == 1 && pw.Cin == C,
+                    const float* bias_host, const float* head_w_host, const float* head_b_host, int head_C, float* out,
+                    cudaStream_t s) {
+  // bias_host [256], head_w_host [head_C][256] (bf16-rounded values as fp32), head_b_host [head_C]: HOST copies, they
+  // travel to the kernel as parameters
+  BDRC_REQUIRE(ctx, dec_tail_supported(C, pw.Cout, head_C, H, W) && pw.R == 1 && pw.S == 1 && pw.Cin == C && bias_host &&
+                        head_w_host && head_b_host,
                "dec_tail: unsupported shape");
   BdrcEncodeTiledFn enc = bdrc_tma_encode_fn();
   const int chunks = pw.Cin_pad / KC;
@@ -336,27 +344,32 @@ int dec_tail_launch(bdrc_ctx* ctx, const bf16* x, int N, int H, int W, int C, co
   DecTailParams p;
   p.n_img = N; p.H = H; p.W = W; p.C = C; p.chunks = chunks;
   p.tiles_x = W / TW; p.tiles_y = H / TH; p.total_tiles = N * p.tiles_x * p.tiles_y;
-  p.dw_w = dw_w9c; p.bias = pw.b; p.head_w = head_w_f32; p.head_b = head_b; p.out = out; p.head_C = head_C;
+  p.dw_w = dw_w9c; p.out = out; p.head_C = head_C;
   p.idesc = make_idesc_bf16(128, 256);
   p.errflag = ctx->d_errflag;
-  const size_t smem = 1024 + 2 * B_BYTES + 2 * A_BYTES + HS * HALO_BYTES + (size_t)(9 * chunks * KC + 256 + MAX_HEAD * 256) * 4 +
-                      21 * 8 + 64;
+  const size_t smem = 1024 + 2 * B_BYTES + 2 * A_BYTES + HS * HALO_BYTES + (size_t)(9 * chunks * KC) * 4 + 21 * 8 + 64;
   BDRC_REQUIRE(ctx, smem <= 226 * 1024, "dec_tail: shared memory budget exceeded");
   const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto hc_tag) -> int {
+    constexpr int HC = decltype(hc_tag)::value;
+    auto kern = dec_tail_kernel<HC>;
+    TailConsts<HC> k;
+    memcpy(k.bias, bias_host, sizeof(k.bias));
+    memcpy(k.head_b, head_b_host, sizeof(k.head_b));
+    memcpy(k.head_w, head_w_host, sizeof(k.head_w));
     BDRC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    kern<<<grid, DT_THREADS, smem, s>>>(mapX, mapW, p);
+    kern<<<grid, DT_THREADS, smem, s>>>(mapX, mapW, p, k);
     BDRC_CHECK_LAUNCH(ctx);
     return 0;
   };
   switch (head_C) {
-    case 1: return launch(dec_tail_kernel<1>);
-    case 2: return launch(dec_tail_kernel<2>);
-    case 3: return launch(dec_tail_kernel<3>);
-    case 4: return launch(dec_tail_kernel<4>);
-    case 5: return launch(dec_tail_kernel<5>);
-    case 6: return launch(dec_tail_kernel<6>);
-    case 7: return launch(dec_tail_kernel<7>);
-    default: return launch(dec_tail_kernel<8>);
+    case 1: return launch(std::integral_constant<int, 1>{});
+    case 2: return launch(std::integral_constant<int, 2>{});
+    case 3: return launch(std::integral_constant<int, 3>{});
+    case 4: return launch(std::integral_constant<int, 4>{});
+    case 5: return launch(std::integral_constant<int, 5>{});
+    case 6: return launch(std::integral_constant<int, 6>{});
+    case 7: return launch(std::integral_constant<int, 7>{});
+    default: return launch(std::integral_constant<int, 8>{});
   }
 }

@@ -74,6 +74,7 @@ struct bdrc_model {
   float* proj_b = nullptr;
   float* head_wf = nullptr;       // [C][256] fp32 holding the bf16-rounded head weights (fused decoder tail)
   float* head_bf = nullptr;       // [C]
+  std::vector<float> tail_bias_h, head_w_h, head_b_h;   // host copies: kernel parameters of the fused decoder tail
   int ocr_in_h = 0;
 };
 
@@ -222,6 +223,11 @@ int load_seg(Loader& L, int n_classes) {
     for (size_t i = 0; i < hw->numel; ++i) wf[i] = __bfloat162float(__float2bfloat16(hw->data[i]));   // as conv_pack_weights stores them
     BDRC_TRY(dev_copy(ctx, m, wf, &m->head_wf));
     BDRC_TRY(dev_copy(ctx, m, std::vector<float>(hb->data, hb->data + n_classes), &m->head_bf));
+    const BlobTensor* tb = L.get("decoder.block2.0.1.bias", {256});
+    if (!tb) return BDRC_ERR_WEIGHTS;
+    m->tail_bias_h.assign(tb->data, tb->data + 256);
+    m->head_w_h = wf;
+    m->head_b_h.assign(hb->data, hb->data + n_classes);
   }
   return 0;
 }
@@ -448,7 +454,7 @@ int seg_forward_chunk(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n, in
     // one kernel: the 304- and 256-channel activations of this resolution never reach HBM (dec_tail.cu)
     bdrc_prof_begin(ctx, "dec.tail dw3x3+1x1+head", 2.0 * n * 128 * 128 * (304.0 * 9 + 256.0 * 304 + (double)C * 256), s);
     BDRC_TRY(dec_tail_launch(ctx, dcat, n, 128, 128, 304, m->dw["decoder.block2.0.0"].w9c, m->conv["decoder.block2.0.1"],
-                             m->head_wf, m->head_bf, C, low, s));
+                             m->tail_bias_h.data(), m->head_w_h.data(), m->head_b_h.data(), C, low, s));
     bdrc_prof_end(ctx, s);
   } else {
     bdrc_prof_begin(ctx, "dec.dw3x3", 2.0 * n * 128 * 128 * 304 * 9, s);

@@ -60,4 +60,5 @@ int aspp_dw3_launch(bdrc_ctx* ctx, const bf16* x, int N, int C, const int rates[
 // the bf16-rounded head weights; out: fp32 NHWC [N][H][W][head_C].
 int dec_tail_supported(int C, int Cout, int head_C, int H, int W);
 int dec_tail_launch(bdrc_ctx* ctx, const bf16* x, int N, int H, int W, int C, const float* dw_w9c, const ConvWeights& pw,
-                    const float* head_w_f32, const float* head_b, int head_C, float* out, cudaStream_t s);
+                    const float* bias_host, const float* head_w_host, const float* head_b_host, int head_C, float* out,
+                    cudaStream_t s);
