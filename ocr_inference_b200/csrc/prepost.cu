@@ -303,61 +303,83 @@ struct PostBatch {
 };
 
 __global__ void __launch_bounds__(256) seg_post_line_lowres_batch_kernel(const PostBatch b) {
-  // block = 64 units x 4 rows, grid = (units / 64, rows / 4, pages): no index division anywhere
+  // block = 64 units x 4 row quads, grid = (units / 64, rows / 16, pages): no index division anywhere.
+  // A thread owns 16 pixels of FOUR consecutive rows (4 | P: one tile): the four rows interpolate between at most
+  // three low-res rows, so 3 x <= 6 corner loads settle 64 pixels (one row per thread needed 12 loads per 16 pixels
+  // and ran at 0.20 of the HBM roofline, bound by load instructions, not bytes).
   const PostPage pg = b.pg[blockIdx.z];
-  const int y = blockIdx.y * 4 + threadIdx.y;
+  const int yq = (blockIdx.y * 4 + threadIdx.y) * 4;
   const int x16 = (blockIdx.x * 64 + threadIdx.x) * 16;
-  if (y >= pg.H0 || x16 >= pg.W0) return;
+  if (yq >= pg.H0 || x16 >= pg.W0) return;
   const int P = b.P, L = P / 4;
-  const int ty = y / P, yy = y - ty * P, tx = x16 / P, xx0 = x16 - tx * P;
+  const int ty = yq / P, yy0 = yq - ty * P, tx = x16 / P, xx0 = x16 - tx * P;
   const float sc = (float)(L - 1) / (float)(P - 1);
-  const float fy = sc * (float)yy;
-  const int y0 = (int)fy, y1 = y0 + (y0 < L - 1 ? 1 : 0);
-  const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
   const float* t = pg.logits + (size_t)(ty * pg.ntx + tx) * L * L;
-  const float* r0 = t + y0 * L;
-  const float* r1 = t + y1 * L;
   const int n = min(16, pg.W0 - x16);
   const int xa = (int)(sc * (float)xx0);
   const int xb = min((int)(sc * (float)(xx0 + n - 1)) + 1, L - 1);
-  float mn = INFINITY, mx = -INFINITY;
-  bool ordered = true;
-  for (int k = xa; k <= xb; ++k) {
-    const float v0 = __ldg(r0 + k), v1 = __ldg(r1 + k);
-    ordered = ordered && (v0 == v0) && (v1 == v1);
-    mn = fminf(mn, fminf(v0, v1));
-    mx = fmaxf(mx, fmaxf(v0, v1));
+  const int ya = (int)(sc * (float)yy0);
+  // per low-res row ya + r: min / max of the corners xa .. xb, and whether they are all ordered (no NaN)
+  float mn[3], mx[3];
+  bool ord[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float* rp = t + min(ya + r, L - 1) * L;
+    float lo = INFINITY, hi = -INFINITY;
+    bool o = true;
+    for (int k = xa; k <= xb; ++k) {
+      const float v = __ldg(rp + k);
+      o = o && (v == v);
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+    mn[r] = lo; mx[r] = hi; ord[r] = o;
   }
   const float thr = b.thr_logit;
-  const float margin = 1e-5f * fmaxf(fmaxf(fabsf(mn), fabsf(mx)), fabsf(thr)) + 1e-30f;
-  uint32_t bits;
-  if (ordered && mn >= thr + margin && mx < INFINITY) {
-    bits = 0xFFFFu;
-  } else if (ordered && mx < thr - margin && mn > -INFINITY) {
-    bits = 0u;
-  } else {
-    bits = 0u;
-    for (int j = 0; j < n; ++j) {
-      const float fx = sc * (float)(xx0 + j);
-      const int x0 = (int)fx, x1 = x0 + (x0 < L - 1 ? 1 : 0);
-      const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
-      const float v = bdrc_bilerp(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), lx0, lx1, ly0, ly1);
-      bits |= (v >= thr ? 1u : 0u) << j;
-    }
-  }
-  uint8_t* o = pg.mask + (size_t)y * pg.W0 + x16;
-  if (n == 16 && (pg.W0 & 15) == 0) {
-    uint4 v;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  const bool wide = n == 16 && (pg.W0 & 15) == 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t c = (bits >> (4 * q)) & 15u;
-      w[q] = ((c & 1u) ? 0x000000FFu : 0u) | ((c & 2u) ? 0x0000FF00u : 0u) | ((c & 4u) ? 0x00FF0000u : 0u) |
-             ((c & 8u) ? 0xFF000000u : 0u);
+  for (int i = 0; i < 4; ++i) {
+    const int y = yq + i;
+    if (y >= pg.H0) break;
+    const float fy = sc * (float)(yy0 + i);
+    const int y0 = (int)fy, y1 = y0 + (y0 < L - 1 ? 1 : 0);
+    const int ra = y0 - ya, rb = y1 - ya;                 // 0 / 1 and ra / ra + 1
+    const float lo = fminf(ra == 0 ? mn[0] : mn[1], rb == 0 ? mn[0] : rb == 1 ? mn[1] : mn[2]);
+    const float hi = fmaxf(ra == 0 ? mx[0] : mx[1], rb == 0 ? mx[0] : rb == 1 ? mx[1] : mx[2]);
+    const bool ordered = (ra == 0 ? ord[0] : ord[1]) && (rb == 0 ? ord[0] : rb == 1 ? ord[1] : ord[2]);
+    const float margin = 1e-5f * fmaxf(fmaxf(fabsf(lo), fabsf(hi)), fabsf(thr)) + 1e-30f;
+    uint32_t bits;
+    if (ordered && lo >= thr + margin && hi < INFINITY) {
+      bits = 0xFFFFu;
+    } else if (ordered && hi < thr - margin && lo > -INFINITY) {
+      bits = 0u;
+    } else {
+      const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+      const float* r0 = t + y0 * L;
+      const float* r1 = t + y1 * L;
+      bits = 0u;
+      for (int j = 0; j < n; ++j) {
+        const float fx = sc * (float)(xx0 + j);
+        const int x0 = (int)fx, x1 = x0 + (x0 < L - 1 ? 1 : 0);
+        const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+        const float v = bdrc_bilerp(__ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1), lx0, lx1, ly0, ly1);
+        bits |= (v >= thr ? 1u : 0u) << j;
+      }
     }
-    *reinterpret_cast<uint4*>(o) = v;
-  } else {
-    for (int j = 0; j < n; ++j) o[j] = ((bits >> j) & 1u) ? 255 : 0;
+    uint8_t* o = pg.mask + (size_t)y * pg.W0 + x16;
+    if (wide) {
+      uint4 v;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t c = (bits >> (4 * q)) & 15u;
+        w[q] = ((c & 1u) ? 0x000000FFu : 0u) | ((c & 2u) ? 0x0000FF00u : 0u) | ((c & 4u) ? 0x00FF0000u : 0u) |
+               ((c & 8u) ? 0xFF000000u : 0u);
+      }
+      *reinterpret_cast<uint4*>(o) = v;
+    } else {
+      for (int j = 0; j < n; ++j) o[j] = ((bits >> j) & 1u) ? 255 : 0;
+    }
   }
 }
 
@@ -835,7 +857,7 @@ int bdrc_seg_postprocess_lowres_batch(bdrc_ctx* ctx, const float* const* logits_
       if (Wc[i] > max_w) max_w = Wc[i];
       if (Hc[i] > max_h) max_h = Hc[i];
     }
-    dim3 grid((unsigned)ceil_div(ceil_div(max_w, 16), 64), (unsigned)ceil_div(max_h, 4), (unsigned)n);
+    dim3 grid((unsigned)ceil_div(ceil_div(max_w, 16), 64), (unsigned)ceil_div(max_h, 16), (unsigned)n);
     bdrc_prof_begin(ctx, "a-3.seg_post", 0, s);
     seg_post_line_lowres_batch_kernel<<<grid, dim3(64, 4), 0, s>>>(b);
     bdrc_prof_end(ctx, s);
