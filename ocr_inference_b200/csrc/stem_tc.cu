@@ -203,7 +203,10 @@ stem_tc_pool_kernel(const uint8_t* __restrict__ in, int N, const bf16* __restric
       const int q = warp >> 2;
       float b[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) b[j] = sBias[q * 16 + j];
+      for (int j = 0; j < 16; j += 4) {   // 16-byte broadcast loads: the kernel is bound by shared-memory wavefronts
+        const float4 b4 = *reinterpret_cast<const float4*>(sBias + q * 16 + j);
+        b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
+      }
       // rows that are not stem pixels of the image store zeros (exact for the max: every window holds a valid value >= 0)
       const uint32_t dead = (~ep_flags & 7u) | (py0 == 0 ? (ep_flags >> 4) & 7u : 0u) | (px0 == 0 ? (ep_flags >> 8) & 7u : 0u);
 #pragma unroll
