@@ -305,8 +305,9 @@ struct PostBatch {
 __global__ void __launch_bounds__(256) seg_post_line_lowres_batch_kernel(const PostBatch b) {
   // block = 64 units x 4 row quads, grid = (units / 64, rows / 16, pages): no index division anywhere.
   // A thread owns 16 pixels of FOUR consecutive rows (4 | P: one tile): the four rows interpolate between at most
-  // three low-res rows, so 3 x <= 6 corner loads settle 64 pixels (one row per thread needed 12 loads per 16 pixels
-  // and ran at 0.20 of the HBM roofline, bound by load instructions, not bytes).
+  // three low-res rows, so 3 x 6 corner loads settle 64 pixels.  ncu (profiles/r02b): the kernel is bound by the
+  // instructions of the per-pixel path, not by bytes -- on logits with sigma = 0.5 noise a fifth of the rows straddle
+  // the threshold and evaluate 16 x ~30 instructions; rows away from band edges cost ~40.
   const PostPage pg = b.pg[blockIdx.z];
   const int yq = (blockIdx.y * 4 + threadIdx.y) * 4;
   const int x16 = (blockIdx.x * 64 + threadIdx.x) * 16;
@@ -325,13 +326,19 @@ __global__ void __launch_bounds__(256) seg_post_line_lowres_batch_kernel(const P
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const float* rp = t + min(ya + r, L - 1) * L;
-    float lo = INFINITY, hi = -INFINITY;
-    bool o = true;
-    for (int k = xa; k <= xb; ++k) {
-      const float v = __ldg(rp + k);
-      o = o && (v == v);
-      lo = fminf(lo, v);
-      hi = fmaxf(hi, v);
+    // 16 pixels span at most 6 low-res columns (16 * 127 / 511 < 4): six unconditional loads with the index clamped
+    // to xb, so that all 18 loads of the thread are in flight together (a loop with run-time bounds issued them one
+    // L2 round trip after the other)
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = __ldg(rp + min(xa + k, xb));
+    float lo = v[0], hi = v[0];
+    bool o = v[0] == v[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+      o = o && (v[k] == v[k]);
+      lo = fminf(lo, v[k]);
+      hi = fmaxf(hi, v[k]);
     }
     mn[r] = lo; mx[r] = hi; ord[r] = o;
   }
