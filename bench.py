@@ -960,9 +960,9 @@ def run_ours(args, rank, world, local_rank):
         "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all layers)",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
         # dram__bytes_read.sum + dram__bytes_write.sum of the five layer-4 launches (512->512 3x3, dilation 2,
-        # 148 tiles) in profiles/r01c_conv_full_raw.csv, mean: 378 MB per launch against 315 MB of algorithmic
-        # input + output + weight bytes (conv2 of a block also reads the residual: +155 MB on 2 of the 5)
-        "traffic": 378.4e6, "traffic_launch": "r34.conv3x3 512->512 @32x32 d2, 148 tiles", "traffic_algorithmic": 315.1e6,
+        # 148 tiles) in profiles/r02c_seg_convs_full_raw.csv (IDs 31-35), mean: 381 MB per launch against 315 MB of
+        # algorithmic input + output + weight bytes (conv2 of a block also reads the residual: +155 MB on 3 of the 5)
+        "traffic": 381.0e6, "traffic_launch": "r34.conv3x3 512->512 @32x32 d2, 148 tiles", "traffic_algorithmic": 315.1e6,
         "launches": len(tc), "avg_launch_ms": tc_ms / max(1, len(tc)),
         "share_of_network_time": tc_ms / all_ms if all_ms else None,
         "share_of_step": tc_ms / ms_profiled if ms_profiled else None,
