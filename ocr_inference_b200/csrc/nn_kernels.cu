@@ -371,22 +371,19 @@ aspp_dw3_kernel(const __grid_constant__ CUtensorMap tmap, int C, int r0, int r1,
 #pragma unroll 1
   for (int b = 0; b < 3; ++b) {
     const int d = rates[b];
-    float w[9][8];
+    // channel pairs as packed fp32x2 operands (each half an IEEE fmaf, same order of taps): half the FMA instructions
+    ulonglong2 w[9][2];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(ws[b] + k * C + ch * ASPP_CH + c8 * 8));
-      const float4 c = __ldg(reinterpret_cast<const float4*>(ws[b] + k * C + ch * ASPP_CH + c8 * 8 + 4));
-      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-      w[k][4] = c.x; w[k][5] = c.y; w[k][6] = c.z; w[k][7] = c.w;
+      w[k][0] = __ldg(reinterpret_cast<const ulonglong2*>(ws[b] + k * C + ch * ASPP_CH + c8 * 8));
+      w[k][1] = __ldg(reinterpret_cast<const ulonglong2*>(ws[b] + k * C + ch * ASPP_CH + c8 * 8 + 4));
     }
     bf16* ob = outs[b] + (size_t)n * ASPP_HW * ASPP_HW * C + ch * ASPP_CH + c8 * 8;
 #pragma unroll 2
     for (int j = 0; j < ITERS; ++j) {
       const int p = g + ASPP_GROUPS * j;      // a warp covers 8 consecutive pixels: 512 contiguous bytes of the slab
       const int y = p / ASPP_HW, x = p % ASPP_HW;
-      float acc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int iy = y + (r - 1) * d;
@@ -395,46 +392,67 @@ aspp_dw3_kernel(const __grid_constant__ CUtensorMap tmap, int C, int r0, int r1,
         for (int s = 0; s < 3; ++s) {
           const int ix = x + (s - 1) * d;
           if (ix < 0 || ix >= ASPP_HW) continue;
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(slab + (size_t)(iy * ASPP_HW + ix) * ASPP_PXB + c8 * 16), f);
+          const uint4 v = *reinterpret_cast<const uint4*>(slab + (size_t)(iy * ASPP_HW + ix) * ASPP_PXB + c8 * 16);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+          const ulonglong2 w0 = w[r * 3 + s][0], w1 = w[r * 3 + s][1];
+          const uint64_t wk[4] = {w0.x, w0.y, w1.x, w1.y};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = fmaf(f[q], w[r * 3 + s][q], acc[q]);
+          for (int q = 0; q < 4; ++q) {
+            uint64_t f2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "r"(u[q] << 16), "r"(u[q] & 0xFFFF0000u));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[q]) : "l"(f2), "l"(wk[q]));
+          }
         }
       }
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * q]), "=f"(acc[2 * q + 1]) : "l"(acc2[q]));
       *reinterpret_cast<uint4*>(ob + (size_t)p * C) = pack8(acc);
     }
   }
 }
 
 // x4 (or xf) align_corners=True upsample, strip variant: each thread produces UP_STRIP consecutive
-// output rows of one column for 8 channels and re-loads a low-res row pair only when it changes
+// output rows of one column for 8 channels and re-loads a low-res row pair only when it changes.
+// grid = (columns x channel groups / 256, strips, images): everything that depends on the output row -- the
+// source rows, the vertical weights, whether a low-res row has to be (re)loaded -- is uniform over the block, so
+// it lives in uniform registers and the row-change tests are uniform branches (ncu r01c: this kernel used 77 % of
+// the issue slots with ~117 instructions per 16-byte store when the row was derived from a flat thread index).
 constexpr int UP_STRIP = 8;
 __global__ void __launch_bounds__(256)
-upsample_ac_strip_kernel(const bf16* __restrict__ in, int N, int H, int W, int C, int f, bf16* __restrict__ out,
+upsample_ac_strip_kernel(const bf16* __restrict__ in, int H, int W, int C, int f, bf16* __restrict__ out,
                          int out_ld, int out_coff) {
   const int Ho = H * f, Wo = W * f, C8 = C / 8;
-  const int strips = (Ho + UP_STRIP - 1) / UP_STRIP;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)N * strips * Wo * C8;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  size_t p = idx / C8;
-  const int x = (int)(p % Wo); p /= Wo;
-  const int st = (int)(p % strips);
-  const int n = (int)(p / strips);
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= Wo * C8) return;
+  const int x = e / C8, c8 = e - x * C8;
+  const int st = blockIdx.y, n = blockIdx.z;
   const float sy = (float)(H - 1) / (float)(Ho - 1), sx = (float)(W - 1) / (float)(Wo - 1);
   const float fx = sx * (float)x;
   const int x0 = (int)fx, x1 = x0 + (x0 < W - 1 ? 1 : 0);
   const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
-  const bf16* b = in + (size_t)n * H * W * C + c8 * 8;
+  const bf16* b0 = in + ((size_t)n * H * W + x0) * C + c8 * 8;
+  const bf16* b1 = in + ((size_t)n * H * W + x1) * C + c8 * 8;
+  bf16* op = out + (((size_t)n * Ho + st * UP_STRIP) * Wo + x) * out_ld + out_coff + c8 * 8;
+  const size_t orow = (size_t)Wo * out_ld;
   int cy0 = -1, cy1 = -1;
-  float a0[8], a1[8];   // horizontally interpolated low-res rows cy0 / cy1
-  auto hrow = [&](int yy, float* dst) {
+  // both interpolations as packed fp32x2 operations on channel pairs (each half an IEEE mul / fma): the kernel is bound
+  // by instruction issue, and the packed forms halve the 32 multiply-adds per stored 16 bytes
+  auto pk = [](float lo, float hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; };
+  auto mul2 = [](uint64_t x, uint64_t y) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y)); return d; };
+  auto fma2 = [](uint64_t x, uint64_t y, uint64_t z) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
+    return d;
+  };
+  const uint64_t LX0 = pk(lx0, lx0), LX1 = pk(lx1, lx1);
+  uint64_t a0[4], a1[4];   // horizontally interpolated low-res rows cy0 / cy1
+  auto hrow = [&](int yy, uint64_t* dst) {
     float v0[8], v1[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)yy * W + x0) * C)), v0);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)yy * W + x1) * C)), v1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b0 + (size_t)yy * W * C)), v0);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b1 + (size_t)yy * W * C)), v1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = lx0 * v0[j] + lx1 * v1[j];
+    for (int j = 0; j < 4; ++j) dst[j] = fma2(LX1, pk(v1[2 * j], v1[2 * j + 1]), mul2(LX0, pk(v0[2 * j], v0[2 * j + 1])));
   };
 #pragma unroll
   for (int i = 0; i < UP_STRIP; ++i) {
@@ -446,7 +464,7 @@ upsample_ac_strip_kernel(const bf16* __restrict__ in, int N, int H, int W, int C
     if (y0 != cy0) {
       if (y0 == cy1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a0[j] = a1[j];
+        for (int j = 0; j < 4; ++j) a0[j] = a1[j];
       } else {
         hrow(y0, a0);
       }
@@ -455,16 +473,23 @@ upsample_ac_strip_kernel(const bf16* __restrict__ in, int N, int H, int W, int C
     if (y1 != cy1) {
       if (y1 == cy0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a1[j] = a0[j];
+        for (int j = 0; j < 4; ++j) a1[j] = a0[j];
       } else {
         hrow(y1, a1);
       }
       cy1 = y1;
     }
-    float r[8];
+    const uint64_t LY0 = pk(ly0, ly0), LY1 = pk(ly1, ly1);
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = ly0 * a0[j] + ly1 * a1[j];
-    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + y) * Wo + x) * out_ld + out_coff + c8 * 8) = pack8(r);
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t r = fma2(LY1, a1[j], mul2(LY0, a0[j]));
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+      const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(op + (size_t)i * orow) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -795,8 +820,9 @@ int aspp_dw3_launch(bdrc_ctx* ctx, const bf16* x, int N, int C, const int rates[
 int upsample_bilinear_ac_launch(bdrc_ctx* ctx, const bf16* in, int N, int H, int W, int C, int f,
                                 bf16* out, int out_ld, int out_coff, cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0, "upsample: C %% 8 != 0");
-  const size_t total = (size_t)N * ((H * f + UP_STRIP - 1) / UP_STRIP) * W * f * (C / 8);
-  upsample_ac_strip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, N, H, W, C, f, out, out_ld, out_coff);
+  const dim3 grid((unsigned)ceil_div(W * f * (C / 8), 256), (unsigned)ceil_div(H * f, UP_STRIP), (unsigned)N);
+  BDRC_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "upsample: too many strips / images for one launch");
+  upsample_ac_strip_kernel<<<grid, 256, 0, s>>>(in, H, W, C, f, out, out_ld, out_coff);
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }
