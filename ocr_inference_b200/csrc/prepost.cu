@@ -2,6 +2,7 @@
 // networks): tiling + adaptive-threshold binarisation, mask thresholding / stitching / resize,
 // cv2-exact bilinear resize, OCR line preparation and greedy CTC decode.
 #include "adaptive.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -626,6 +627,104 @@ ctc_topk_kernel(const float* __restrict__ logits, int L, int V, int T, int layou
   if (lane == 0) cnt[(size_t)l * T + t] = n;
 }
 
+// [T][V] logits of a page batch (the layout the Easter2 head writes): one persistent CTA per SM walks over lines.
+// A line is cut into groups of 32 time steps; warp w owns groups w and w + CTCB_WARPS and one shared-memory slot for
+// each.  A group lands in its slot by ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on the
+// slot's mbarrier: no registers, no instructions per byte); the warp takes the argmax of the group's rows (lane = row;
+// the row pitch V is odd for the 77-symbol charset: conflict-free) and at once re-arms the slot with the same group of
+// the CTA's NEXT line, so the copy of one slot runs under the argmax of the other and a whole line (154 KB) per SM
+// stays in flight while the collapse of the current one runs.  Collapse: keep flags by ballot, per-group counts, a
+// 16-entry prefix, kept ids written in time order.  Bit-equal to the serial scan (first maximum wins, a NaN counts as
+// the maximum).  Needs 16-byte aligned groups ((V * T) % 4 == 0, aligned base), T <= 64 * CTCB_WARPS and 2 * CTCB_WARPS
+// slots of 128 V bytes; bdrc_ctc_greedy falls back to the staged kernel below otherwise.
+constexpr int CTCB_WARPS = 8;
+constexpr int CTCB_GROUPS = 2 * CTCB_WARPS;
+__global__ void __launch_bounds__(CTCB_WARPS * 32, 1)
+ctc_greedy_bulk_kernel(const float* __restrict__ logits, int L, int V, int T, int blank, int32_t* __restrict__ ids,
+                       int32_t* __restrict__ lens, int* errflag) {
+  extern __shared__ __align__(128) uint8_t ctcb_sm[];
+  const uint32_t slot_bytes = 128u * (uint32_t)V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctcb_sm + (size_t)CTCB_GROUPS * slot_bytes);
+  int* am = reinterpret_cast<int*>(bars + CTCB_GROUPS);         // [2][32 * CTCB_GROUPS] argmax per step
+  int* wcnt = am + 2 * 32 * CTCB_GROUPS;                        // [2][CTCB_GROUPS] kept symbols per group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (T + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CTCB_GROUPS; ++i) tcptx::mbar_init(tcptx::smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](int l, int g) {
+    const uint32_t bytes = (uint32_t)min(32, T - 32 * g) * (uint32_t)V * 4u;
+    const uint32_t bar = tcptx::smem_u32(&bars[g]);
+    tcptx::mbar_arrive_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tcptx::smem_u32(ctcb_sm + (size_t)g * slot_bytes)),
+                   "l"(reinterpret_cast<uint64_t>(logits + ((size_t)l * T + 32 * g) * V)), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0 && (int)blockIdx.x < L) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (warp + h * CTCB_WARPS < G) fetch((int)blockIdx.x, warp + h * CTCB_WARPS);
+  }
+  uint32_t phase = 0;
+  int buf = 0;
+  for (int l = blockIdx.x; l < L; l += gridDim.x, buf ^= 1, phase ^= 1) {
+    int* amb = am + buf * 32 * CTCB_GROUPS;
+    int* wc = wcnt + buf * CTCB_GROUPS;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = warp + h * CTCB_WARPS;
+      if (g >= G) break;
+      tcptx::mbar_wait(tcptx::smem_u32(&bars[g]), phase, errflag, 9);
+      if (lane < T - 32 * g) {
+        const float* row = reinterpret_cast<const float*>(ctcb_sm + (size_t)g * slot_bytes) + lane * V;
+        // first maximum among the numbers (strict >), first NaN beside it: a NaN wins like in np.argmax
+        float bv = row[0];
+        int bi = 0, ni = bv != bv ? 0 : V;
+#pragma unroll 7
+        for (int v = 1; v < V; ++v) {
+          const float x = row[v];
+          if (x > bv) { bv = x; bi = v; }                 // never true for a NaN on either side
+          if (x != x) ni = min(ni, v);
+        }
+        amb[32 * g + lane] = ni < V ? ni : bi;
+      }
+      __syncwarp();
+      if (lane == 0 && l + (int)gridDim.x < L) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's reads of the slot before the copy's writes
+        fetch(l + (int)gridDim.x, g);
+      }
+    }
+    __syncthreads();
+    uint32_t masks[2];
+    int idv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = warp + h * CTCB_WARPS, t = 32 * g + lane;
+      const bool in = g < G && t < T;
+      idv[h] = in ? amb[t] : blank;
+      const bool keep = in && idv[h] != blank && (t == 0 || idv[h] != amb[t - 1]);
+      masks[h] = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) wc[g] = __popc(masks[h]);
+    }
+    __syncthreads();
+    const int cnt = lane < CTCB_GROUPS ? wc[lane] : 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = warp + h * CTCB_WARPS;
+      int before = lane < g ? cnt : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+      if ((masks[h] >> lane) & 1u) ids[(size_t)l * T + before + __popc(masks[h] & ((1u << lane) - 1u))] = idv[h];
+      if (g == G - 1 && lane == 0) lens[l] = before + __popc(masks[h]);
+    }
+    // am / wcnt are double-buffered: the next line's writes go to the other half, and a warp is two barriers
+    // past this line's reads before it writes this half again
+  }
+}
+
 constexpr int CTC_ROWS = 128;
 __global__ void __launch_bounds__(512)
 ctc_greedy_kernel(const float* __restrict__ logits, int V, int T, int layout, int blank,
@@ -950,6 +1049,24 @@ int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int
   BDRC_REQUIRE(ctx, logits && ids && lens && V > 0 && T > 0 && T <= 20000 &&
                         (layout == BDRC_LAYOUT_TV || layout == BDRC_LAYOUT_VT),
                "ctc_greedy: bad arguments (V=%d T=%d)", V, T);
+  if (layout == BDRC_LAYOUT_TV && T <= 32 * CTCB_GROUPS && ((long long)V * T) % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const size_t bsmem = (size_t)CTCB_GROUPS * 128 * V + CTCB_GROUPS * sizeof(uint64_t) +
+                         (size_t)(2 * 32 * CTCB_GROUPS + 2 * CTCB_GROUPS) * sizeof(int);
+    if (bsmem <= 220 * 1024) {
+      static size_t attr_bytes = 0;
+      if (bsmem > attr_bytes) {
+        BDRC_CUDA(ctx, cudaFuncSetAttribute(ctc_greedy_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_bytes = 220 * 1024;
+      }
+      bdrc_prof_begin(ctx, "a-9.ctc_greedy", 0, (cudaStream_t)stream);
+      ctc_greedy_bulk_kernel<<<L < ctx->sm_count ? L : ctx->sm_count, CTCB_WARPS * 32, bsmem, (cudaStream_t)stream>>>(
+          logits, L, V, T, blank, ids, lens, ctx->d_errflag);
+      bdrc_prof_end(ctx, (cudaStream_t)stream);
+      BDRC_CHECK_LAUNCH(ctx);
+      return 0;
+    }
+  }
   const size_t smem = (size_t)2 * T * sizeof(int) +
                       (layout == BDRC_LAYOUT_TV ? (size_t)CTC_ROWS * (V | 1) * sizeof(float) : 0);
   BDRC_REQUIRE(ctx, smem <= 200 * 1024, "ctc_greedy: V * 128 + 2 T exceeds the shared-memory budget (V=%d T=%d)", V, T);

@@ -108,7 +108,8 @@ def test_ocr_prepare_lines_bit_exact(engine, pre_pad):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("L,V,T", [(1, 77, 500), (7, 77, 500), (3, 5, 33), (2, 200, 1000), (4, 77, 1)])
+@pytest.mark.parametrize("L,V,T", [(1, 77, 500), (7, 77, 500), (3, 5, 33), (2, 200, 1000), (4, 77, 1),
+                                   (450, 77, 500), (5, 76, 512), (3, 8, 130), (2, 77, 36)])
 def test_ctc_greedy_bit_exact(engine, layout, L, V, T):
     rng = np.random.default_rng(L * 1000 + V + T)
     logits = rng.normal(0, 1, (L, T, V)).astype(np.float32)
@@ -118,6 +119,13 @@ def test_ctc_greedy_bit_exact(engine, layout, L, V, T):
         logits[0, 20:30, 3] = 9.0               # a repeated label that must collapse
         logits[0, 30, 0] = 20.0
         logits[0, 31:35, 3] = 9.0               # same label after a blank must be emitted again
+    if T > 40 and L > 1 and V > 9:
+        logits[1, 5, 7] = np.nan                # a NaN counts as the maximum (np.argmax), the first one wins
+        logits[1, 5, 9] = np.nan
+        logits[1, 6, 0] = np.nan                # ... also in column 0
+        logits[1, 7, 2] = -0.0                  # -0.0 == 0.0: the first of the two wins
+        logits[1, 7, :] = np.minimum(logits[1, 7, :], 0.0)
+        logits[1, 7, 4] = 0.0
     dev = _dev(logits if layout == 0 else np.ascontiguousarray(logits.transpose(0, 2, 1)))
     ids, lens = engine.ctc_greedy(dev, layout=layout, blank=0)
     ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
