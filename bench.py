@@ -28,6 +28,7 @@ import argparse
 import json
 import os
 import sys
+import threading
 import time
 
 import numpy as np
@@ -816,6 +817,38 @@ def bench_c4(eng, steps: int = 2):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+C5_DEADLINE_S = 240
+
+
+class Deadline:
+    """Arms a timer: unless cancel() comes first, `on_timeout` runs (if given) and the PROCESS exits with code 0.
+    seconds=None arms nothing."""
+
+    def __init__(self, seconds, on_timeout=None, _exit=os._exit):
+        self._timer = None
+        if seconds is None:
+            return
+
+        def fire():
+            try:
+                if on_timeout:
+                    on_timeout()
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] deadline callback failed: {e!r}", file=sys.stderr)
+            finally:
+                sys.stdout.flush()
+                sys.stderr.flush()
+                _exit(0)
+
+        self._timer = threading.Timer(seconds, fire)
+        self._timer.daemon = True
+        self._timer.start()
+
+    def cancel(self):
+        if self._timer is not None:
+            self._timer.cancel()
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -926,19 +959,46 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, iob_ms = float(t[0]), float(t[1]), float(t[2])
 
+    def finish(c5_block, side: bool):
+        _emit_line(args, world, eng, sampler, pages, out, prof, ms, ms_profiled, e2e_ms, iob_ms, launches, checksum,
+                   c5_block, side)
+
     # ---- C5: the page-sharded page -> text run, at every N ----------------------------------------------
+    # Under torchrun a rank that fails or stalls inside C5 would leave the others waiting in a collective and the job
+    # without its JSON line; every rank therefore arms a deadline: when it passes, rank 0 prints the headline with
+    # c5 = {"error": ...} and every rank leaves with exit code 0.
     c5 = None
+    c5_failed = False
     if args.extras:
+        guard = Deadline(C5_DEADLINE_S if world > 1 else None,
+                         (lambda: finish({"error": f"C5 did not finish within {C5_DEADLINE_S} s on {world} ranks"},
+                                         side=False)) if rank == 0 else None)
         try:
             c5 = bench_c5(eng, rank, world, sampler)
         except Exception as e:  # noqa: BLE001  (the headline must still print)
             c5 = {"error": repr(e)}
-            if world > 1:
-                raise
+            c5_failed = True
+            print(f"[bench rank {rank}] C5 failed: {e!r}", file=sys.stderr, flush=True)
+        finally:
+            guard.cancel()
     if rank != 0:
         if world > 1:
+            if c5_failed:
+                os._exit(0)          # peers may be stuck in a collective of C5: no orderly shutdown to wait for
             dist.destroy_process_group()
         return
+    finish(c5, side=True)
+    if world > 1:
+        if c5_failed:
+            sys.stdout.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
+
+def _emit_line(args, world, eng, sampler, pages, out, prof, ms, ms_profiled, e2e_ms, iob_ms, launches, checksum, c5,
+               side: bool):
+    """Rank 0: assemble and print the ONE JSON line.  side=False (C5 deadline path) skips every further measurement."""
+    from ocr_inference_b200.synthetic_weights import seg_flops_per_tile
 
     total_pages = PAGES_PER_STEP * args.steps * world
     value = total_pages / (ms / 1e3)
@@ -972,10 +1032,10 @@ def run_ours(args, rank, world, local_rank):
                           "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 and v[1] > 0 else None)}
                       for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},
     }
-    cpu_v, cpu_s, cores = cpu_reference_pages_per_sec(1) if world >= 1 and args.cpu_baseline else (None, None, None)
+    cpu_v, cpu_s, cores = cpu_reference_pages_per_sec(1) if side and args.cpu_baseline else (None, None, None)
     c1 = c3 = c4 = stages = None
     errors = {}
-    if args.extras:
+    if args.extras and side:
         for name, fn in (("roofline_stages", lambda: roofline_stages(eng)),
                          ("c1", lambda: bench_c1(eng, max(5, args.steps), 3, args.cpu_baseline) if world == 1 else None),
                          ("c3", lambda: bench_c3(eng, 5, with_cpu=args.cpu_baseline) if world == 1 else None),
@@ -1027,8 +1087,6 @@ def run_ours(args, rank, world, local_rank):
                             **({"errors": errors} if errors else {})},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

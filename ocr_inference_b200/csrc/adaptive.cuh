@@ -177,6 +177,26 @@ struct SinkOcrLines {
         if (y >= IH || x >= IW) continue;
         lines[((size_t)img * W + x) * Cpad + y] = __float2bfloat16(res[r * SW + c] ? 1.f : -1.f);
       }
+      // the padding channels IH .. Cpad-1 of this strip's columns, once, by the CTA's last block (a memset of the
+      // whole [n][W][Cpad] buffer did this before: 33 MB written twice per 64 lines)
+      if (y0 + RB >= IH && Cpad > IH) {
+        const int npad = Cpad - IH;
+        if (((IH | Cpad) & 7) == 0 && (reinterpret_cast<uintptr_t>(lines) & 15) == 0) {          // 16-byte stores: (x * Cpad + IH) * 2 B is 16-byte aligned
+          const int q = npad / 8;
+          for (int i = threadIdx.x; i < SW * q; i += THREADS) {
+            const int c = i / q, k = i - c * q;
+            const int x = x0 + c;
+            if (x < IW)
+              *reinterpret_cast<uint4*>(lines + ((size_t)img * W + x) * Cpad + IH + 8 * k) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+          for (int i = threadIdx.x; i < SW * npad; i += THREADS) {
+            const int c = i / npad, k = i - c * npad;
+            const int x = x0 + c;
+            if (x < IW) lines[((size_t)img * W + x) * Cpad + IH + k] = __float2bfloat16(0.f);
+          }
+        }
+      }
     }
     if (lines_f32) {
       for (int i = threadIdx.x; i < RB * SW; i += THREADS) {
@@ -264,7 +284,9 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
     if (b + 1 < n_blocks) prefetch(b + 1);
 
     // ---- row pass of block b: ring[row][c] = sum_k g[row][c + k] * w[k], k ascending, FMA ----
-    if (b < n_blocks) {
+    // (rows past the image bottom -- 16 of the 96 streamed rows of an 80-row OCR canvas -- are skipped by whole
+    //  warps: nobody reads their ring rows, the column pass clamps to IH - 1)
+    if (b < n_blocks && RB * b + (int)(threadIdx.x / (SW / 4)) < IH) {
       const int r = threadIdx.x / (SW / 4), c = (threadIdx.x % (SW / 4)) * 4;
       const float* gp = g + r * GSTRIDE + GOFF + c;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -296,13 +318,12 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         }
         w0 = n.x; w1 = n.y; w2 = n.z; w3 = n.w;
       }
-      if (RB * b + r < IH)
-        *reinterpret_cast<float4*>(ring + ((RB * b + r) & (RING - 1)) * SW + c) = make_float4(a0, a1, a2, a3);
+      *reinterpret_cast<float4*>(ring + ((RB * b + r) & (RING - 1)) * SW + c) = make_float4(a0, a1, a2, a3);
     }
 
     // ---- column pass + threshold of block b - 2 (its 51-row window was complete one barrier ago) ----
     const int ob = b - 2;
-    if (ob >= 0 && ob < n_blocks) {
+    if (ob >= 0 && ob < n_blocks && RB * ob + (int)(threadIdx.x / SW) * 4 < IH) {   // warp-uniform; the sinks never read res rows >= IH
       const int c = threadIdx.x % SW, r4 = RB * ob + (threadIdx.x / SW) * 4;   // output rows r4 .. r4+3
       float v[2 * KR + 4];
       if (r4 - KR >= 0 && r4 + 3 + KR < IH) {

@@ -1030,10 +1030,8 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
   ocr_canvas_kernel<<<grid, 128, 0, s>>>(crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status);
   bdrc_prof_end(ctx, s);
   BDRC_CHECK_LAUNCH(ctx);
-  bdrc_prof_begin(ctx, "a-7.zero_pad_channels", 0, s);
-  if (lines_bf16 && Cpad > Ht)   // zero the padding channels Ht..Cpad-1
-    BDRC_CUDA(ctx, cudaMemsetAsync(lines_bf16, 0, (size_t)L * Wt * Cpad * sizeof(bf16), s));
-  bdrc_prof_end(ctx, s);
+  // (the padding channels Ht..Cpad-1 of lines_bf16 are zeroed by the threshold kernel's sink, which covers every
+  //  column of every line)
   adaptive::SrcGrayBatch src{canvas, Ht, Wt};
   adaptive::SinkOcrLines sink{reinterpret_cast<bf16*>(lines_bf16), lines_f32, Ht, Wt, Cpad};
   bdrc_prof_begin(ctx, "a-7.adaptive_threshold", 0, s);

@@ -405,3 +405,30 @@ def test_image_dataset_and_page_loader(tmp_path):
     (tmp_path / "d.png").write_bytes(b"broken")
     with pytest.raises(OSError):
         list(PageLoader(str(tmp_path)))
+
+
+def test_bench_deadline_fires_and_cancels():
+    """bench.py arms a deadline around the multi-rank C5 block: past it the callback runs (rank 0 prints the
+    headline line) and the process leaves with exit code 0; cancel() disarms it; seconds=None arms nothing."""
+    import importlib.util
+    import os
+    import threading
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    fired, left = [], threading.Event()
+    bench.Deadline(0.05, lambda: fired.append("line"), _exit=lambda code: (fired.append(code), left.set()))
+    assert left.wait(5.0) and fired == ["line", 0]
+    fired.clear()
+    boom = bench.Deadline(0.05, lambda: 1 / 0, _exit=lambda code: (fired.append(code), left.set()))
+    left.clear()
+    assert left.wait(5.0) and fired == [0]                 # a failing callback still ends the process with 0
+    del boom
+    fired.clear()
+    d = bench.Deadline(0.2, lambda: fired.append("late"), _exit=lambda code: fired.append(code))
+    d.cancel()
+    time_ = __import__("time")
+    time_.sleep(0.4)
+    assert fired == []
+    bench.Deadline(None).cancel()

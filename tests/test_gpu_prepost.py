@@ -107,6 +107,26 @@ def test_ocr_prepare_lines_bit_exact(engine, pre_pad):
         assert not bf[i, :, 80:].any()
 
 
+@pytest.mark.parametrize("Ht,Wt", [(80, 2000), (76, 1000), (33, 130)])
+def test_ocr_prepare_lines_fills_a_poisoned_buffer(engine, Ht, Wt):
+    """The threshold kernel's sink writes EVERY element of the [L][Wt][128] network input -- rows of the image and
+    the zero padding channels (16-byte and scalar paths, canvas heights that are not a multiple of the 32-row block)
+    -- so a caller-provided slice of a larger batch needs no memset."""
+    import torch
+
+    crops = synth.line_crops(77, 5) + [synth.line_crop(3, 30, 400), synth.line_crop(4, 160, 3000)]
+    dev, hw, off = engine.pack_crops(crops)
+    out = torch.full((len(crops), Wt, 128), 7.0, dtype=torch.bfloat16, device=engine.device)
+    lines, f32 = engine.ocr_prepare_lines(dev, hw, off, len(crops), Ht, Wt, False, want_f32=True, out=out)
+    bf = lines.float().cpu().numpy()
+    got = f32.cpu().numpy()
+    for i, c in enumerate(crops):
+        ref = ho.prepare_ocr_line(c, Ht, Wt, pre_pad=False, closed_form=False)[0]
+        assert int((got[i] != ref).sum()) == 0, f"line {i} shape {c.shape}"
+        assert np.array_equal(bf[i, :, :Ht], ref.T)
+        assert not bf[i, :, Ht:].any()
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("L,V,T", [(1, 77, 500), (7, 77, 500), (3, 5, 33), (2, 200, 1000), (4, 77, 1),
                                    (450, 77, 500), (5, 76, 512), (3, 8, 130), (2, 77, 36)])
