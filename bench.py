@@ -604,6 +604,9 @@ def bench_c5(eng, rank: int, world: int, sampler, steps: int = 3, pages_per_rank
 
     sharding.run_sharded(n_pages, load, process, chunk=96)      # warm-up at full size: pinned buffers, worker processes
     barrier()
+    if rank == C5_FAULT_RANK:
+        pipe.close()
+        raise RuntimeError("injected C5 failure (BDRC_BENCH_C5_FAULT)")
     cpu0, w0 = _proc_tree_cpu_seconds(), time.time()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -817,7 +820,20 @@ def bench_c4(eng, steps: int = 2):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
-C5_DEADLINE_S = 240
+C5_DEADLINE_S = int(os.environ.get("BDRC_C5_DEADLINE_S", "240"))
+C5_FAULT_RANK = int(os.environ.get("BDRC_BENCH_C5_FAULT", "-1"))      # test hook: this rank fails inside C5 (tools/c5_fault.sh)
+
+
+def _kill_children():
+    """os._exit skips multiprocessing's atexit hook: end the geometry workers by hand so that no orphan keeps the
+    job's stdout / stderr pipes open."""
+    try:
+        import multiprocessing as mp
+
+        for c in mp.active_children():
+            c.kill()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 class Deadline:
@@ -838,6 +854,7 @@ class Deadline:
             finally:
                 sys.stdout.flush()
                 sys.stderr.flush()
+                _kill_children()
                 _exit(0)
 
         self._timer = threading.Timer(seconds, fire)
@@ -984,6 +1001,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         if world > 1:
             if c5_failed:
+                _kill_children()
                 os._exit(0)          # peers may be stuck in a collective of C5: no orderly shutdown to wait for
             dist.destroy_process_group()
         return
@@ -991,6 +1009,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         if c5_failed:
             sys.stdout.flush()
+            _kill_children()
             os._exit(0)
         dist.destroy_process_group()
 

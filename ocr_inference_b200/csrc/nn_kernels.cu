@@ -617,7 +617,7 @@ constexpr int SE_CH = 8;
 __global__ void __launch_bounds__(256)
 se_partial_gate_kernel(const bf16* __restrict__ d, int T, int C, float* __restrict__ partial, int* __restrict__ tickets,
                        const float* __restrict__ W1, const float* __restrict__ b1, int Cmid, const float* __restrict__ W2,
-                       const float* __restrict__ b2, float* __restrict__ gate) {
+                       const float* __restrict__ b2, float* __restrict__ gate, int direct) {
   extern __shared__ float se_sm[];                 // [slices][C] partial sums, later the MLP's staging
   __shared__ int last;
   const int q = blockIdx.x % SE_CH, l = blockIdx.x / SE_CH;
@@ -673,6 +673,50 @@ se_partial_gate_kernel(const bf16* __restrict__ d, int T, int C, float* __restri
 #pragma unroll
     for (int k = 0; k < SE_CH; ++k) sum += __ldcg(partial + ((size_t)l * SE_CH + k) * C + c);
     m[c] = sum / (float)T;
+  }
+  if (direct) {
+    // The MLP straight from the weights in L2 (same summation order as the staged form below, so the same bits):
+    // a warp per hidden unit reads its W1 row in 128-byte pieces, a thread per channel its own W2 row as float4s,
+    // every load of a round in flight together -- two L2 round trips instead of a 64 KB staging pass.
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < Cmid; o += nw) {
+      const float* wr = W1 + (size_t)o * C;
+      float sum = 0.f;
+      if (C == 256) {
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = __ldg(wr + lane + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum = fmaf(w[k], m[lane + 32 * k], sum);
+      } else {
+        for (int c = lane; c < C; c += 32) sum = fmaf(__ldg(wr + c), m[c], sum);
+      }
+      for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+      if (lane == 0) z[o] = fmaxf(sum + b1[o], 0.f);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < C; o += blockDim.x) {
+      const float* wr = W2 + (size_t)o * Cmid;
+      float sum = b2[o];
+      if (Cmid == 32) {
+        float4 w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(wr) + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          sum = fmaf(w[k].x, z[4 * k], sum);
+          sum = fmaf(w[k].y, z[4 * k + 1], sum);
+          sum = fmaf(w[k].z, z[4 * k + 2], sum);
+          sum = fmaf(w[k].w, z[4 * k + 3], sum);
+        }
+      } else {
+        for (int c = 0; c < Cmid; ++c) sum = fmaf(__ldg(wr + c), z[c], sum);
+      }
+      gate[(size_t)l * C + o] = 1.f / (1.f + expf(-sum));
+    }
+    if (threadIdx.x == 0) tickets[l] = 0;
+    return;
   }
   for (int i = threadIdx.x; i < Cmid * C / 4; i += blockDim.x)
     reinterpret_cast<float4*>(w1s)[i] = __ldg(reinterpret_cast<const float4*>(W1) + i);
@@ -865,7 +909,10 @@ int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, i
     BDRC_CUDA(ctx, cudaFuncSetAttribute(se_partial_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  se_partial_gate_kernel<<<L * SE_CH, 256, smem, s>>>(d, T, C, partial, tickets, W1, b1, Cmid, W2, b2, gate);
+  // BDRC_SE_STAGED=1 keeps the round-2 form (weights staged in shared memory) for A/B timing; same results
+  static const int direct = []() { const char* e = getenv("BDRC_SE_STAGED"); return (e && e[0] == '1') ? 0 : 1; }();
+  se_partial_gate_kernel<<<L * SE_CH, 256, smem, s>>>(d, T, C, partial, tickets, W1, b1, Cmid, W2, b2, gate,
+                                                      direct && (reinterpret_cast<uintptr_t>(W2) & 15) == 0 ? 1 : 0);
   BDRC_CHECK_LAUNCH(ctx);
   const size_t total8 = (size_t)L * T * (C / 8);
   se_apply_kernel<<<(unsigned)((total8 + 511) / 512), 256, 0, s>>>(res, res_ld, d, gate, T, C, total8, out, out_ld);

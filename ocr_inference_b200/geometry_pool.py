@@ -32,8 +32,16 @@ def _worker(tasks, results):
         results.put(("init_error", traceback.format_exc()))
         return
     shms: dict[str, shared_memory.SharedMemory] = {}
+    import queue
+
+    parent = os.getppid()
     while True:
-        job = tasks.get()
+        try:
+            job = tasks.get(timeout=2.0)
+        except queue.Empty:
+            if os.getppid() != parent:      # the owning process is gone without close() (killed, os._exit): no orphans
+                break
+            continue
         if job is None:
             break
         ticket, name, shape, merge_lines, census = job

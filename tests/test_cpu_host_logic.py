@@ -432,3 +432,33 @@ def test_bench_deadline_fires_and_cancels():
     time_.sleep(0.4)
     assert fired == []
     bench.Deadline(None).cancel()
+
+
+def test_geometry_workers_leave_when_their_owner_is_gone():
+    """A GeometryPool worker must not outlive an owner that went away without close() (os._exit, SIGKILL): an
+    orphan would keep the job's stdout / stderr pipes open."""
+    import subprocess
+    import sys
+    import time
+
+    code = ("import os, sys\n"
+            "from ocr_inference_b200.geometry_pool import GeometryPool\n"
+            "if __name__ == '__main__':\n"
+            "    p = GeometryPool(1)\n"
+            "    print(p._procs[0].pid, flush=True)\n"
+            "    os._exit(0)\n")
+    root = os.path.join(os.path.dirname(__file__), "..")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    pid = int(r.stdout.strip().splitlines()[-1])
+
+    def alive():
+        try:
+            with open(f"/proc/{pid}/status") as f:
+                return "State:\tZ" not in f.read()
+        except OSError:
+            return False
+
+    t0 = time.time()
+    while alive() and time.time() - t0 < 30:
+        time.sleep(0.5)
+    assert not alive(), "the orphaned geometry worker is still running"
