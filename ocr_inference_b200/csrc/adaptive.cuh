@@ -32,8 +32,11 @@ constexpr int GSTRIDE = 92;            // padded row stride of the staged gray b
 constexpr int GOFF = 4;                // staged column c lives at g[row * GSTRIDE + GOFF + c]: a quad store that hangs over the
                                        // 82 columns by up to 3 on either side lands in padding, no predicates
 constexpr int RING = 128;              // row-pass ring (rows), power of two
+constexpr int WIN = 2 * KR + 4;        // ring rows under the four output rows of a column-pass thread
+constexpr int RING_PHYS = RING + WIN;  // rows of the buffer: slots 0 .. WIN-1 are kept twice (at s and at s + RING), so a
+                                       // window that starts anywhere in the ring is WIN consecutive rows of the buffer
 constexpr int THREADS = 256;
-constexpr size_t SMEM_BYTES = (size_t)(RB * GSTRIDE + RING * SW) * sizeof(float) + RING * SW + RB * SW;
+constexpr size_t SMEM_BYTES = (size_t)(RB * GSTRIDE + RING_PHYS * SW) * sizeof(float) + RING * SW + RB * SW;
 
 __constant__ float c_gauss[KS];
 
@@ -214,8 +217,8 @@ __global__ void __launch_bounds__(THREADS, 3)
 adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int strips_x) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* g = reinterpret_cast<float*>(smem_raw);                 // [RB][GSTRIDE]  staged gray block
-  float* ring = g + RB * GSTRIDE;                                // [RING][SW]     row-pass results
-  uint8_t* gc = reinterpret_cast<uint8_t*>(ring + RING * SW);    // [RING][SW]     gray of the strip itself
+  float* ring = g + RB * GSTRIDE;                                // [RING_PHYS][SW] row-pass results
+  uint8_t* gc = reinterpret_cast<uint8_t*>(ring + RING_PHYS * SW);   // [RING][SW]  gray of the strip itself
   uint8_t* res = gc + RING * SW;                                 // [RB][SW]
 
   const int sx = blockIdx.x % strips_x;
@@ -223,6 +226,12 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
   const int x0 = sx * SW;
   const typename Src::View sv = src.view(img);
   const int n_blocks = (IH + RB - 1) / RB;
+  // Where the row-pass result of image row y lives.  Large images: ring slot y % RING (+ the copy at slot + RING for
+  // slots < WIN), windows clamped at the image border take the slow path of the column pass.  Small images (an
+  // 80-row OCR canvas: four of its five column-pass warps sit at a border): row y at buffer row y + KR, the KR rows
+  // above / below it filled with copies of row 0 / row IH-1 when those are computed -- the replicate border
+  // materialised, every window WIN consecutive buffer rows at immediate offsets.
+  const bool small = IH + 2 * KR <= RING_PHYS;
 
   // Staging works on quads: tile columns x0 - 28 + 4q .. + 3 (a 4-aligned superset of the 82 staged columns),
   // staged column c = 4q - 3 + j; quads 7 .. 14 are the strip itself.  The raw words of block b + 1 are loaded
@@ -318,25 +327,36 @@ adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int st
         }
         w0 = n.x; w1 = n.y; w2 = n.z; w3 = n.w;
       }
-      *reinterpret_cast<float4*>(ring + ((RB * b + r) & (RING - 1)) * SW + c) = make_float4(a0, a1, a2, a3);
+      const float4 acc = make_float4(a0, a1, a2, a3);
+      const int y = RB * b + r;
+      if (small) {
+        *reinterpret_cast<float4*>(ring + (y + KR) * SW + c) = acc;
+        if (y == 0) {
+#pragma unroll
+          for (int k = 0; k < KR; ++k) *reinterpret_cast<float4*>(ring + k * SW + c) = acc;
+        }
+        if (y == IH - 1) {
+#pragma unroll
+          for (int k = 1; k <= KR; ++k) *reinterpret_cast<float4*>(ring + (y + KR + k) * SW + c) = acc;
+        }
+      } else {
+        const int sl = y & (RING - 1);
+        *reinterpret_cast<float4*>(ring + sl * SW + c) = acc;
+        if (sl < WIN) *reinterpret_cast<float4*>(ring + (sl + RING) * SW + c) = acc;
+      }
     }
 
     // ---- column pass + threshold of block b - 2 (its 51-row window was complete one barrier ago) ----
     const int ob = b - 2;
     if (ob >= 0 && ob < n_blocks && RB * ob + (int)(threadIdx.x / SW) * 4 < IH) {   // warp-uniform; the sinks never read res rows >= IH
       const int c = threadIdx.x % SW, r4 = RB * ob + (threadIdx.x / SW) * 4;   // output rows r4 .. r4+3
-      float v[2 * KR + 4];
-      if (r4 - KR >= 0 && r4 + 3 + KR < IH) {
-        const int s0 = (r4 - KR) & (RING - 1);     // warp-uniform (one r4 per warp)
-        if (s0 + 2 * KR + 4 <= RING) {             // window does not wrap: immediate offsets, no index math
-          const float* rp = ring + s0 * SW + c;
+      float v[WIN];
+      if (small || (r4 - KR >= 0 && r4 + 3 + KR < IH)) {
+        // warp-uniform (one r4 per warp); WIN consecutive buffer rows: immediate offsets, no index math
+        const float* rp = ring + (small ? r4 : ((r4 - KR) & (RING - 1))) * SW + c;
 #pragma unroll
-          for (int i = 0; i < 2 * KR + 4; ++i) v[i] = rp[i * SW];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[((s0 + i) & (RING - 1)) * SW + c];
-        }
-      } else {   // replicate border at the top / bottom of the image
+        for (int i = 0; i < WIN; ++i) v[i] = rp[i * SW];
+      } else {   // replicate border at the top / bottom of a large image
 #pragma unroll
         for (int i = 0; i < 2 * KR + 4; ++i) v[i] = ring[(min(max(r4 - KR + i, 0), IH - 1) & (RING - 1)) * SW + c];
       }

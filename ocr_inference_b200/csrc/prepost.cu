@@ -1017,7 +1017,8 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
                            size_t workspace_bytes, void* stream) {
   if (!ctx) return BDRC_ERR_ARG;
   if (L == 0) return 0;
-  BDRC_REQUIRE(ctx, crops && crop_hw && crop_off && L > 0 && Ht > 0 && Wt > 0 && Cpad >= Ht,
+  BDRC_REQUIRE(ctx, crops && crop_hw && crop_off && L > 0 && Ht > 0 && Wt > 0 && (Cpad >= Ht || !lines_bf16) &&
+                        (lines_bf16 || lines_f32),
                "ocr_prepare_lines: bad arguments");
   BDRC_REQUIRE(ctx, workspace && workspace_bytes >= bdrc_ocr_prepare_workspace_bytes(L, Ht, Wt),
                "ocr_prepare_lines: workspace too small");

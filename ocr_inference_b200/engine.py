@@ -530,8 +530,18 @@ class Engine:
         return dev, meta_dev[:8 * n].view(torch.int32).view(n, 2), meta_dev[8 * n:16 * n].view(torch.int64)
 
     def ocr_prepare_lines(self, crops_dev, hw_dev, off_dev, L: int, Ht: int, Wt: int, pre_pad: bool,
-                          want_f32: bool = False, out: torch.Tensor | None = None):
-        """`out` (optional): a contiguous bf16 [L, Wt, OCR_CPAD] slice of a larger line batch to fill."""
+                          want_f32: bool = False, out: torch.Tensor | None = None, want_bf16: bool = True):
+        """`out` (optional): a contiguous bf16 [L, Wt, OCR_CPAD] slice of a larger line batch to fill.
+        want_bf16=False (with want_f32): only the reference-layout fp32 [L, Ht, Wt] lines, any Ht."""
+        if not want_bf16:
+            if not want_f32 or out is not None:
+                raise ValueError("ocr_prepare_lines: want_bf16=False needs want_f32=True and no out")
+            f32 = torch.empty((L, Ht, Wt), dtype=torch.float32, device=self.device)
+            ws = self._workspace("ocr_prep", int(self.lib.bdrc_ocr_prepare_workspace_bytes(L, Ht, Wt)))
+            self._check(self.lib.bdrc_ocr_prepare_lines(
+                self.ctx.h, crops_dev.data_ptr(), hw_dev.data_ptr(), off_dev.data_ptr(), L, Ht, Wt, int(pre_pad),
+                OCR_CPAD, None, f32.data_ptr(), ws.data_ptr(), ws.numel(), self.stream), "ocr_prepare_lines")
+            return None, f32
         if out is not None and (tuple(out.shape) != (L, Wt, OCR_CPAD) or out.dtype != torch.bfloat16
                                 or not out.is_contiguous()):
             raise ValueError("ocr_prepare_lines: out must be a contiguous bf16 [L, Wt, OCR_CPAD] tensor")

@@ -127,6 +127,20 @@ def test_ocr_prepare_lines_fills_a_poisoned_buffer(engine, Ht, Wt):
         assert not bf[i, :, Ht:].any()
 
 
+@pytest.mark.parametrize("Ht,Wt", [(1, 64), (25, 300), (128, 500), (132, 420), (133, 420), (200, 333), (300, 96)])
+def test_ocr_prepare_lines_any_canvas_height(engine, Ht, Wt):
+    """The threshold kernel keeps canvases of up to 132 rows whole in its row ring (replicate border materialised)
+    and streams taller ones through the ring with its first rows kept twice: both sides of that switch, ring wrap
+    included, against cv2 (fp32 reference-layout output only: the network layout holds 128 rows at most)."""
+    crops = synth.line_crops(55, 3) + [synth.line_crop(3, 30, 400), synth.line_crop(4, 160, 3000)]
+    dev, hw, off = engine.pack_crops(crops)
+    _, f32 = engine.ocr_prepare_lines(dev, hw, off, len(crops), Ht, Wt, False, want_f32=True, want_bf16=False)
+    got = f32.cpu().numpy()
+    for i, c in enumerate(crops):
+        ref = ho.prepare_ocr_line(c, Ht, Wt, pre_pad=False, closed_form=False)[0]
+        assert int((got[i] != ref).sum()) == 0, f"line {i} shape {c.shape}"
+
+
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("L,V,T", [(1, 77, 500), (7, 77, 500), (3, 5, 33), (2, 200, 1000), (4, 77, 1),
                                    (450, 77, 500), (5, 76, 512), (3, 8, 130), (2, 77, 36)])
