@@ -216,6 +216,9 @@ template <class Src, class Sink>
 __global__ void __launch_bounds__(THREADS, 3)
 adaptive_threshold_kernel(const Src src, const Sink sink, int IH, int IW, int strips_x) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  // programmatic dependent launch (launch(..., pdl = true): the OCR line chain); no-ops in a plain launch
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float* g = reinterpret_cast<float*>(smem_raw);                 // [RB][GSTRIDE]  staged gray block
   float* ring = g + RB * GSTRIDE;                                // [RING_PHYS][SW] row-pass results
   uint8_t* gc = reinterpret_cast<uint8_t*>(ring + RING_PHYS * SW);   // [RING][SW]  gray of the strip itself
@@ -405,7 +408,7 @@ static cudaError_t upload_gauss() {
 
 template <class Src, class Sink>
 int launch(bdrc_ctx* ctx, const Src& src, const Sink& sink, int n_img, int IH, int IW,
-           cudaStream_t s) {
+           cudaStream_t s, bool pdl = false) {
   BDRC_CUDA(ctx, upload_gauss());
   auto kern = adaptive_threshold_kernel<Src, Sink>;
   static bool attr_set = false;   // one flag per <Src, Sink> instantiation
@@ -416,7 +419,17 @@ int launch(bdrc_ctx* ctx, const Src& src, const Sink& sink, int n_img, int IH, i
   const int rx = ceil_div(IW, SW);
   const long long blocks = (long long)rx * n_img;
   if (blocks == 0 || IH <= 0) return 0;
-  kern<<<(unsigned)blocks, THREADS, SMEM_BYTES, s>>>(src, sink, IH, IW, rx);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, src, sink, IH, IW, rx));
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

@@ -296,8 +296,18 @@ struct Arena {
 
 // Tiles per forward chunk.  Multiples of 37 give every ResNet stage a whole number of waves on 148 SMs / 74 CTA
 // pairs (a 32x32 stage has 8 pixel tiles per image), and larger chunks amortise the ~57 launches of a forward:
-// measured 91 us per tile at 48 tiles, 80 at 74, 77 at 148 (7.4 GB of activations, mid layers spill the L2).
-constexpr int SEG_CHUNK = 148;
+// measured (round 1 kernels) 91 us per tile at 48 tiles, 80 at 74, 77 at 148; round 2, the 384 tiles of a C2 step on one
+// box: 25.92 / 26.05 ms in chunks of 148 (148 + 148 + 88), 25.79 at 192, 25.60 / 25.22 in ONE chunk of 384 (a third of
+// the launches, one partial last wave per layer instead of three; 19 GB of activations instead of 7.4).
+constexpr int SEG_CHUNK_DEFAULT = 384;
+static int seg_chunk() {   // BDRC_SEG_CHUNK overrides (sweeps: tools/seg_chunk_sweep.sh); read once
+  static const int v = [] {
+    const char* e = getenv("BDRC_SEG_CHUNK");
+    const int x = e ? atoi(e) : 0;
+    return (x >= 1 && x <= 1024) ? x : SEG_CHUNK_DEFAULT;
+  }();
+  return v;
+}
 constexpr int SEG_P = 512;
 
 size_t seg_bytes_per_tile(int C) {
@@ -484,6 +494,7 @@ int seg_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const void* tiles, int n_tile
   BDRC_REQUIRE(ctx, ws && ws_bytes >= bdrc_seg_workspace_bytes(m, n_tiles), "seg_forward: workspace too small");
   const int C = m->n_out;
   const size_t tile_in = (size_t)SEG_P * SEG_P * (cin == 1 ? 1 : 3 * sizeof(float));
+  const int SEG_CHUNK = seg_chunk();
   for (int t0 = 0; t0 < n_tiles; t0 += SEG_CHUNK) {
     const int n = n_tiles - t0 < SEG_CHUNK ? n_tiles - t0 : SEG_CHUNK;
     BDRC_TRY(seg_forward_chunk(
@@ -573,7 +584,7 @@ int ocr_forward_impl(bdrc_ctx* ctx, bdrc_model* m, const bf16* lines, int L, int
     const FcWeights& f1 = m->fc[p + ".se_fc1"];
     const FcWeights& f2 = m->fc[p + ".se_fc2"];
     bdrc_prof_begin(ctx, "ocr.se", 0, s);
-    BDRC_TRY(se_fused_launch(ctx, P, 512, da, L, T, 256, f1.w, f1.b, 32, f2.w, f2.b, P + 256, 512, gate, s));
+    BDRC_TRY(se_fused_launch(ctx, P, 512, da, L, T, 256, f1.w, f1.b, 32, f2.w, f2.b, P + 256, 512, gate, /*pdl=*/1, s));
     bdrc_prof_end(ctx, s);
     prev = P; prev_ld = 512; data_off = 256; cin = 256;
   }
@@ -636,7 +647,7 @@ void bdrc_free_model(bdrc_model* m) {
 
 size_t bdrc_seg_workspace_bytes(bdrc_model* m, int n_tiles) {
   if (!m || n_tiles <= 0) return 0;
-  const int n = n_tiles < SEG_CHUNK ? n_tiles : SEG_CHUNK;
+  const int n = n_tiles < seg_chunk() ? n_tiles : seg_chunk();
   return seg_bytes_per_tile(m->n_out) * (size_t)n;
 }
 

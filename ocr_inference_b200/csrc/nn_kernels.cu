@@ -620,6 +620,10 @@ se_partial_gate_kernel(const bf16* __restrict__ d, int T, int C, float* __restri
                        const float* __restrict__ b2, float* __restrict__ gate, int direct) {
   extern __shared__ float se_sm[];                 // [slices][C] partial sums, later the MLP's staging
   __shared__ int last;
+  // programmatic dependent launch (se_fused_launch, pdl = 1): the next kernel of the chain may be scheduled as soon as
+  // every CTA of this one is resident; nothing is read or written before the previous kernel has completed
+  tcptx::griddep_launch();
+  tcptx::griddep_wait();
   const int q = blockIdx.x % SE_CH, l = blockIdx.x / SE_CH;
   const int Tq = (T + SE_CH - 1) / SE_CH;
   const int t0 = q * Tq, t1 = min(T, t0 + Tq);
@@ -742,6 +746,8 @@ __global__ void __launch_bounds__(256)
 se_apply_kernel(const bf16* __restrict__ res, int res_ld, const bf16* __restrict__ d, const float* __restrict__ gate, int T,
                 int C, size_t total8, bf16* __restrict__ out, int out_ld) {
   const int C8 = C / 8;
+  tcptx::griddep_launch();
+  tcptx::griddep_wait();
   // two 16-byte items per thread, both loads in flight before either is used
   const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   uint4 rv[2], dv4[2];
@@ -890,7 +896,7 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
 
 int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, int L, int T, int C, const float* W1,
                     const float* b1, int Cmid, const float* W2, const float* b2, bf16* out, int out_ld, float* scratch,
-                    cudaStream_t s) {
+                    int pdl, cudaStream_t s) {
   BDRC_REQUIRE(ctx, C % 8 == 0 && C / 8 <= 256 && res_ld % 8 == 0 && out_ld % 8 == 0 && Cmid >= 1 && scratch &&
                         (Cmid * C) % 4 == 0,
                "se_fused: C, res_ld, out_ld must be multiples of 8");
@@ -911,11 +917,22 @@ int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, i
   }
   // BDRC_SE_STAGED=1 keeps the round-2 form (weights staged in shared memory) for A/B timing; same results
   static const int direct = []() { const char* e = getenv("BDRC_SE_STAGED"); return (e && e[0] == '1') ? 0 : 1; }();
-  se_partial_gate_kernel<<<L * SE_CH, 256, smem, s>>>(d, T, C, partial, tickets, W1, b1, Cmid, W2, b2, gate,
-                                                      direct && (reinterpret_cast<uintptr_t>(W2) & 15) == 0 ? 1 : 0);
-  BDRC_CHECK_LAUNCH(ctx);
+  const int dflag = direct && (reinterpret_cast<uintptr_t>(W2) & 15) == 0 ? 1 : 0;
   const size_t total8 = (size_t)L * T * (C / 8);
-  se_apply_kernel<<<(unsigned)((total8 + 511) / 512), 256, 0, s>>>(res, res_ld, d, gate, T, C, total8, out, out_ld);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.gridDim = dim3((unsigned)(L * SE_CH));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, se_partial_gate_kernel, d, T, C, partial, tickets, W1, b1, Cmid, W2, b2, gate, dflag));
+  cfg.gridDim = dim3((unsigned)((total8 + 511) / 512));
+  cfg.dynamicSmemBytes = 0;
+  BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, se_apply_kernel, res, res_ld, d, (const float*)gate, T, C, total8, out, out_ld));
   BDRC_CHECK_LAUNCH(ctx);
   return 0;
 }

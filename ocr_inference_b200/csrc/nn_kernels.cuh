@@ -41,7 +41,7 @@ int aspp_pool_bias_launch(bdrc_ctx* ctx, const bf16* x, int N, int HW, int Cin, 
 // counters se_fused_reset zeroes once per forward.
 int se_fused_launch(bdrc_ctx* ctx, const bf16* res, int res_ld, const bf16* d, int L, int T, int C, const float* W1,
                     const float* b1, int Cmid, const float* W2, const float* b2, bf16* out, int out_ld, float* scratch,
-                    cudaStream_t s);
+                    int pdl, cudaStream_t s);
 size_t se_fused_scratch_floats(int L, int C);
 int se_fused_reset(bdrc_ctx* ctx, float* scratch, int L, int C, cudaStream_t s);
 int se_fused_chunks(void);

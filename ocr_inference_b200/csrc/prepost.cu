@@ -477,6 +477,8 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
   __shared__ int r_i0[CANVAS_ROWS], r_i1[CANVAS_ROWS];
   __shared__ float r_w0[CANVAS_ROWS], r_w1[CANVAS_ROWS];
   __shared__ double g_scale_x;
+  tcptx::griddep_launch();   // programmatic dependent launch inside the OCR line chain (bdrc_ocr_prepare_lines)
+  tcptx::griddep_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y0 = blockIdx.y * CANVAS_ROWS;
   const int l = blockIdx.z;
@@ -508,9 +510,7 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
   if (x >= Wt) return;
   const int rh = g_i[0], rw = g_i[1], top = g_i[2], left = g_i[3];
   const bool live = h > 0 && w0 > 0;
-  if (live && (rh <= 0 || rw <= 0)) {
-    if (x == 0 && y0 == 0) status[l] = 1;     // cv2.resize would raise on an empty target
-  }
+  if (x == 0 && y0 == 0) status[l] = (live && (rh <= 0 || rw <= 0)) ? 1 : 0;   // 1: cv2.resize would raise on an empty target
   const bool in_x = live && rh > 0 && rw > 0 && x >= left && x < left + rw;
   const int dx = x - left;
   const uint8_t* base = crops + off[l];
@@ -643,6 +643,8 @@ __global__ void __launch_bounds__(CTCB_WARPS * 32, 1)
 ctc_greedy_bulk_kernel(const float* __restrict__ logits, int L, int V, int T, int blank, int32_t* __restrict__ ids,
                        int32_t* __restrict__ lens, int* errflag) {
   extern __shared__ __align__(128) uint8_t ctcb_sm[];
+  tcptx::griddep_launch();   // launched as a programmatic dependent of the network's last kernel
+  tcptx::griddep_wait();
   const uint32_t slot_bytes = 128u * (uint32_t)V;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctcb_sm + (size_t)CTCB_GROUPS * slot_bytes);
   int* am = reinterpret_cast<int*>(bars + CTCB_GROUPS);         // [2][32 * CTCB_GROUPS] argmax per step
@@ -1025,10 +1027,21 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* canvas = reinterpret_cast<uint8_t*>(workspace);
   int* status = reinterpret_cast<int*>(canvas + align_up((size_t)L * Ht * Wt, 256));
-  BDRC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)L * sizeof(int), s));
-  dim3 grid(ceil_div(Wt, 128), ceil_div(Ht, CANVAS_ROWS), L);
+  // status[l] is written by the canvas kernel for every line: no memset node between the kernels of consecutive calls.
+  // Programmatic dependent launch of canvas / threshold / CTC was measured (every kernel waits for its predecessor
+  // before it touches memory): 0.7062 against 0.7063 ms per 64-line step, no gain -- and early-resident CTAs of
+  // these kernels could hold SM slots the segmentation convs of the page pipeline want; left off (numAttrs = 0).
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(Wt, 128), ceil_div(Ht, CANVAS_ROWS), L);
+  cfg.blockDim = dim3(128);
+  cfg.stream = s;
+  cfg.attrs = pdl_attr;
+  cfg.numAttrs = 0;
   bdrc_prof_begin(ctx, "a-7.canvas", 0, s);
-  ocr_canvas_kernel<<<grid, 128, 0, s>>>(crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status);
+  BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, ocr_canvas_kernel, crops, crop_hw, crop_off, Ht, Wt, pre_pad, canvas, status));
   bdrc_prof_end(ctx, s);
   BDRC_CHECK_LAUNCH(ctx);
   // (the padding channels Ht..Cpad-1 of lines_bf16 are zeroed by the threshold kernel's sink, which covers every
@@ -1036,7 +1049,7 @@ int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* c
   adaptive::SrcGrayBatch src{canvas, Ht, Wt};
   adaptive::SinkOcrLines sink{reinterpret_cast<bf16*>(lines_bf16), lines_f32, Ht, Wt, Cpad};
   bdrc_prof_begin(ctx, "a-7.adaptive_threshold", 0, s);
-  const int rc = adaptive::launch(ctx, src, sink, L, Ht, Wt, s);
+  const int rc = adaptive::launch(ctx, src, sink, L, Ht, Wt, s, /*pdl=*/false);
   bdrc_prof_end(ctx, s);
   return rc;
 }
@@ -1059,8 +1072,17 @@ int bdrc_ctc_greedy(bdrc_ctx* ctx, const float* logits, int L, int V, int T, int
         attr_bytes = 220 * 1024;
       }
       bdrc_prof_begin(ctx, "a-9.ctc_greedy", 0, (cudaStream_t)stream);
-      ctc_greedy_bulk_kernel<<<L < ctx->sm_count ? L : ctx->sm_count, CTCB_WARPS * 32, bsmem, (cudaStream_t)stream>>>(
-          logits, L, V, T, blank, ids, lens, ctx->d_errflag);
+      cudaLaunchAttribute pdl_attr[1];
+      pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(L < ctx->sm_count ? L : ctx->sm_count));
+      cfg.blockDim = dim3(CTCB_WARPS * 32);
+      cfg.dynamicSmemBytes = bsmem;
+      cfg.stream = (cudaStream_t)stream;
+      cfg.attrs = pdl_attr;
+      cfg.numAttrs = 0;   // see bdrc_ocr_prepare_lines
+      BDRC_CUDA(ctx, cudaLaunchKernelEx(&cfg, ctc_greedy_bulk_kernel, logits, L, V, T, blank, ids, lens, ctx->d_errflag));
       bdrc_prof_end(ctx, (cudaStream_t)stream);
       BDRC_CHECK_LAUNCH(ctx);
       return 0;
