@@ -258,8 +258,10 @@ int bdrc_mask_components(bdrc_ctx* ctx, const uint8_t* mask, int H, int W, int32
  * Per line: optional h x h white pre-pad left/right, aspect-preserving cv2 resize to fit
  * Wt x Ht, centre pad with black, adaptive-threshold binarise, -> {-1,+1}.
  * Output `lines`: bf16 [L][Wt][Cpad] time-major (image rows are channels, zero-padded from
- * Ht to Cpad) -- the layout the recogniser's first conv consumes.  `lines_f32` (optional,
- * may be NULL) receives the reference layout fp32 [L][Ht][Wt] for parity checks. */
+ * Ht to Cpad; EVERY element is written, the buffer needs no initialisation) -- the layout the
+ * recogniser's first conv consumes.  `lines_f32` (optional, may be NULL) receives the
+ * reference layout fp32 [L][Ht][Wt] for parity checks.  `lines` may be NULL when `lines_f32`
+ * is given (then any Ht is accepted; with `lines`, Cpad >= Ht). */
 size_t bdrc_ocr_prepare_workspace_bytes(int L, int Ht, int Wt);
 int bdrc_ocr_prepare_lines(bdrc_ctx* ctx, const uint8_t* crops, const int32_t* crop_hw,
                            const int64_t* crop_off, int L, int Ht, int Wt, int pre_pad,
