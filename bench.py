@@ -424,6 +424,23 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
     prof_big = [(n_, t_, f_) for (n_, t_, f_) in eng.profile_results() if f_ > 0]
     eng.profile(False)
     big_tf = sum(x[2] for x in prof_big) / (sum(x[1] for x in prof_big) / 1e3) / 1e12 if prof_big else 0.0
+    # SURVEY 8(d) C1, fixed-size variant: 64 crops that already are 80 x 2000 (the resize of a-7 is the identity)
+    fx_dev, fx_hw, fx_off = eng.pack_crops(synthetic.line_crops(1001, C1_LINES, fixed=(80, 2000)))
+
+    def step_fixed():
+        lines, _ = eng.ocr_prepare_lines(fx_dev, fx_hw, fx_off, C1_LINES, 80, 2000, False)
+        return eng.ctc_greedy(eng.ocr_forward(ocr.ocr_session, lines), blank=blank)
+
+    for _ in range(3):
+        step_fixed()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        step_fixed()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_fixed = f0.elapsed_time(f1) / steps
     ids1, lens1 = step_device()
     valid = _t.arange(ids1.shape[1], device=ids1.device)[None, :] < lens1[:, None]     # ids beyond lens are unwritten
     same_big = bool(_t.equal(lens8[:C1_LINES], lens1) and _t.equal(ids8[:C1_LINES][valid], ids1[valid]))
@@ -441,6 +458,7 @@ def bench_c1(eng, steps: int, warmup: int, with_cpu: bool):
         "lines_per_sec": C1_LINES / (ms / 1e3), "ms_per_step": ms, "launches_per_step": int(launches),
         "timed": f"median of 3 loops of {steps} steps, CUDA events", "ms_per_step_loops": [round(x, 4) for x in loops],
         "lines_per_sec_batch_of_512": L8 / (ms_big / 1e3), "batch_of_512_equals_batch_of_64": same_big,
+        "lines_per_sec_fixed_size_80x2000": C1_LINES / (ms_fixed / 1e3), "ms_per_step_fixed_size_80x2000": ms_fixed,
         "e2e_lines_per_sec": C1_LINES / (e2e_ms / 1e3), "e2e_ms_per_step": e2e_ms,
         "e2e_api": "OCRInference.run_batch(host crops) -> list[str]",
         "h2d_bytes_per_step": int(sum(c.nbytes for c in crops)),
