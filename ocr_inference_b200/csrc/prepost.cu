@@ -475,7 +475,7 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
   // horizontal coefficients of a column are computed once per thread and reused for all rows of the block.
   __shared__ int g_i[4];                       // rh, rw, top, left
   __shared__ int r_i0[CANVAS_ROWS], r_i1[CANVAS_ROWS];
-  __shared__ float r_w0[CANVAS_ROWS], r_w1[CANVAS_ROWS];
+  __shared__ int r_b0[CANVAS_ROWS], r_b1[CANVAS_ROWS];      // 11-bit fixed-point vertical weights
   __shared__ double g_scale_x;
   tcptx::griddep_launch();   // programmatic dependent launch inside the OCR line chain (bdrc_ocr_prepare_lines)
   tcptx::griddep_wait();
@@ -500,7 +500,7 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
       }
     }
     r_i0[threadIdx.x] = cy.i0; r_i1[threadIdx.x] = cy.i1;
-    r_w0[threadIdx.x] = cy.w0; r_w1[threadIdx.x] = cy.w1;
+    r_b0[threadIdx.x] = fix11(cy.w0); r_b1[threadIdx.x] = fix11(cy.w1);
     if (threadIdx.x == 0) {
       g_i[0] = rh; g_i[1] = rw; g_i[2] = top; g_i[3] = left;
       g_scale_x = scale_x;
@@ -522,11 +522,29 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
   const int mode = !in_x ? 0 : (rh == h && rw == w) ? 1 : (w == 2 * rw && h == 2 * rh) ? 2 : 3;
   LinCoef cx = {0, 0, 1.f, 0.f};
   int a0 = 0, a1 = 0;
+  int o0 = 0, o1 = 0;            // byte offsets of the two source columns inside a crop row
+  bool p0 = false, p1 = false;   // the column lies in the white pre-pad patch
   if (mode == 3) {
     cx = lin_coef_scaled(dx, w, g_scale_x, false);
     a0 = fix11(cx.w0);
     a1 = fix11(cx.w1);
+    p0 = pre_pad && (cx.i0 < h || cx.i0 >= h + w0);
+    p1 = pre_pad && (cx.i1 < h || cx.i1 >= h + w0);
+    o0 = p0 ? 0 : (pre_pad ? cx.i0 - h : cx.i0) * 3;
+    o1 = p1 ? 0 : (pre_pad ? cx.i1 - h : cx.i1) * 3;
   }
+  // The 11-bit bilinear of cv2 is separable (resize_fix_sample): the horizontal pass of a source row, (s0 a0 + s1 a1)
+  // >> 4 per channel, is kept for the next canvas rows -- consecutive rows share source rows whenever the vertical
+  // scale is below ~2 (the row indices are block-uniform, so the reuse branches do not diverge).
+  auto hrow = [&](int sy, int* o3) {
+    const uint8_t* rowp = base + (size_t)sy * w0 * 3;
+    int s0[3], s1[3];
+    if (p0) { s0[0] = s0[1] = s0[2] = 255; } else { s0[0] = rowp[o0]; s0[1] = rowp[o0 + 1]; s0[2] = rowp[o0 + 2]; }
+    if (p1) { s1[0] = s1[1] = s1[2] = 255; } else { s1[0] = rowp[o1]; s1[1] = rowp[o1 + 1]; s1[2] = rowp[o1 + 2]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o3[k] = (s0[k] * a0 + s1[k] * a1) >> 4;
+  };
+  int ya = -1, yb = -1, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
 #pragma unroll 4
   for (int r = 0; r < CANVAS_ROWS; ++r) {
     const int y = y0 + r;
@@ -543,11 +561,22 @@ ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__
         fetch(2 * dy + 1, 2 * dx, c); fetch(2 * dy + 1, 2 * dx + 1, d);
         for (int k = 0; k < 3; ++k) px[k] = (a[k] + b[k] + c[k] + d[k] + 2) >> 2;
       } else {
-        const int b0 = fix11(r_w0[r]), b1 = fix11(r_w1[r]);
-        int s00[3], s01[3], s10[3], s11[3];
-        fetch(r_i0[r], cx.i0, s00); fetch(r_i0[r], cx.i1, s01);
-        fetch(r_i1[r], cx.i0, s10); fetch(r_i1[r], cx.i1, s11);
-        for (int k = 0; k < 3; ++k) px[k] = resize_fix_sample(s00[k], s01[k], s10[k], s11[k], a0, a1, b0, b1);
+        const int i0 = r_i0[r], i1 = r_i1[r], b0 = r_b0[r], b1 = r_b1[r];
+        int h0[3], h1[3];
+        if (i0 == yb) { h0[0] = vb[0]; h0[1] = vb[1]; h0[2] = vb[2]; }
+        else if (i0 == ya) { h0[0] = va[0]; h0[1] = va[1]; h0[2] = va[2]; }
+        else hrow(i0, h0);
+        if (i1 == i0) { h1[0] = h0[0]; h1[1] = h0[1]; h1[2] = h0[2]; }
+        else if (i1 == yb) { h1[0] = vb[0]; h1[1] = vb[1]; h1[2] = vb[2]; }
+        else if (i1 == ya) { h1[0] = va[0]; h1[1] = va[1]; h1[2] = va[2]; }
+        else hrow(i1, h1);
+        ya = i0; yb = i1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          va[k] = h0[k]; vb[k] = h1[k];
+          const int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;    // = resize_fix_sample
+          px[k] = min(max(v, 0), 255);
+        }
       }
       g = (uint8_t)((px[0] * 9798 + px[1] * 19235 + px[2] * 3735 + 16384) >> 15);
     }
