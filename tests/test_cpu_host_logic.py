@@ -462,3 +462,53 @@ def test_geometry_workers_leave_when_their_owner_is_gone():
     while alive() and time.time() - t0 < 30:
         time.sleep(0.5)
     assert not alive(), "the orphaned geometry worker is still running"
+
+
+def _check_bench_line(d, reference: bool):
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "pages_per_sec" and d["unit"] == "pages/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    if reference:
+        assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["value"] == d["value"]
+    else:
+        r = d["roofline"]
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in r, k
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert d["gpu_launches"] > 0 and d["simt_conv_launches"] == 0
+        assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+        assert d["e2e"]["h2d_bytes_per_step"] == 16 * 2048 * 3072 * 3 and d["e2e"]["d2h_bytes_per_step"] == 16 * 2048 * 3072
+        for k in ("a-1", "a-3", "a-5", "a-7", "a-9"):
+            assert 0 < d["roofline_stages"][k]["frac"] < 1, k
+        assert d["c1"]["roofline"]["bound"] == "tensor" and d["c3"]["cpu_baseline"]["kind"] == "port"
+        assert d["c5"]["collectives_on_data_path"] == 0 and d["c5"]["scaling"] == "weak"
+
+
+def test_bench_lines_keep_the_contract():
+    """The JSON line of `bench.py --impl reference` (run here: the oracle on the host cores) and the committed GPU
+    lines of the final build carry every key the bench contract names."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.join(os.path.dirname(__file__), "..")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1                                    # ONE JSON line on stdout
+    _check_bench_line(json.loads(lines[0]), reference=True)
+    with open(os.path.join(root, "profiles", "r02e_bench.json")) as f:
+        _check_bench_line(json.loads(f.read()), reference=False)
+    with open(os.path.join(root, "profiles", "r02e_bench_2gpu.json")) as f:
+        d2 = json.loads(f.read())
+    assert d2["n_gpus"] == 2 and d2["c5"]["n_gpus"] == 2 and d2["c5"]["pages_ok"] == d2["c5"]["pages_per_step"]
+    with open(os.path.join(root, "profiles", "r02e_bench_2gpu_c5_fault.json")) as f:
+        lines = [ln for ln in f.read().splitlines() if ln.strip()]
+    assert len(lines) == 1 and "error" in json.loads(lines[0])["c5"]
