@@ -464,7 +464,7 @@ float sigmoid_logit_threshold(float thr) {
 // a-7 OCR line preparation, stage 1: (pre-pad) + aspect-preserving cv2 resize + black padding
 // + gray, written as a u8 gray canvas [L][Ht][Wt]
 // ------------------------------------------------------------------------------------------
-constexpr int CANVAS_ROWS = 8;   // canvas rows per block
+constexpr int CANVAS_ROWS = 16;  // canvas rows per block
 __global__ void __launch_bounds__(128)
 ocr_canvas_kernel(const uint8_t* __restrict__ crops, const int32_t* __restrict__ hw,
                   const int64_t* __restrict__ off, int Ht, int Wt, int pre_pad,
