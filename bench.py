@@ -867,10 +867,16 @@ class Deadline:
 
     def __init__(self, seconds, on_timeout=None, _exit=os._exit):
         self._timer = None
+        self._lock = threading.Lock()
+        self._state = "armed"
         if seconds is None:
             return
 
         def fire():
+            with self._lock:
+                if self._state != "armed":
+                    return
+                self._state = "fired"
             try:
                 if on_timeout:
                     on_timeout()
@@ -887,8 +893,16 @@ class Deadline:
         self._timer.start()
 
     def cancel(self):
+        """Disarm.  If the deadline is already firing, the caller parks here until the process exit it ends with: the
+        guarded section must not go on to print a second line."""
+        with self._lock:
+            fired = self._state == "fired"
+            if not fired:
+                self._state = "cancelled"
         if self._timer is not None:
             self._timer.cancel()
+        if fired:
+            threading.Event().wait(600.0)
 
 
 def run_ours(args, rank, world, local_rank):
